@@ -1,0 +1,97 @@
+"""ORACLE (test infrastructure) — one G-LIS adversarial training iteration, restated.
+
+Follows ``g_lis/main.py:526-589`` of the reference (losses :308-312, optimizers
+:313-314, constant targets :508-510) as a function of explicit inputs, with the
+legacy semantics of SURVEY.md App. B:
+
+* ``zero_grad`` zero-fills existing gradients (B.4): a parameter that has received a
+  gradient once keeps decaying its RMSprop ``square_avg`` on every later step even when
+  the stochastic LIS depth skipped it; a parameter that never received one is skipped.
+* RMSprop (B.5): ``v = a v + (1-a) g^2 ; p -= lr g / (sqrt(v) + eps)``, a=.9, eps=1e-6.
+* BCE (B.6): modern form (log clamped at -100); equal to the 2017 kernel away from
+  saturation.  MSE (B.7): mean over all elements, times ``lambda_r**(i+1)``.
+* The separate ``.backward()`` calls of :579 and :586 add into the same ``.grad``
+  fields, which is what happens here too.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def rmsprop_update(params, state, lr, alpha=0.9, eps=1e-6):
+    """In-place legacy RMSprop over ``params`` (skips ``grad is None``); ``state`` maps
+    parameter -> square_avg.  g_lis/main.py:313-314 / torch.optim.RMSprop (no momentum)."""
+    with torch.no_grad():
+        for p in params:
+            if p.grad is None:
+                continue
+            v = state.get(p)
+            if v is None:
+                v = state[p] = torch.zeros_like(p)
+            g = p.grad
+            v.mul_(alpha).addcmul_(g, g, value=1.0 - alpha)
+            p.addcdiv_(g, v.sqrt().add_(eps), value=-lr)
+
+
+def _zero_fill(module):
+    for p in module.parameters():
+        if p.grad is not None:
+            p.grad.detach_()
+            p.grad.zero_()
+
+
+def glis_iteration(gen, dis, gen_state, dis_state, real, z_d, z_g, lr, lambda_r=0.9,
+                   depth_d=None, depth_g=None, alpha=0.9, eps=1e-6):
+    """One iteration: D on real, D on fake (G under no_grad), D update, G+LIS update.
+
+    ``depth_d`` / ``depth_g`` force the number of LIS modules run in the D-fake and G
+    forwards (``None`` = draw from ``gen.rng`` exactly as the reference does).
+    Returns a dict of python floats: d_real, d_fake, g, r (list), depth_d, depth_g.
+    """
+    B = real.size(0)
+    ones = torch.ones(B, 1, dtype=real.dtype)
+    zeros = torch.zeros(B, 1, dtype=real.dtype)
+
+    # ---- D step (:537-568)
+    for p in dis.parameters():
+        p.requires_grad_(True)
+    _zero_fill(dis)
+    loss_d_real = F.binary_cross_entropy(dis(real), ones)
+    loss_d_real.backward()
+    with torch.no_grad():
+        fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
+    loss_d_fake = F.binary_cross_entropy(dis(fake.detach()), zeros)
+    loss_d_fake.backward()
+    rmsprop_update(list(dis.parameters()), dis_state, lr, alpha, eps)
+
+    # ---- G step (:571-589)
+    for p in dis.parameters():
+        p.requires_grad_(False)
+    _zero_fill(gen)
+    fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
+    loss_g = F.binary_cross_entropy(dis(fake), ones)
+    loss_g.backward(retain_graph=(lambda_r > 0 and len(lis_g) > 0))
+    loss_r = []
+    if lambda_r > 0:
+        for i, u in enumerate(lis_g):
+            l = F.mse_loss(u, z_g) * (lambda_r ** (i + 1))
+            l.backward(retain_graph=(i + 1) < len(lis_g))
+            loss_r.append(l.item())
+    rmsprop_update(list(gen.parameters()), gen_state, lr, alpha, eps)
+    for p in dis.parameters():
+        p.requires_grad_(True)
+
+    return {"d_real": loss_d_real.item(), "d_fake": loss_d_fake.item(), "g": loss_g.item(),
+            "r": loss_r, "depth_d": len(lis_d), "depth_g": len(lis_g)}
+
+
+class GLISOracleTrainer:
+    """Holds G, D and both RMSprop states; ``step`` = :func:`glis_iteration`."""
+
+    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6):
+        self.gen, self.dis = gen, dis
+        self.lr, self.lambda_r, self.alpha, self.eps = lr, lambda_r, alpha, eps
+        self.gen_state, self.dis_state = {}, {}
+
+    def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
+        return glis_iteration(self.gen, self.dis, self.gen_state, self.dis_state, real, z_d, z_g,
+                              self.lr, self.lambda_r, depth_d, depth_g, self.alpha, self.eps)
