@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the G-LIS training step (BASELINE.json metric):
+
+    G-LIS train images/sec at 80x80, batch 64 per GPU (config 2: nfeature 64, 4 levels,
+    code 256, 1 LIS module, lr 2e-5, lambda_r 0.9), synthetic data, random-init weights.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full iteration of g_lis/main.py:526-589 (D-real, D-fake, D update, G+LIS
+update).  Prints ONE JSON line (rank 0).  `value` is measured with the inputs already in
+HBM; `e2e` drives the same step from pinned host buffers (H2D of the image batch and both
+noise batches every step, D2H of the three losses).  `roofline` describes the dominant
+kernel family timed live with CUDA events; `cpu_baseline` is the oracle's step on the
+host cores (N=1 only).  `--impl reference` times that CPU oracle alone (the reference's
+python-2.7 / PyTorch@065c5986 pin cannot be installed offline; torch 2.11 CPU is the
+nearest installable build — SURVEY.md §8c).
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gan-error-avoidance_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CFG = dict(W=80, H=80, B=64, nfeature=64, nlayer=4, code=256, n_lis=1, lr=2e-5, lambda_r=0.9)
+WORKLOAD = "G-LIS 1 LIS module, 80x80 CelebA-shaped synthetic, batch 64/GPU (BASELINE configs[1])"
+# F_step = 8 F_D + 4 F_G + 4 F_LIS = 250.9 GFLOP at config 2 (B = 64)
+GFLOP_PER_STEP = 250.9
+SEED = 1234
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                              ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_oracle_pair():
+    import oracle
+    torch.manual_seed(SEED)
+    g = oracle.GeneratorLearnedInputSpace(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight",
+                                          CFG["n_lis"], "fractional")
+    d = oracle.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", 0)
+    return g, d
+
+
+def time_cpu_oracle(steps, warmup):
+    """Seconds per step of the oracle's iteration on all host cores (bounded sample)."""
+    from oracle.step import GLISOracleTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g, d = build_oracle_pair()
+    tr = GLISOracleTrainer(g, d, lr=CFG["lr"], lambda_r=CFG["lambda_r"])
+    B = CFG["B"]
+    gen = torch.Generator().manual_seed(SEED + 1)
+    times = []
+    for i in range(warmup + steps):
+        real = torch.rand(B, 3, CFG["H"], CFG["W"], generator=gen)
+        zd, zg = torch.randn(B, CFG["code"], generator=gen), torch.randn(B, CFG["code"], generator=gen)
+        t0 = time.perf_counter()
+        tr.step(real, zd, zg, CFG["n_lis"], CFG["n_lis"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), cores
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sec, cores = time_cpu_oracle(args.steps, args.warmup)
+    ips = CFG["B"] / sec
+    sample = "%d full config-2 iterations (B=64) after %d warm-up, oracle port on torch %s CPU, %s" % (
+        args.steps, args.warmup, torch.__version__, cpu_model())
+    print(json.dumps({
+        "impl": "reference", "metric": "G-LIS train images/sec at 80x80 bs64/GPU", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": CFG["B"],
+                   "note": "python2.7/PyTorch@065c5986 pin not installable offline; nearest installable "
+                           "PyTorch CPU build used (oracle port of the reference step)"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, world, local):
+    import torch.distributed as dist
+    import common.model as pm
+    from glis_b200 import _lib, dp, ops
+    from glis_b200.trainer import GLISTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the product path needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    data_seed = dp.seed_everything(SEED, rank)
+    gen = pm.GeneratorLearnedInputSpace(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight",
+                                        CFG["n_lis"], "fractional").to(dev)
+    dis = pm.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", 0).to(dev)
+    sync = dp.GradSync(world) if world > 1 else None
+    tr = GLISTrainer(gen, dis, lr=CFG["lr"], lambda_r=CFG["lambda_r"], grad_sync=sync)
+    B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
+    depth = CFG["n_lis"]  # LIS depth forced to "all": fixed work per step (the stochastic schedule halves LIS work)
+
+    # ---- device-resident inputs (value): Philox on the device, a fresh batch every step
+    real = torch.empty(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+    zd, zg = torch.empty(B, code, device=dev), torch.empty(B, code, device=dev)
+    counter = [0]
+
+    def device_step():
+        off = counter[0] * (1 << 22)
+        counter[0] += 1
+        ops.uniform_(real, data_seed, off)
+        ops.randn_(zd, data_seed + 7, off)
+        ops.randn_(zg, data_seed + 13, off)
+        return tr.step(real, zd, zg, depth, depth)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    ms_total = timed_region(device_step, args.steps)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- per-kernel timing for the roofline (separate short pass; events serialise nothing)
+    _lib.timed.enabled = True
+    for _ in range(min(args.steps, 5)):
+        device_step()
+    torch.cuda.synchronize()
+    _lib.timed.enabled = False
+    per_kernel = _lib.timer_summary()
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses
+    h_real = torch.rand(B, 3, H, W).pin_memory()
+    h_zd, h_zg = torch.randn(B, code).pin_memory(), torch.randn(B, code).pin_memory()
+    h_loss = torch.empty(3).pin_memory()
+    d_real = torch.empty(B, 3, H, W, device=dev)
+
+    def e2e_step():
+        d_real.copy_(h_real, non_blocking=True)
+        zd.copy_(h_zd, non_blocking=True)
+        zg.copy_(h_zg, non_blocking=True)
+        out = tr.step(d_real, zd, zg, depth, depth)
+        h_loss.copy_(torch.stack([out["d_real"], out["d_fake"], out["g"]]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the losses every step
+
+    for _ in range(max(3, args.warmup // 2)):
+        e2e_step()
+    ms_e2e = timed_region(e2e_step, args.steps) / args.steps
+    e2e_value = B * world / (ms_e2e * 1e-3)
+    h2d = h_real.numel() * 4 + h_zd.numel() * 4 + h_zg.numel() * 4
+    d2h = h_loss.numel() * 4
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    # dominant kernel family = the conv/deconv/wgrad contraction launches
+    fam = {k: v for k, v in per_kernel.items() if "conv" in k}
+    roofline = None
+    if fam:
+        def flops(tag):
+            dims = dict(kv.split("=") for kv in tag.split()[1:])
+            return 2.0 * int(dims["M"]) * int(dims["N"]) * int(dims["K"])
+        top = max(fam.items(), key=lambda kv: kv[1][0] * kv[1][1])
+        tag, (cnt, ms) = top
+        ach = flops(tag) / (ms * 1e-3) / 1e12
+        tot_ms = sum(c * m for c, m in fam.values()) / min(args.steps, 5)
+        tot_fl = sum(flops(t) * c for t, (c, m) in fam.items()) / min(args.steps, 5)
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tf_sustained"], "traffic": None, "kernel": tag,
+                    "launches_per_step": cnt / min(args.steps, 5), "ms_per_launch": ms,
+                    "peak_source": peaks["source"] + " bf16 dense, sustained",
+                    "all_contractions": {"ms_per_step": tot_ms, "tflops": tot_fl / (tot_ms * 1e-3) / 1e12,
+                                         "share_of_step": tot_ms / ms_step}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores = time_cpu_oracle(3, 1)
+        cpu = {"value": B / sec, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "3 full config-2 iterations (B=64) after 1 warm-up; oracle port, torch %s CPU, %s; "
+                         "reference pin (py2.7/PyTorch@065c5986) not installable offline" % (torch.__version__,
+                                                                                           cpu_model())}
+    act_mb = 4 * (13.52e6 + 12.29e6) * 2 / 1e6
+    print(json.dumps({
+        "metric": "G-LIS train images/sec at 80x80 bs64/GPU", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "lis_depth": "all", "precision": "fp32 FFMA contractions",
+                   "l2": "inputs larger than L2: ~%.0f MB of activations + 36 MB of weights touched per step"
+                         % act_mb,
+                   "gflop_per_step": GFLOP_PER_STEP,
+                   "step_tflops": GFLOP_PER_STEP * world / ms_step},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from glis_b200 import dp
+        dp.init_from_env("nccl")
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

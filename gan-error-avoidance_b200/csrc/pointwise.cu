@@ -1,0 +1,320 @@
+// HBM-bound pieces of the G-LIS step: TPReLU (standalone form), per-channel reductions,
+// the BCE / MSE losses with their gradients, fused RMSprop, and the Philox generators.
+// All are grid-stride kernels sized to a multiple of the 148 SMs.
+#include "common.cuh"
+
+namespace glis {
+
+constexpr int PW_NT = 256;
+static inline int pw_blocks(int64_t numel, int per_thread = 4) {
+  int64_t b = (numel + (int64_t)PW_NT * per_thread - 1) / ((int64_t)PW_NT * per_thread);
+  const int64_t cap = 148 * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+__device__ __forceinline__ float clamp01(float a) { return fminf(fmaxf(a, 0.f), 1.f); }
+
+__global__ void __launch_bounds__(PW_NT)
+tprelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
+                  float* __restrict__ out, int64_t numel, int C, int inner) {
+  for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
+    const int c = (int)((i / inner) % C);
+    const float bb = __ldg(b + c), a = clamp01(__ldg(a_raw + c));
+    const float t = x[i] - bb;
+    out[i] = (t > 0.f ? t : a * t) + bb;
+  }
+}
+
+// Adds `v` into acc[c]; when the whole warp targets one channel the warp reduces first.
+__device__ __forceinline__ void channel_accumulate(float* acc, int c, float v, bool active) {
+  const unsigned full = 0xffffffffu;
+  const int c0 = __shfl_sync(full, c, 0);
+  const bool uniform = __all_sync(full, (!active) || c == c0) && __shfl_sync(full, (int)active, 0);
+  if (uniform) {
+    const float s = warp_sum(active ? v : 0.f);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc + c0, s);
+  } else if (active) {
+    atomicAdd(acc + c, v);
+  }
+}
+
+constexpr int SMEM_CH = 2048;  // channels staged in shared memory per accumulator
+
+__global__ void __launch_bounds__(PW_NT)
+tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
+                  const float* __restrict__ dout, float* __restrict__ dx, float* __restrict__ da,
+                  float* __restrict__ db, int64_t numel, int C, int inner) {
+  __shared__ float sa[SMEM_CH], sb[SMEM_CH];
+  const bool staged = C <= SMEM_CH;
+  if (staged) {
+    for (int c = threadIdx.x; c < C; c += PW_NT) { sa[c] = 0.f; sb[c] = 0.f; }
+    __syncthreads();
+  }
+  float* acc_a = staged ? sa : da;
+  float* acc_b = staged ? sb : db;
+  const int64_t stride = (int64_t)gridDim.x * PW_NT;
+  const int64_t rounds = (numel + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * PW_NT + threadIdx.x;
+    const bool active = i < numel;
+    int c = 0; float ga = 0.f, gb = 0.f;
+    if (active) {
+      c = (int)((i / inner) % C);
+      const float ar = __ldg(a_raw + c), bb = __ldg(b + c), a = clamp01(ar);
+      const float t = x[i] - bb, g = dout[i];
+      const bool neg = !(t > 0.f);
+      dx[i] = neg ? a * g : g;
+      if (neg) {
+        ga = (ar >= 0.f && ar <= 1.f) ? g * t : 0.f;
+        gb = g * (1.f - a);
+      }
+    }
+    channel_accumulate(acc_a, c, ga, active);
+    channel_accumulate(acc_b, c, gb, active);
+  }
+  if (staged) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += PW_NT) {
+      if (sa[c] != 0.f) atomicAdd(da + c, sa[c]);
+      if (sb[c] != 0.f) atomicAdd(db + c, sb[c]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PW_NT)
+channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, int C, int inner) {
+  __shared__ float sa[SMEM_CH];
+  const bool staged = C <= SMEM_CH;
+  if (staged) {
+    for (int c = threadIdx.x; c < C; c += PW_NT) sa[c] = 0.f;
+    __syncthreads();
+  }
+  float* acc = staged ? sa : out;
+  const int64_t stride = (int64_t)gridDim.x * PW_NT;
+  const int64_t rounds = (numel + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * PW_NT + threadIdx.x;
+    const bool active = i < numel;
+    const int c = active ? (int)((i / inner) % C) : 0;
+    channel_accumulate(acc, c, active ? x[i] : 0.f, active);
+  }
+  if (staged) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += PW_NT)
+      if (sa[c] != 0.f) atomicAdd(out + c, sa[c]);
+  }
+}
+
+// One block: B is the batch (tens to thousands of logits).
+__global__ void __launch_bounds__(PW_NT)
+bce_logits_kernel(const float* __restrict__ logit, float target, int B, float gscale, float* __restrict__ loss,
+                  float* __restrict__ dlogit, float* __restrict__ prob) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += PW_NT) {
+    const float l = logit[i];
+    const float p = 1.f / (1.f + expf(-l));
+    // nn.BCELoss on p with log clamped at -100 (modern torch)
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    acc -= target * lp + (1.f - target) * l1p;
+    if (dlogit) {
+      // d/dl of the clamped form: the clamped branch has zero slope
+      float g = 0.f;
+      if (target != 0.f && lp > -100.f) g -= target * (1.f - p);
+      if (target != 1.f && l1p > -100.f) g += (1.f - target) * p;
+      dlogit[i] = gscale * g / (float)B;
+    }
+    if (prob) prob[i] = p;
+  }
+  acc = block_sum<PW_NT>(acc, red);
+  if (threadIdx.x == 0) loss[0] = acc / (float)B;
+}
+
+__global__ void __launch_bounds__(PW_NT)
+mse_scaled_kernel(const float* __restrict__ u, const float* __restrict__ z, int64_t numel, float lambda,
+                  float* __restrict__ loss, float* __restrict__ du, int accumulate) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  const float k = 2.f * lambda / (float)numel;
+  for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
+    const float d = u[i] - z[i];
+    acc = fmaf(d, d, acc);
+    if (du) du[i] = accumulate ? du[i] + k * d : k * d;
+  }
+  acc = block_sum<PW_NT>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * lambda / (float)numel);
+}
+
+__global__ void __launch_bounds__(PW_NT)
+rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, int64_t numel,
+               float lr, float alpha, float eps, float gscale) {
+  const int64_t n4 = numel >> 2;
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)v)) & 15) == 0;
+  const int64_t tid = (int64_t)blockIdx.x * PW_NT + threadIdx.x, stride = (int64_t)gridDim.x * PW_NT;
+  if (vec) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 pp = p4[i], vv = v4[i]; const float4 gg = g4[i];
+      float* pa = &pp.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gr = ga[j] * gscale;
+        va[j] = alpha * va[j] + (1.f - alpha) * gr * gr;
+        pa[j] -= lr * gr / (sqrtf(va[j]) + eps);
+      }
+      p4[i] = pp; v4[i] = vv;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < numel; i += stride) {
+      const float gr = g[i] * gscale;
+      const float vv = alpha * v[i] + (1.f - alpha) * gr * gr;
+      v[i] = vv; p[i] -= lr * gr / (sqrtf(vv) + eps);
+    }
+  } else {
+    for (int64_t i = tid; i < numel; i += stride) {
+      const float gr = g[i] * gscale;
+      const float vv = alpha * v[i] + (1.f - alpha) * gr * gr;
+      v[i] = vv; p[i] -= lr * gr / (sqrtf(vv) + eps);
+    }
+  }
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter = (offset + element/4), key = seed
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+  k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c, k);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.f / 16777216.f); }  // [0,1)
+
+template <bool NORMAL>
+__global__ void __launch_bounds__(PW_NT)
+philox_fill_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint64_t offset) {
+  const int64_t quads = (numel + 3) >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PW_NT) {
+    uint32_t r[4];
+    philox4(seed, offset + (uint64_t)q, r);
+    float v[4];
+    if (NORMAL) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float u1 = 1.f - u01(r[2 * h]);  // (0,1]
+        const float u2 = u01(r[2 * h + 1]);
+        const float rad = sqrtf(-2.f * logf(u1));
+        float s, c;
+        sincospif(2.f * u2, &s, &c);
+        v[2 * h] = rad * c; v[2 * h + 1] = rad * s;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = u01(r[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < numel) out[q * 4 + j] = v[j];
+  }
+}
+
+}  // namespace glis
+
+using namespace glis;
+
+extern "C" int glis_tprelu_forward(const float* x, const float* a_raw, const float* b, float* out,
+                                   int64_t numel, int C, int inner, void* stream) {
+  GLIS_REQUIRE(x && a_raw && b && out, GLIS_E_BADARG, "glis_tprelu_forward: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_forward: bad sizes");
+  if (numel == 0) return GLIS_OK;
+  tprelu_fwd_kernel<<<pw_blocks(numel), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, out, numel, C, inner);
+  GLIS_CHECK_LAUNCH("glis_tprelu_forward");
+  return GLIS_OK;
+}
+
+extern "C" int glis_tprelu_backward(const float* x, const float* a_raw, const float* b, const float* dout,
+                                    float* dx, float* da, float* db, int64_t numel, int C, int inner,
+                                    void* stream) {
+  GLIS_REQUIRE(x && a_raw && b && dout && dx && da && db, GLIS_E_BADARG, "glis_tprelu_backward: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_backward: bad sizes");
+  if (numel == 0) return GLIS_OK;
+  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, dout, dx, da, db, numel,
+                                                                            C, inner);
+  GLIS_CHECK_LAUNCH("glis_tprelu_backward");
+  return GLIS_OK;
+}
+
+extern "C" int glis_channel_sum(const float* x, float* out, int64_t numel, int C, int inner, int accumulate,
+                                void* stream) {
+  GLIS_REQUIRE(x && out, GLIS_E_BADARG, "glis_channel_sum: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_channel_sum: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    if (cudaMemsetAsync(out, 0, sizeof(float) * C, st) != cudaSuccess) {
+      set_error("glis_channel_sum: memset failed");
+      return GLIS_E_CUDA;
+    }
+  }
+  if (numel == 0) return GLIS_OK;
+  channel_sum_kernel<<<pw_blocks(numel, 8), PW_NT, 0, st>>>(x, out, numel, C, inner);
+  GLIS_CHECK_LAUNCH("glis_channel_sum");
+  return GLIS_OK;
+}
+
+extern "C" int glis_bce_logits(const float* logit, float target, int B, float gscale, float* loss, float* dlogit,
+                               float* prob, void* stream) {
+  GLIS_REQUIRE(logit && loss, GLIS_E_BADARG, "glis_bce_logits: NULL pointer");
+  GLIS_REQUIRE(B > 0, GLIS_E_BADARG, "glis_bce_logits: empty batch");
+  bce_logits_kernel<<<1, PW_NT, 0, (cudaStream_t)stream>>>(logit, target, B, gscale, loss, dlogit, prob);
+  GLIS_CHECK_LAUNCH("glis_bce_logits");
+  return GLIS_OK;
+}
+
+extern "C" int glis_mse_scaled(const float* u, const float* z, int64_t numel, float lambda, float* loss, float* du,
+                               int accumulate, void* stream) {
+  GLIS_REQUIRE(u && z && loss, GLIS_E_BADARG, "glis_mse_scaled: NULL pointer");
+  GLIS_REQUIRE(numel > 0, GLIS_E_BADARG, "glis_mse_scaled: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) {
+    set_error("glis_mse_scaled: memset failed");
+    return GLIS_E_CUDA;
+  }
+  mse_scaled_kernel<<<pw_blocks(numel), PW_NT, 0, st>>>(u, z, numel, lambda, loss, du, accumulate);
+  GLIS_CHECK_LAUNCH("glis_mse_scaled");
+  return GLIS_OK;
+}
+
+extern "C" int glis_rmsprop(float* p, const float* g, float* v, int64_t numel, float lr, float alpha, float eps,
+                            float gscale, void* stream) {
+  GLIS_REQUIRE(p && g && v, GLIS_E_BADARG, "glis_rmsprop: NULL pointer");
+  GLIS_REQUIRE(numel >= 0, GLIS_E_BADARG, "glis_rmsprop: negative size");
+  if (numel == 0) return GLIS_OK;
+  rmsprop_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(p, g, v, numel, lr, alpha, eps, gscale);
+  GLIS_CHECK_LAUNCH("glis_rmsprop");
+  return GLIS_OK;
+}
+
+extern "C" int glis_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream) {
+  GLIS_REQUIRE(out && numel >= 0, GLIS_E_BADARG, "glis_randn: bad arguments");
+  if (numel == 0) return GLIS_OK;
+  philox_fill_kernel<true><<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(out, numel, seed, offset);
+  GLIS_CHECK_LAUNCH("glis_randn");
+  return GLIS_OK;
+}
+
+extern "C" int glis_uniform(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream) {
+  GLIS_REQUIRE(out && numel >= 0, GLIS_E_BADARG, "glis_uniform: bad arguments");
+  if (numel == 0) return GLIS_OK;
+  philox_fill_kernel<false><<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(out, numel, seed, offset);
+  GLIS_CHECK_LAUNCH("glis_uniform");
+  return GLIS_OK;
+}

@@ -1,0 +1,289 @@
+// fp32 FFMA gather-GEMM kernels: the exact-arithmetic path of every convolution-shaped
+// contraction of the G-LIS step (conv / transposed conv / linear, forward, data gradient
+// and weight gradient).  They serve (i) as the fp32 reference the tensor-core kernels are
+// checked against on the device, and (ii) as the product kernels of the layers whose
+// contraction is too thin for tcgen05 tiles (Cin=3, Cout=3, Cout=1 heads, batch-64 linears).
+//
+// Forward launch (glis_conv_forward):
+//   out[n,oy,ox,co] = sum_{tap,ci} in[n, iy(oy,tap), ix(ox,tap), ci] * wpack[tap][ci][co]
+// as a 64(pixels) x 64(channels) block tile with a 4x4 register micro-tile per thread and
+// K = (tap,ci) walked in chunks of 16.  A transposed convolution is decomposed into
+// stride_h*stride_w output phases (blockIdx.z) so that no multiply is spent on zeros.
+#include "common.cuh"
+
+namespace glis {
+
+struct PhaseInfo {
+  int ry, rx;    // first output row/col of this phase
+  int Hq, Wq;    // number of output rows/cols of this phase
+  int nth, ntw;  // taps of this phase along h / w
+  int py, px;    // phase index (first tap) along h / w
+};
+
+__device__ __forceinline__ PhaseInfo decode_phase(const glis_geom_t& g, int z) {
+  PhaseInfo p;
+  if (g.relation == GLIS_CONV) {
+    p.ry = p.rx = 0; p.Hq = g.Ho; p.Wq = g.Wo; p.nth = g.KH; p.ntw = g.KW; p.py = p.px = 0;
+  } else {
+    p.py = z / g.stride_w; p.px = z % g.stride_w;
+    p.ry = ((p.py - g.pad_h) % g.stride_h + g.stride_h) % g.stride_h;
+    p.rx = ((p.px - g.pad_w) % g.stride_w + g.stride_w) % g.stride_w;
+    p.Hq = g.Ho > p.ry ? (g.Ho - p.ry + g.stride_h - 1) / g.stride_h : 0;
+    p.Wq = g.Wo > p.rx ? (g.Wo - p.rx + g.stride_w - 1) / g.stride_w : 0;
+    p.nth = g.KH > p.py ? (g.KH - p.py + g.stride_h - 1) / g.stride_h : 0;
+    p.ntw = g.KW > p.px ? (g.KW - p.px + g.stride_w - 1) / g.stride_w : 0;
+  }
+  return p;
+}
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+__global__ void __launch_bounds__(NT)
+gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __restrict__ wp,
+                const glis_epilogue_t ep, float* __restrict__ out) {
+  const PhaseInfo ph = decode_phase(g, blockIdx.z);
+  const int P = g.N * ph.Hq * ph.Wq;  // output pixels of this phase
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= P) return;
+  const int n0 = blockIdx.y * BN;
+  const int ntaps = ph.nth * ph.ntw;
+  const int K = ntaps * g.Ci;
+
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  // ---- A-load role: k = tid % 16, pixels tid/16 + 16 j
+  const int a_k = tid & 15;
+  int a_n[4], a_oy[4], a_ox[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int m = m0 + (tid >> 4) + 16 * j;
+    if (m < P) {
+      int qx = m % ph.Wq; int t = m / ph.Wq; int qy = t % ph.Hq; a_n[j] = t / ph.Hq;
+      if (g.relation == GLIS_CONV) { a_oy[j] = qy; a_ox[j] = qx; }
+      else { a_oy[j] = qy * g.stride_h + ph.ry; a_ox[j] = qx * g.stride_w + ph.rx; }
+    } else { a_n[j] = -1; a_oy[j] = a_ox[j] = 0; }
+  }
+  // ---- B-load role: col = tid % 64, rows tid/64 + 4 j
+  const int b_c = tid & 63, b_r = tid >> 6;
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    {  // A tile
+      const int kk = k0 + a_k;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < K) {
+        const int tap = kk / g.Ci, ci = kk - tap * g.Ci;
+        const int jh = tap / ph.ntw, jw = tap - jh * ph.ntw;
+        int kh, kw;
+        if (g.relation == GLIS_CONV) { kh = jh; kw = jw; }
+        else { kh = ph.py + jh * g.stride_h; kw = ph.px + jw * g.stride_w; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (a_n[j] < 0) continue;
+          int iy, ix;
+          if (g.relation == GLIS_CONV) {
+            iy = a_oy[j] * g.stride_h - g.pad_h + kh * g.dil_h;
+            ix = a_ox[j] * g.stride_w - g.pad_w + kw * g.dil_w;
+          } else {
+            iy = (a_oy[j] + g.pad_h - kh) / g.stride_h;  // exact inside a phase
+            ix = (a_ox[j] + g.pad_w - kw) / g.stride_w;
+            if (a_oy[j] + g.pad_h - kh < 0) iy = -1;
+            if (a_ox[j] + g.pad_w - kw < 0) ix = -1;
+          }
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+            v[j] = __ldg(in + (((int64_t)a_n[j] * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[a_k][(tid >> 4) + 16 * j] = v[j];
+    }
+    {  // B tile
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = b_r + 4 * j, kk = k0 + r, co = n0 + b_c;
+        float v = 0.f;
+        if (kk < K && co < g.Co) {
+          const int tap = kk / g.Ci, ci = kk - tap * g.Ci;
+          const int jh = tap / ph.ntw, jw = tap - jh * ph.ntw;
+          int kh, kw;
+          if (g.relation == GLIS_CONV) { kh = jh; kw = jw; }
+          else { kh = ph.py + jh * g.stride_h; kw = ph.px + jw * g.stride_w; }
+          v = __ldg(wp + ((int64_t)(kh * g.KW + kw) * g.Ci + ci) * g.Co + co);
+        }
+        Bs[r][b_c] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, activation, optional pre-activation save
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= P) continue;
+    int qx = m % ph.Wq; int t = m / ph.Wq; int qy = t % ph.Hq; int n = t / ph.Hq;
+    int oy = qy, ox = qx;
+    if (g.relation == GLIS_TCONV) { oy = qy * g.stride_h + ph.ry; ox = qx * g.stride_w + ph.rx; }
+    const int64_t base = (((int64_t)n * g.Ho + oy) * g.Wo + ox) * g.Co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= g.Co) continue;
+      float y = acc[i][j];
+      if (ep.bias) y += __ldg(ep.bias + co);
+      if (ep.preact) ep.preact[base + co] = y;
+      float o = y;
+      if (ep.act == GLIS_ACT_TPRELU) {
+        const float b = __ldg(ep.act_b + co), a = __ldg(ep.act_a + co);
+        const float tt = y - b;
+        o = (tt > 0.f ? tt : a * tt) + b;
+      } else if (ep.act == GLIS_ACT_SIGMOID) {
+        o = 1.f / (1.f + expf(-y));
+      }
+      out[base + co] = o;
+    }
+  }
+}
+
+// Weight gradient: G[a][b][tap] += sum_pix small[pix][a] * big[gather(pix,tap)][b]
+// Block tile 64 (a) x 64 (flattened tap*Cb + b), K = pixels of `small`, split over blockIdx.z.
+__global__ void __launch_bounds__(NT)
+gather_gemm_wgrad(const glis_geom_t g, const float* __restrict__ small, const float* __restrict__ big,
+                  float* __restrict__ G, int pix_per_split) {
+  const int Ca = g.Co, Cb = g.Ci, T = g.KH * g.KW;
+  const int P = g.N * g.Ho * g.Wo;
+  const int a0 = blockIdx.x * BM, c0 = blockIdx.y * BN;
+  const int p_begin = blockIdx.z * pix_per_split;
+  const int p_end = min(P, p_begin + pix_per_split);
+  if (p_begin >= p_end) return;
+
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int l_c = tid & 63, l_r = tid >> 6;  // both tiles: col = tid%64, rows tid/64 + 4j
+  // B column decode (fixed for the block's lifetime)
+  const int nn = c0 + l_c;
+  const bool b_ok = nn < T * Cb;
+  const int tap = b_ok ? nn / Cb : 0, bch = b_ok ? nn - tap * Cb : 0;
+  const int kh = tap / g.KW, kw = tap - kh * g.KW;
+  const bool a_ok = (a0 + l_c) < Ca;
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int p0 = p_begin; p0 < p_end; p0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = l_r + 4 * j, pix = p0 + r;
+      float va = 0.f, vb = 0.f;
+      if (pix < p_end) {
+        if (a_ok) va = __ldg(small + (int64_t)pix * Ca + a0 + l_c);
+        if (b_ok) {
+          const int ox = pix % g.Wo; const int t = pix / g.Wo; const int oy = t % g.Ho; const int n = t / g.Ho;
+          const int iy = oy * g.stride_h - g.pad_h + kh * g.dil_h;
+          const int ix = ox * g.stride_w - g.pad_w + kw * g.dil_w;
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+            vb = __ldg(big + (((int64_t)n * g.Hi + iy) * g.Wi + ix) * Cb + bch);
+        }
+      }
+      As[r][l_c] = va;
+      Bs[r][l_c] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + ty * 4 + i;
+    if (a >= Ca) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + tx * 4 + j;
+      if (c >= T * Cb) continue;
+      const int tp = c / Cb, b = c - tp * Cb;
+      atomicAdd(G + ((int64_t)a * Cb + b) * T + tp, acc[i][j]);
+    }
+  }
+}
+
+int validate_geom(const glis_geom_t* g, const char* who) {
+  GLIS_REQUIRE(g != nullptr, GLIS_E_BADARG, "%s: geometry is NULL", who);
+  GLIS_REQUIRE(g->relation == GLIS_CONV || g->relation == GLIS_TCONV, GLIS_E_BADARG,
+               "%s: unknown relation %d", who, g->relation);
+  GLIS_REQUIRE(g->N > 0 && g->Hi > 0 && g->Wi > 0 && g->Ci > 0 && g->Ho > 0 && g->Wo > 0 && g->Co > 0,
+               GLIS_E_BADARG, "%s: non-positive tensor extent", who);
+  GLIS_REQUIRE(g->KH > 0 && g->KW > 0 && g->stride_h > 0 && g->stride_w > 0 && g->dil_h > 0 && g->dil_w > 0 &&
+                   g->pad_h >= 0 && g->pad_w >= 0,
+               GLIS_E_BADARG, "%s: bad kernel/stride/pad/dilation", who);
+  if (g->relation == GLIS_TCONV)
+    GLIS_REQUIRE(g->dil_h == 1 && g->dil_w == 1, GLIS_E_UNSUPPORTED, "%s: dilated transposed relation", who);
+  const int64_t big = (int64_t)1 << 31;
+  GLIS_REQUIRE((int64_t)g->N * g->Hi * g->Wi < big && (int64_t)g->N * g->Ho * g->Wo < big, GLIS_E_UNSUPPORTED,
+               "%s: more than 2^31 pixels", who);
+  return GLIS_OK;
+}
+
+int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
+                      float* out, cudaStream_t st) {
+  int nphase = 1, maxP = g->N * g->Ho * g->Wo;
+  if (g->relation == GLIS_TCONV) {
+    nphase = g->stride_h * g->stride_w;
+    const int Hq = cdiv(g->Ho, g->stride_h), Wq = cdiv(g->Wo, g->stride_w);
+    maxP = g->N * Hq * Wq;
+  }
+  dim3 grid(cdiv(maxP, BM), cdiv(g->Co, BN), nphase);
+  gather_gemm_fwd<<<grid, NT, 0, st>>>(*g, in, wpack, *ep, out);
+  GLIS_CHECK_LAUNCH("glis_conv_forward(fp32)");
+  return GLIS_OK;
+}
+
+int simt_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
+  const int T = g->KH * g->KW;
+  const int P = g->N * g->Ho * g->Wo;
+  const int tiles = cdiv(g->Co, BM) * cdiv((int64_t)T * g->Ci, BN);
+  // enough K-splits to fill the machine a few times over, at least 64 pixels each
+  int splits = (148 * 4 + tiles - 1) / tiles;
+  splits = max(1, min(splits, cdiv(P, 64)));
+  int per = cdiv(P, splits);
+  per = cdiv(per, BK) * BK;
+  splits = cdiv(P, per);
+  dim3 grid(cdiv(g->Co, BM), cdiv((int64_t)T * g->Ci, BN), splits);
+  gather_gemm_wgrad<<<grid, NT, 0, st>>>(*g, small, big, G, per);
+  GLIS_CHECK_LAUNCH("glis_conv_wgrad(fp32)");
+  return GLIS_OK;
+}
+
+}  // namespace glis

@@ -1,0 +1,135 @@
+"""ctypes binding of ``libglis_b200.so`` (C ABI declared in ``include/glis_b200.h``).
+
+There is no fallback: if the shared library is missing or a kernel reports an error the
+call raises.  Pointers are borrowed from torch tensors for the duration of a call and the
+work is enqueued on torch's current CUDA stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglis_b200.so")
+
+CONV, TCONV = 0, 1
+ACT_NONE, ACT_TPRELU, ACT_SIGMOID = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+
+
+class Geom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "relation", "N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co",
+        "KH", "KW", "stride_h", "stride_w", "pad_h", "pad_w", "dil_h", "dil_w")]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("act_a", C.c_void_p),
+                ("act_b", C.c_void_p), ("preact", C.c_void_p)]
+
+
+_vp, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
+
+# name -> argtypes; every symbol include/glis_b200.h declares
+SIGNATURES = {
+    "glis_wn_prepare": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "glis_wn_project": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "glis_conv_forward": [C.POINTER(Geom), _vp, _vp, C.POINTER(Epilogue), _vp, _i, _vp],
+    "glis_conv_wgrad": [C.POINTER(Geom), _vp, _vp, _vp, _i, _vp],
+    "glis_tprelu_forward": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "glis_tprelu_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "glis_channel_sum": [_vp, _vp, _i64, _i, _i, _i, _vp],
+    "glis_bce_logits": [_vp, _f, _i, _f, _vp, _vp, _vp, _vp],
+    "glis_mse_scaled": [_vp, _vp, _i64, _f, _vp, _vp, _i, _vp],
+    "glis_rmsprop": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
+    "glis_randn": [_vp, _i64, _u64, _u64, _vp],
+    "glis_uniform": [_vp, _i64, _u64, _u64, _vp],
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raises ``RuntimeError`` if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "glis_b200: %s is missing — build it with `python __graft_entry__.py` "
+            "(or `make -C gan-error-avoidance_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.glis_last_error.restype = C.c_char_p
+    lib.glis_last_error.argtypes = []
+    lib.glis_version.restype = C.c_int
+    lib.glis_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, load().glis_last_error().decode()))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a dense fp32 CUDA tensor (or NULL for None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("glis_b200 kernels need CUDA tensors; there is no CPU path")
+    if t.dtype != torch.float32:
+        raise RuntimeError("glis_b200 kernels are fp32 at the API boundary, got %s" % t.dtype)
+    return C.c_void_p(t.data_ptr())
+
+
+# kernels enqueued by one successful call of each entry point (memsets are not kernels)
+KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
+
+launch_count = 0     # kernels this process enqueued through the C ABI
+_timers = {}         # tag -> list of (start_event, end_event); see `timed`
+
+
+def call(name, *args, kernels=None):
+    global launch_count
+    check(getattr(load(), name)(*args), name)
+    launch_count += KERNELS_PER_CALL[name] if kernels is None else kernels
+
+
+class timed(object):
+    """``with timed(tag):`` brackets the enclosed launches with CUDA events on the current
+    stream when profiling is on (bench.py's per-kernel roofline); free otherwise."""
+
+    enabled = False
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if timed.enabled:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if timed.enabled:
+            self.end.record()
+            _timers.setdefault(self.tag, []).append((self.start, self.end))
+        return False
+
+
+def timer_summary(reset=True):
+    """tag -> (launches, mean milliseconds). Call after a device synchronize."""
+    out = {k: (len(v), sum(s.elapsed_time(e) for s, e in v) / len(v)) for k, v in _timers.items() if v}
+    if reset:
+        _timers.clear()
+    return out

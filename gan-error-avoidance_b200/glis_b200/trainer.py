@@ -1,0 +1,118 @@
+"""The G-LIS adversarial training iteration on the sm_100a kernels.
+
+``GLISTrainer.step`` performs exactly one iteration of the reference's loop
+(g_lis/main.py:526-589): D on a real batch, D on a generated batch (G under no-grad),
+RMSprop on D, then G + LIS against D with the latent-reconstruction losses, RMSprop on
+G.  Parameters, gradients and RMSprop state of each network live in three flat fp32
+buffers so that ``zero_grad`` is one memset, the optimizer one kernel and — under data
+parallelism — the gradient exchange a handful of large all-reduces.
+
+Legacy semantics kept: gradients are zero-filled, never dropped, so a
+LIS module skipped by the stochastic depth still decays its ``square_avg``; a parameter
+that never received a gradient has g = v = 0 and the update leaves it untouched.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+class FlatParams(object):
+    """Re-homes a module's parameters (and their ``.grad``) into contiguous flat buffers."""
+
+    ALIGN = 4  # floats (16 bytes)
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters()]
+        if not self.params:
+            raise ValueError("module has no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("glis_b200: move the networks to a CUDA device first (no CPU path)")
+        self.offsets = []
+        total = 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = total
+        self.p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.p[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.p[o:o + n].view(p.shape)
+            p.grad = self.g[o:o + n].view(p.shape)
+
+    def zero_grad(self):
+        self.g.zero_()
+
+    def rebind_grads(self):
+        """Autograd may have replaced ``.grad`` (it does not for in-place accumulation, but a
+        user could); make sure every parameter still accumulates into the flat buffer."""
+        for p, o in zip(self.params, self.offsets):
+            want = self.g[o:o + p.numel()].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                if p.grad is not None:
+                    want.add_(p.grad)
+                p.grad = want
+
+    def rmsprop_step(self, lr, alpha=0.9, eps=1e-6, gscale=1.0):
+        ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale)
+
+
+class GLISTrainer(object):
+    """One object per (G-LIS, D) pair; ``step`` = one reference training iteration."""
+
+    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6, grad_sync=None):
+        self.gen, self.dis = gen, dis
+        self.lr, self.lambda_r, self.alpha, self.eps = lr, lambda_r, alpha, eps
+        self.gen_flat = FlatParams(gen)
+        self.dis_flat = FlatParams(dis)
+        # grad_sync(flat_grad_tensor, tag) -> gscale ; installed by the data-parallel wrapper
+        self.grad_sync = grad_sync
+        self.launches = 0
+
+    def _set_dis_requires_grad(self, flag):
+        for p in self.dis_flat.params:
+            p.requires_grad_(flag)
+
+    def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
+        gen, dis = self.gen, self.dis
+        B = real.shape[0]
+        ones = torch.ones(B, 1, device=real.device)
+        zeros = torch.zeros(B, 1, device=real.device)
+
+        # ---- D step
+        self._set_dis_requires_grad(True)
+        self.dis_flat.zero_grad()
+        loss_d_real = F.binary_cross_entropy(dis(real), ones)
+        loss_d_real.backward()
+        with torch.no_grad():
+            fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
+        loss_d_fake = F.binary_cross_entropy(dis(fake.detach()), zeros)
+        loss_d_fake.backward()
+        self.dis_flat.rebind_grads()
+        gs = self.grad_sync(self.dis_flat.g, "dis") if self.grad_sync else 1.0
+        self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+
+        # ---- G step
+        self._set_dis_requires_grad(False)
+        self.gen_flat.zero_grad()
+        fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
+        loss_g = F.binary_cross_entropy(dis(fake), ones)
+        total = loss_g
+        loss_r = []
+        if self.lambda_r > 0:
+            for i, u in enumerate(lis_g):
+                l = F.mse_loss(u, z_g) * (self.lambda_r ** (i + 1))
+                loss_r.append(l.detach())
+                total = total + l
+        total.backward()
+        self.gen_flat.rebind_grads()
+        gs = self.grad_sync(self.gen_flat.g, "gen") if self.grad_sync else 1.0
+        self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+        self._set_dis_requires_grad(True)
+
+        return {"d_real": loss_d_real.detach(), "d_fake": loss_d_fake.detach(), "g": loss_g.detach(),
+                "r": loss_r, "depth_d": len(lis_d), "depth_g": len(lis_g)}

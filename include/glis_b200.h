@@ -1,0 +1,150 @@
+/*
+ * glis_b200.h — C ABI of the B200-native G-LIS training-step kernels.
+ *
+ * The reference (aleju/gan-error-avoidance) has no FFI layer of its own: every device
+ * op is a stock PyTorch call made from its Python nn.Modules.  Each entry point below
+ * therefore cites the reference *call site* it replaces (paths relative to the
+ * upstream repository).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a name ends in `_host`.  The library
+ *     borrows them for the duration of the call: it never allocates, frees or retains
+ *     device memory (workspaces are caller-provided).
+ *   - Activations are fp32, NHWC ("channels_last"): element (n,y,x,c) at ((n*H+y)*W+x)*C+c.
+ *     A (B,F) matrix is the H=W=1 case.
+ *   - Parameters keep the reference's shapes ("master" layout): conv (Cout,Cin,KH,KW),
+ *     transposed conv (Cin,Cout,KH,KW), linear (out,in), scale/bias one value per
+ *     output channel, TPReLU slope/translation one value per channel.
+ *   - Every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no
+ *     host synchronisation.  Entry points are re-entrant.
+ *   - Return value: 0 on success, a negative GLIS_E* code otherwise;
+ *     glis_last_error() returns a thread-local description.  Nothing throws or exits.
+ */
+#ifndef GLIS_B200_H
+#define GLIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLIS_OK 0
+#define GLIS_E_BADARG (-1)      /* null pointer, negative size, inconsistent geometry */
+#define GLIS_E_UNSUPPORTED (-2) /* valid request this build has no kernel for */
+#define GLIS_E_CUDA (-3)        /* CUDA runtime error at enqueue */
+#define GLIS_E_WORKSPACE (-4)   /* caller workspace too small */
+
+/* gather relation between the "out" grid of a kernel and the tensor it reads */
+#define GLIS_CONV 0   /* in = out*stride - pad + k*dil   (F.conv2d forward) */
+#define GLIS_TCONV 1  /* in = (out + pad - k)/stride     (F.conv_transpose2d forward) */
+
+/* epilogue activation */
+#define GLIS_ACT_NONE 0
+#define GLIS_ACT_TPRELU 1  /* (t>0 ? t : a*t) + b, t = y-b, a pre-clamped to [0,1] */
+#define GLIS_ACT_SIGMOID 2
+
+/* arithmetic of the contraction */
+#define GLIS_PREC_FP32 0    /* fp32 FFMA (exact-mode reference kernels, edge layers) */
+#define GLIS_PREC_BF16X3 1  /* tcgen05 bf16 hi/lo split, 3 MMAs per k-step, ~2^-16 rel. */
+#define GLIS_PREC_BF16 2    /* tcgen05 bf16, 1 MMA per k-step, ~2^-8 rel. */
+
+/* Geometry of one (transposed) convolution.  `in`/`out` refer to the tensors of THIS
+ * kernel launch (a dgrad launch swaps the layer's roles).  A linear layer is
+ * KH=KW=Hi=Wi=Ho=Wo=1. */
+typedef struct glis_geom {
+  int32_t relation;          /* GLIS_CONV | GLIS_TCONV */
+  int32_t N, Hi, Wi, Ci;     /* tensor that is read */
+  int32_t Ho, Wo, Co;        /* tensor that is written */
+  int32_t KH, KW, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+} glis_geom_t;
+
+/* Fused epilogue of a forward launch: y = acc + bias[c]; out = act(y). */
+typedef struct glis_epilogue {
+  const float* bias;   /* per out-channel, or NULL */
+  int32_t act;         /* GLIS_ACT_* */
+  const float* act_a;  /* TPReLU slope, already clamped to [0,1] (per out-channel) */
+  const float* act_b;  /* TPReLU translation (per out-channel) */
+  float* preact;       /* if non-NULL, y (before act) is also stored here (NHWC) */
+} glis_epilogue_t;
+
+const char* glis_last_error(void);
+int glis_version(void);
+
+/* ---- weight normalisation ------------------------------------------------------
+ * Replaces `_WeightNormalizedConvNd.weight_norm` (common/modules/WeightNormalizedConv.py:29-38)
+ * and `WeightNormalizedLinear.weight_norm` (WeightNormalizedLinear.py:30-31), plus the
+ * division / scale of `norm_scale_bias` (Conv.py:40-47, Linear.py:33-37), folded into the
+ * weights once per parameter update:  w_hat[o] = w[o] * scale[o] / sqrt(c*|w[o]|^2 + 1e-6).
+ *
+ *   w        master weights; out_axis = 0 for conv/linear (Cout,Cin,T), 1 for transposed (Cin,Cout,T)
+ *   c        weight_norm_factor (1, or 1/(stride_h*stride_w) for transposed conv)
+ *   norm     [Cout]  out: sqrt(c*sum w^2 + 1e-6)
+ *   pack_io  [T][Cin][Cout]  out (may be NULL): w_hat laid out for a launch that reads Cin, writes Cout
+ *   pack_oi  [T][Cout][Cin]  out (may be NULL): w_hat laid out for the data-gradient launch
+ */
+int glis_wn_prepare(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                    float c, float* norm, float* pack_io, float* pack_oi, void* stream);
+
+/* Backward of the normalisation: given the raw gradient G w.r.t. w_hat
+ * (master layout), dw[o] (+)= (s/n)(G[o] - c w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n.
+ * `accumulate` != 0 adds into dw / dscale instead of overwriting. */
+int glis_wn_project(const float* G, const float* w, const float* scale, const float* norm,
+                    int out_axis, int Cout, int Cin, int T, float c, float* dw, float* dscale,
+                    int accumulate, void* stream);
+
+/* ---- convolution-shaped contractions --------------------------------------------
+ * Forward of F.conv2d (WeightNormalizedConv.py:80), F.conv_transpose2d (:98), F.linear
+ * (WeightNormalizedLinear.py:42) and, with the roles swapped, their data gradients.
+ *   in   [N,Hi,Wi,Ci]   wpack [KH*KW][Ci][Co] (from glis_wn_prepare)   out [N,Ho,Wo,Co]
+ */
+int glis_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
+                      const glis_epilogue_t* ep, float* out, int precision, void* stream);
+
+/* Raw weight gradient in master layout: G[a][b][tap] = sum_pix small[pix][a] * big[pix*s-p+k][b].
+ * conv layer:  small = dy (Ca=Cout), big = x (Cb=Cin);  transposed: small = x (Ca=Cin), big = dy.
+ * `g` describes the gather small(out grid: Ho,Wo,Co=Ca) <- big(Hi,Wi,Ci=Cb), relation GLIS_CONV.
+ * G must be zero-filled by the caller when `accumulate` == 0 is intended (the kernel always adds).
+ */
+int glis_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G,
+                    int precision, void* stream);
+
+/* ---- pointwise / reductions -------------------------------------------------------
+ * TPReLU forward (common/modules/TPReLU.py:16-18) on a tensor whose channel of element i is
+ * (i / inner) % C  (inner = 1 for NHWC and (B,C); H*W for NCHW-contiguous). a_raw is clamped here. */
+int glis_tprelu_forward(const float* x, const float* a_raw, const float* b, float* out,
+                        int64_t numel, int C, int inner, void* stream);
+/* dx = dout*(t<=0 ? clamp(a) : 1); da_raw += sum dout*t*[t<=0]*[0<=a_raw<=1]; db += sum dout*[t<=0]*(1-clamp(a)). */
+int glis_tprelu_backward(const float* x, const float* a_raw, const float* b, const float* dout,
+                         float* dx, float* da, float* db, int64_t numel, int C, int inner,
+                         void* stream);
+/* out[c] (+)= sum over elements of channel c (bias gradient: WeightNormalizedConv.py:47-48 backward). */
+int glis_channel_sum(const float* x, float* out, int64_t numel, int C, int inner, int accumulate,
+                     void* stream);
+
+/* Mean binary cross entropy on logits against a constant target (nn.Sigmoid + nn.BCELoss,
+ * common/model.py:61, g_lis/main.py:311,555,564,578).  loss[0] = mean; dlogit[i] = gscale*(p_i - t)/B
+ * (may be NULL); prob (may be NULL) receives sigmoid(logit). */
+int glis_bce_logits(const float* logit, float target, int B, float gscale, float* loss,
+                    float* dlogit, float* prob, void* stream);
+
+/* lambda * mean((u - z)^2) (nn.MSELoss, g_lis/main.py:312,584-585); du (+)= 2*lambda*(u-z)/numel. */
+int glis_mse_scaled(const float* u, const float* z, int64_t numel, float lambda, float* loss,
+                    float* du, int accumulate, void* stream);
+
+/* RMSprop without momentum (optim.RMSprop, g_lis/main.py:313-314) over one flat buffer:
+ * v = alpha v + (1-alpha) g^2 ; p -= lr g / (sqrt(v)+eps).  gscale multiplies g first
+ * (1/world_size after a sum all-reduce). */
+int glis_rmsprop(float* p, const float* g, float* v, int64_t numel, float lr, float alpha,
+                 float eps, float gscale, void* stream);
+
+/* Standard-normal fill (torch.randn at g_lis/main.py:561,576): Philox4x32-10 + Box-Muller. */
+int glis_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream);
+/* U[0,1) fill (synthetic "real" batches of the benchmark). */
+int glis_uniform(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIS_B200_H */

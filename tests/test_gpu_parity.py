@@ -1,0 +1,366 @@
+"""GPU parity: the sm_100a path (through the ctypes C ABI) against the oracle on identical
+weights and inputs, and against the golden vectors produced by the reference's sources.
+
+Tolerances (north star): relative error = max|got-want| / max|want|.
+  fp32 contraction mode :  forward / losses <= 1e-4,  gradients <= 1e-3
+  (the fp32 kernels land around 1e-6 / 1e-5; the bounds are the contract, not the typical value)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.step import GLISOracleTrainer
+from util import copy_params, randomize_params_, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, GRAD_TOL = 1e-4, 1e-3
+DEV = "cuda"
+
+
+def _product():
+    import common.model as pm
+    import common.modules as pmod
+    return pm, pmod
+
+
+def _check_module(ref, prod, x, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL, seed=0):
+    """ref: oracle module (CPU, fp64), prod: product module (CUDA, fp32) with equal params."""
+    gen = torch.Generator().manual_seed(seed)
+    xr = x.double().clone().requires_grad_(True)
+    xp = x.float().to(DEV).requires_grad_(True)
+    yr, yp = ref(xr), prod(xp)
+    assert tuple(yr.shape) == tuple(yp.shape)
+    assert rel_err(yp, yr) <= fwd_tol, "forward %g" % rel_err(yp, yr)
+    r = torch.rand(yr.shape, generator=gen, dtype=torch.float64) * 2 - 1
+    (yr * r).sum().backward()
+    (yp * r.float().to(DEV)).sum().backward()
+    assert rel_err(xp.grad, xr.grad) <= grad_tol, "dx %g" % rel_err(xp.grad, xr.grad)
+    for (n, pr), (_, pp) in zip(ref.named_parameters(), prod.named_parameters()):
+        e = rel_err(pp.grad, pr.grad)
+        assert e <= grad_tol, "grad %s %g" % (n, e)
+
+
+def _pair(make_ref, make_prod, seed=1):
+    gen = torch.Generator().manual_seed(seed)
+    ref = make_ref()
+    randomize_params_(ref, gen)
+    prod = make_prod()
+    copy_params(prod, ref)
+    return ref.double(), prod.to(DEV)
+
+
+CONV_CASES = [
+    # (Cin, Cout, k, s, p, scale/bias, N, H, W)
+    (3, 5, 4, 2, (1, 1), False, 2, 8, 12),
+    (4, 6, 4, 2, (2, 1), True, 2, 10, 8),
+    (6, 1, (3, 5), 1, 0, True, 3, 3, 5),
+    (4, 3, 3, 1, (1, 1), False, 2, 6, 6),
+    (3, 64, 4, 2, 1, False, 3, 32, 32),       # D level 0 shape family (Cin = 3)
+    (64, 128, 4, 2, 1, False, 2, 20, 20),     # D level 1 family
+    (70, 33, 4, 2, (2, 2), True, 2, 10, 14),  # ragged channel counts, pad 2
+    (128, 1, (5, 5), 1, 0, True, 5, 5, 5),    # D head
+    (32, 16, (4, 4), 1, 0, True, 4, 4, 4),    # R head family (Cout = code)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_wn_conv2d(case):
+    _, pmod = _product()
+    ci, co, k, s, p, aff, n, h, w = case
+    ref, prod = _pair(lambda: oracle.WeightNormalizedConv2d(ci, co, k, s, p, scale=aff, bias=aff),
+                      lambda: pmod.WeightNormalizedConv2d(ci, co, k, s, p, scale=aff, bias=aff))
+    x = torch.rand(n, ci, h, w, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    _check_module(ref, prod, x)
+
+
+DECONV_CASES = [
+    (6, 4, 4, 2, (1, 1), False, 2, 5, 3),
+    (4, 3, 4, 2, (2, 1), True, 2, 5, 4),
+    (64, 3, 4, 2, 1, True, 2, 16, 16),        # G level 0 family (Cout = 3)
+    (128, 64, 4, 2, 1, False, 2, 10, 10),
+    (40, 24, 4, 2, (2, 2), False, 3, 6, 9),
+    (16, 8, 3, 1, 1, True, 2, 7, 7),          # stride 1 transposed
+]
+
+
+@pytest.mark.parametrize("case", DECONV_CASES)
+def test_wn_conv_transpose2d(case):
+    _, pmod = _product()
+    ci, co, k, s, p, aff, n, h, w = case
+    ref, prod = _pair(lambda: oracle.WeightNormalizedConvTranspose2d(ci, co, k, s, p, scale=aff, bias=aff),
+                      lambda: pmod.WeightNormalizedConvTranspose2d(ci, co, k, s, p, scale=aff, bias=aff))
+    x = torch.rand(n, ci, h, w, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    _check_module(ref, prod, x)
+
+
+def test_conv_transpose_output_size():
+    _, pmod = _product()
+    ref, prod = _pair(lambda: oracle.WeightNormalizedConvTranspose2d(4, 3, 3, 2, 1),
+                      lambda: pmod.WeightNormalizedConvTranspose2d(4, 3, 3, 2, 1))
+    x = torch.rand(2, 4, 5, 5) - 0.5
+    yr = ref(x.double(), output_size=(10, 10))
+    yp = prod(x.to(DEV), output_size=(10, 10))
+    assert yp.shape == (2, 3, 10, 10) and rel_err(yp, yr) <= FWD_TOL
+    with pytest.raises(ValueError):
+        prod(x.to(DEV), output_size=(12, 12))
+
+
+@pytest.mark.parametrize("case", [(7, 10, False, 4), (7, 5, True, 4), (256, 256, False, 64), (64, 800, False, 32)])
+def test_wn_linear(case):
+    _, pmod = _product()
+    i, o, aff, b = case
+    ref, prod = _pair(lambda: oracle.WeightNormalizedLinear(i, o, scale=aff, bias=aff, init_factor=0.01),
+                      lambda: pmod.WeightNormalizedLinear(i, o, scale=aff, bias=aff, init_factor=0.01))
+    _check_module(ref, prod, torch.randn(b, i, generator=torch.Generator().manual_seed(5)))
+
+
+@pytest.mark.parametrize("shape", [(5, 6), (2, 3, 4, 5), (64, 256), (4, 32, 10, 10)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_tprelu(shape, channels_last):
+    _, pmod = _product()
+    if channels_last and len(shape) != 4:
+        pytest.skip("2-D input has one layout")
+    ref, prod = _pair(lambda: oracle.TPReLU(shape[1]), lambda: pmod.TPReLU(shape[1]))
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(6))
+    gen = torch.Generator().manual_seed(7)
+    xr = x.double().requires_grad_(True)
+    xp = x.to(DEV)
+    if channels_last:
+        xp = xp.contiguous(memory_format=torch.channels_last)
+    xp.requires_grad_(True)
+    yr, yp = ref(xr), prod(xp)
+    assert rel_err(yp, yr) <= 1e-6
+    r = torch.rand(yr.shape, generator=gen, dtype=torch.float64) - 0.5
+    (yr * r).sum().backward()
+    (yp * r.float().to(DEV)).sum().backward()
+    assert rel_err(xp.grad, xr.grad) <= 1e-6
+    assert rel_err(prod.weight.grad, ref.weight.grad) <= 1e-4
+    assert rel_err(prod.bias.grad, ref.bias.grad) <= 1e-4
+
+
+def test_weight_norm_and_norm_scale_bias_helpers():
+    _, pmod = _product()
+    for ref, prod in [
+        _pair(lambda: oracle.WeightNormalizedConv2d(5, 7, 4, 2, 1), lambda: pmod.WeightNormalizedConv2d(5, 7, 4, 2, 1)),
+        _pair(lambda: oracle.WeightNormalizedConvTranspose2d(5, 7, 4, 2, 1),
+              lambda: pmod.WeightNormalizedConvTranspose2d(5, 7, 4, 2, 1)),
+    ]:
+        nr, np_ = ref.weight_norm(), prod.weight_norm()
+        assert sorted(np_.shape) == sorted(nr.shape) and rel_err(np_.reshape(-1), nr.reshape(-1)) <= 1e-6
+        z = torch.randn(2, 7, 3, 3)
+        assert rel_err(prod.norm_scale_bias(z.to(DEV)), ref.norm_scale_bias(z.double())) <= 1e-6
+    ref, prod = _pair(lambda: oracle.WeightNormalizedLinear(6, 9), lambda: pmod.WeightNormalizedLinear(6, 9))
+    assert prod.weight_norm().shape == (9, 1)
+    assert rel_err(prod.weight_norm(), ref.weight_norm()) <= 1e-6
+
+
+# ---------------------------------------------------------------- golden vectors (reference sources)
+def _golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    return {k: z[k] for k in z.files}
+
+
+def _grp(store, prefix):
+    pre = prefix + "/"
+    return {k[len(pre):]: v for k, v in store.items() if k.startswith(pre)}
+
+
+def test_golden_modules(golden_dir):
+    _, pmod = _product()
+    cases = {
+        "conv_s2": lambda: pmod.WeightNormalizedConv2d(3, 5, 4, 2, (1, 1), scale=False, bias=False),
+        "conv_s2_pad2_affine": lambda: pmod.WeightNormalizedConv2d(4, 6, 4, 2, (2, 1)),
+        "conv_head": lambda: pmod.WeightNormalizedConv2d(6, 1, (3, 5)),
+        "conv_3x3_s1": lambda: pmod.WeightNormalizedConv2d(4, 3, 3, 1, (1, 1), scale=False, bias=False),
+        "deconv_s2": lambda: pmod.WeightNormalizedConvTranspose2d(6, 4, 4, 2, (1, 1), scale=False, bias=False),
+        "deconv_s2_pad2_affine": lambda: pmod.WeightNormalizedConvTranspose2d(4, 3, 4, 2, (2, 1)),
+        "linear_plain": lambda: pmod.WeightNormalizedLinear(7, 10, scale=False, bias=False, init_factor=0.01),
+        "linear_affine": lambda: pmod.WeightNormalizedLinear(7, 5),
+        "tprelu_2d": lambda: pmod.TPReLU(6),
+        "tprelu_4d": lambda: pmod.TPReLU(3),
+    }
+    store = _golden(golden_dir, "modules.npz")
+    for case, build in cases.items():
+        g = _grp(store, case)
+        m = build().to(DEV)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.copy_(torch.from_numpy(g["p." + n]).float())
+        x = torch.from_numpy(g["x"]).float().to(DEV).requires_grad_(True)
+        y = m(x)
+        assert rel_err(y, torch.from_numpy(g["y"])) <= FWD_TOL, case
+        (y * torch.from_numpy(g["r"]).float().to(DEV)).sum().backward()
+        assert rel_err(x.grad, torch.from_numpy(g["dx"])) <= GRAD_TOL, case
+        for n, p in m.named_parameters():
+            assert rel_err(p.grad, torch.from_numpy(g["g." + n])) <= GRAD_TOL, (case, n)
+
+
+def test_golden_models(golden_dir):
+    pm, _ = _product()
+    cases = {
+        "D_16": (lambda: pm.build_discriminator(16, 16, 4, 2, "weight", 0), None),
+        "D_20x12_pad": (lambda: pm.build_discriminator(20, 12, 4, 3, "weight", 0), None),
+        "R_16": (lambda: pm.build_reverser(16, 16, 4, 2, 8, "weight", 0), None),
+        "G_16": (lambda: pm.build_generator(16, 16, 4, 2, 8, "weight"), None),
+        "G_20x12_pad": (lambda: pm.build_generator(20, 12, 4, 3, 8, "weight"), None),
+        "GLIS_16_k2of3": (lambda: pm.GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 3, "fractional"), 2),
+        "GLIS_16_nearest": (lambda: pm.GeneratorLearnedInputSpace(16, 16, 4, 3, 8, "weight", 1, "nearest"), "all"),
+    }
+    store = _golden(golden_dir, "models.npz")
+    for case, (build, depth) in cases.items():
+        g = _grp(store, case)
+        net = build()
+        net.load_state_dict({k[2:]: torch.from_numpy(v).float() for k, v in g.items() if k.startswith("p.")})
+        net = net.to(DEV).eval()
+        x = torch.from_numpy(g["x"]).float().to(DEV).requires_grad_(True)
+        out = net(x, n_execute_lis_layers=depth) if depth is not None else net(x)
+        flat = [out[0]] + list(out[1]) if isinstance(out, tuple) else [out]
+        loss = 0
+        for i, o in enumerate(flat):
+            assert rel_err(o, torch.from_numpy(g["y%d" % i])) <= FWD_TOL, (case, i)
+            loss = loss + (o * torch.from_numpy(g["r%d" % i]).float().to(DEV)).sum()
+        loss.backward()
+        assert rel_err(x.grad, torch.from_numpy(g["dx"])) <= GRAD_TOL, case
+        grads = {k: p.grad for k, p in zip(net.state_dict().keys(), net.parameters())}
+        for k, p in net.named_parameters():
+            key = k.replace("·", ".")
+            want = torch.from_numpy(g["g." + key])
+            got = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert rel_err(got, want) <= GRAD_TOL, (case, key)
+
+
+def test_golden_training_iterations(golden_dir):
+    """Three reference-semantics iterations (stock torch optimizers on the reference's modules)."""
+    pm, _ = _product()
+    from glis_b200.trainer import GLISTrainer
+    s = _golden(golden_dir, "glis_steps.npz")
+    cfg = _grp(s, "cfg")
+    W, H, B, code, nf, nl, n_lis = (int(cfg[k]) for k in ("W", "H", "B", "code", "nf", "nl", "n_lis"))
+    gen = pm.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis, "fractional")
+    dis = pm.build_discriminator(W, H, nf, nl, "weight", 0)
+    gen.load_state_dict({k: torch.from_numpy(v).float() for k, v in _grp(s, "init/g").items()})
+    dis.load_state_dict({k: torch.from_numpy(v).float() for k, v in _grp(s, "init/d").items()})
+    tr = GLISTrainer(gen.to(DEV), dis.to(DEV), lr=float(cfg["lr"]), lambda_r=float(cfg["lam"]))
+    for it, (kd, kg) in enumerate(cfg["depths"]):
+        g = _grp(s, "it%d" % it)
+        f = lambda a: torch.from_numpy(a).float().to(DEV)
+        out = tr.step(f(g["real"]), f(g["zd"]), f(g["zg"]), depth_d=int(kd), depth_g=int(kg))
+        for name in ("d_real", "d_fake", "g"):
+            assert abs(out[name].item() - float(g[name])) <= FWD_TOL * abs(float(g[name])), (it, name)
+        for i, l in enumerate(out["r"]):
+            assert abs(l.item() - float(g["r"][i])) <= FWD_TOL * abs(float(g["r"][i])), (it, "r", i)
+        # lr = 1e-2 makes every RMSprop update O(lr): parameters must track to 1e-3 of their scale
+        for k, v in gen.state_dict().items():
+            assert rel_err(v, torch.from_numpy(g["g/" + k])) <= 2e-3, (it, "gen", k)
+        for k, v in dis.state_dict().items():
+            assert rel_err(v, torch.from_numpy(g["d/" + k])) <= 2e-3, (it, "dis", k)
+
+
+# ---------------------------------------------------------------- whole-step parity vs the oracle
+def _make_pair(W, H, nf, nl, code, n_lis, seed=11):
+    pm, _ = _product()
+    torch.manual_seed(seed)
+    og = oracle.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis, "fractional")
+    od = oracle.build_discriminator(W, H, nf, nl, "weight", 0)
+    pg = pm.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis, "fractional")
+    pd = pm.build_discriminator(W, H, nf, nl, "weight", 0)
+    copy_params(pg, og)
+    copy_params(pd, od)
+    return og, od, pg.to(DEV), pd.to(DEV)
+
+
+def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
+    from glis_b200.trainer import GLISTrainer
+    ot = GLISOracleTrainer(og, od, lr=lr, lambda_r=0.9)
+    pt = GLISTrainer(pg, pd, lr=lr, lambda_r=0.9)
+    gen = torch.Generator().manual_seed(seed)
+    for it, (kd, kg) in enumerate(depths):
+        real = torch.rand(B, 3, H, W, generator=gen)
+        zd, zg = torch.randn(B, code, generator=gen), torch.randn(B, code, generator=gen)
+        lo = ot.step(real, zd, zg, kd, kg)
+        lp = pt.step(real.to(DEV), zd.to(DEV), zg.to(DEV), kd, kg)
+        for name in ("d_real", "d_fake", "g"):
+            assert abs(lp[name].item() - lo[name]) <= FWD_TOL * abs(lo[name]), (it, name, lp[name].item(), lo[name])
+        assert len(lp["r"]) == len(lo["r"])
+        for a, b in zip(lp["r"], lo["r"]):
+            assert abs(a.item() - b) <= FWD_TOL * abs(b), (it, "r")
+    return ot, pt
+
+
+def test_step_parity_cfg1_shape():
+    """BASELINE config 1: 32x32, batch 32, nfeature 64, 3 levels, code 256, 1 LIS module."""
+    og, od, pg, pd = _make_pair(32, 32, 64, 3, 256, 1)
+    lr = 2e-5
+    before = {k: v.clone() for k, v in og.state_dict().items()}
+    _run_steps(og, od, pg, pd, 32, 32, 32, 256, [(1, 1), (0, 1), (1, 0)], lr)
+    # parameters moved by ~lr per step; compare the UPDATE (delta) to 1e-3 of its own scale
+    for k, v in pg.state_dict().items():
+        want = og.state_dict()[k] - before[k]
+        got = v.cpu() - before[k]
+        assert rel_err(got, want) <= 5e-3, k
+    for k, v in pd.state_dict().items():
+        assert rel_err(v, od.state_dict()[k]) <= 1e-5, k
+
+
+def test_step_parity_three_lis_modules_and_skips():
+    og, od, pg, pd = _make_pair(16, 16, 8, 2, 32, 3, seed=12)
+    _run_steps(og, od, pg, pd, 8, 16, 16, 32, [(3, 2), (0, 0), (1, 3), (2, 1)], 1e-3)
+    for k, v in pg.state_dict().items():
+        assert rel_err(v, og.state_dict()[k]) <= 2e-3, k
+    for k, v in pd.state_dict().items():
+        assert rel_err(v, od.state_dict()[k]) <= 2e-3, k
+
+
+def test_step_parity_padded_nonsquare():
+    """W=20 (pads at level 1), H=12, three levels — the `w % 4 == 2` rule on one axis only."""
+    og, od, pg, pd = _make_pair(20, 12, 8, 3, 16, 1, seed=13)
+    _run_steps(og, od, pg, pd, 4, 12, 20, 16, [(1, 1), (1, 1)], 1e-3)
+    for k, v in pd.state_dict().items():
+        assert rel_err(v, od.state_dict()[k]) <= 2e-3, k
+
+
+def test_philox_generators():
+    from glis_b200 import ops
+    a = ops.randn_(torch.empty(1 << 20, device=DEV), seed=1234)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1) < 5e-3
+    assert abs((a ** 4).mean().item() - 3) < 0.1
+    b = ops.randn_(torch.empty(1 << 20, device=DEV), seed=1234)
+    assert torch.equal(a, b)                                      # counter-based: reproducible
+    c = ops.randn_(torch.empty(1 << 20, device=DEV), seed=1234, offset=1 << 18)
+    assert not torch.equal(a, c)
+    u = ops.uniform_(torch.empty(1 << 20, device=DEV), seed=7)
+    assert 0 <= u.min().item() and u.max().item() < 1 and abs(u.mean().item() - 0.5) < 2e-3
+
+
+def test_loss_kernels():
+    from glis_b200 import ops
+    lg = torch.randn(64, device=DEV) * 3
+    for t in (0.0, 1.0):
+        loss, dl, pr = ops.bce_logits(lg, t, want_prob=True)
+        l64 = lg.double().cpu().requires_grad_(True)
+        ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(l64), torch.full((64,), t, dtype=torch.float64))
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert rel_err(dl, l64.grad) <= 1e-5 and rel_err(pr, torch.sigmoid(l64)) <= 1e-6
+    u, z = torch.randn(64, 256, device=DEV), torch.randn(64, 256, device=DEV)
+    du = torch.zeros_like(u)
+    loss = ops.mse_scaled(u, z, 0.81, du)
+    assert abs(loss.item() - 0.81 * ((u - z) ** 2).mean().item()) <= 1e-5 * loss.item()
+    assert rel_err(du, 2 * 0.81 * (u - z) / u.numel()) <= 1e-6
+
+
+def test_rmsprop_kernel_matches_torch():
+    from glis_b200 import ops
+    n = 100003
+    p = torch.randn(n, device=DEV); g = torch.randn(n, device=DEV); v = torch.rand(n, device=DEV)
+    pr = p.clone().cpu().double().requires_grad_(True)
+    opt = torch.optim.RMSprop([pr], lr=1e-2, eps=1e-6, alpha=0.9)
+    opt.state[pr]["square_avg"] = v.cpu().double().clone(); opt.state[pr]["step"] = torch.tensor(0.)
+    pr.grad = g.cpu().double()
+    opt.step()
+    ops.rmsprop_(p, g, v, 1e-2, 0.9, 1e-6)
+    assert rel_err(p, pr) <= 1e-6 and rel_err(v, opt.state[pr]["square_avg"]) <= 1e-6

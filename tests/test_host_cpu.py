@@ -1,0 +1,127 @@
+"""CPU-side checks: the C ABI loads and exports everything the header declares, the host
+mirror of the reference API has the reference's names / shapes / keys, and the product
+refuses to run without CUDA (no silent fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from glis_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "glis_b200.h")).read()
+    declared = set(re.findall(r"\b(glis_[a-z0-9_]+)\s*\(", header))
+    declared -= {"glis_geom", "glis_epilogue"}
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python __graft_entry__.py"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.SIGNATURES) | {"glis_last_error", "glis_version"}
+    assert _lib.load().glis_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    from glis_b200 import _lib
+    assert ctypes.sizeof(_lib.Geom) == 16 * 4
+    assert ctypes.sizeof(_lib.Epilogue) == 5 * 8
+
+
+def test_error_convention_bad_args_no_gpu_needed():
+    from glis_b200 import _lib
+    lib = _lib.load()
+    rc = lib.glis_rmsprop(None, None, None, 10, 0.1, 0.9, 1e-6, 1.0, None)
+    assert rc == -1 and b"NULL" in lib.glis_last_error()
+    g = _lib.Geom()
+    rc = lib.glis_conv_forward(ctypes.byref(g), None, None, None, None, 0, None)
+    assert rc == -1 and b"relation" in lib.glis_last_error() or b"extent" in lib.glis_last_error()
+
+
+def test_product_keys_match_reference_catalogue(golden_dir):
+    from common.model import (GeneratorLearnedInputSpace, build_discriminator, build_generator,
+                              build_reverser)
+    z = np.load(os.path.join(golden_dir, "models.npz"))
+    builders = {
+        "D_16": lambda: build_discriminator(16, 16, 4, 2, "weight", 0),
+        "D_20x12_pad": lambda: build_discriminator(20, 12, 4, 3, "weight", 0),
+        "R_16": lambda: build_reverser(16, 16, 4, 2, 8, "weight", 0),
+        "G_16": lambda: build_generator(16, 16, 4, 2, 8, "weight"),
+        "G_20x12_pad": lambda: build_generator(20, 12, 4, 3, 8, "weight"),
+        "GLIS_16_k2of3": lambda: GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 3, "fractional"),
+        "GLIS_16_nearest": lambda: GeneratorLearnedInputSpace(16, 16, 4, 3, 8, "weight", 1, "nearest"),
+        "D_16_affine": lambda: build_discriminator(16, 16, 4, 2, "weight-affine", 0),
+    }
+    for case, build in builders.items():
+        want = {k[len(case) + 3:]: z[k].shape for k in z.files if k.startswith(case + "/p.")}
+        sd = build().state_dict()
+        assert sorted(sd) == sorted(want), case
+        for k in sd:
+            assert tuple(sd[k].shape) == want[k], (case, k)
+
+
+def test_state_dict_roundtrip_with_dotted_keys():
+    from common.model import build_discriminator
+    a, b = build_discriminator(16, 16, 4, 2, "weight", 0), build_discriminator(16, 16, 4, 2, "weight", 0)
+    b.load_state_dict(a.state_dict())
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    assert "level.0.conv.weight" in a.state_dict()
+
+
+def test_module_api_surface():
+    from common.modules import (TPReLU, View, WeightNormalizedConv2d, WeightNormalizedConvTranspose2d,
+                                WeightNormalizedLinear)
+    c = WeightNormalizedConv2d(3, 8, 4, 2, 1)
+    assert c.weight.shape == (8, 3, 4, 4) and c.scale.shape == (1, 8, 1, 1) and c.bias.shape == (1, 8, 1, 1)
+    assert c.weight_norm_factor == 1.0 and not c.transposed
+    t = WeightNormalizedConvTranspose2d(8, 3, 4, 2, 1, scale=False, bias=False)
+    assert t.weight.shape == (8, 3, 4, 4) and t.scale is None and t.bias is None
+    assert t.weight_norm_factor == 0.25 and t.transposed
+    l = WeightNormalizedLinear(5, 7, init_factor=0.01)
+    assert l.weight.shape == (7, 5) and l.scale.shape == (1, 7) and l.bias.shape == (1, 7)
+    assert float(l.weight.abs().max()) <= 0.01 / 5 ** 0.5 + 1e-9
+    p = TPReLU(6)
+    assert p.num_parameters == 6 and float(p.weight[0]) == 0.25 and float(p.bias.abs().sum()) == 0
+    v = View(2, 3)
+    assert v(torch.arange(12.).view(2, 6)).shape == (2, 2, 3)
+    assert "WeightNormalizedLinear (5 -> 7)" == repr(l)
+
+
+def test_builder_errors_match_reference():
+    from common.model import GeneratorLearnedInputSpace, build_discriminator
+    with pytest.raises(ValueError):
+        build_discriminator(15, 16, 4, 2, "weight", 0)
+    with pytest.raises(Exception):
+        GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 1, "cubic")
+    with pytest.raises(NotImplementedError):
+        build_discriminator(16, 16, 4, 2, "batch", 0)
+
+
+def test_no_cpu_fallback():
+    from common.modules import TPReLU, WeightNormalizedLinear
+    with pytest.raises(RuntimeError):
+        WeightNormalizedLinear(4, 4)(torch.zeros(2, 4))
+    with pytest.raises(RuntimeError):
+        TPReLU(4)(torch.zeros(2, 4))
+
+
+def test_lis_depth_rule_product():
+    from common.model import GeneratorLearnedInputSpace
+
+    class Seq(object):
+        def __init__(self, vals):
+            self.vals, self.n = list(vals), 0
+
+        def random(self):
+            self.n += 1
+            return self.vals.pop(0)
+
+    g = GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 3, "fractional")
+    g.rng = Seq([0.2, 0.2, 0.6]); assert g.lis_depth() == 1 and g.rng.n == 2
+    g.rng = Seq([0.9, 0.9, 0.9]); assert g.lis_depth() == 3
+    g.eval(); g.rng = Seq([0.0, 0.0, 0.0]); assert g.lis_depth() == 3
+    g.train(); g.rng = Seq([0.5] * 3); assert g.lis_depth(2) == 2 and g.rng.n == 3
