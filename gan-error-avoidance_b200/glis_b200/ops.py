@@ -138,6 +138,7 @@ class WNContraction(torch.autograd.Function):
         out = conv_forward(spec, L.TCONV if spec.transposed else L.CONV, xc, pack_io, shape, bias=b)
         ctx.spec = spec
         ctx.has_scale, ctx.has_bias = scale is not None, bias is not None
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.save_for_backward(xc, weight, scale, norm, pack_oi)
         return out
 
@@ -185,8 +186,8 @@ class WNContraction(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             dbias = torch.empty(cout, device=dyc.device, dtype=torch.float32)
             L.call("glis_channel_sum", L.ptr(dyc), L.ptr(dbias), dyc.numel(), cout, 1, 0, L.stream())
-            dbias = dbias.view(-1)
-        return dx, dw, dscale, (None if dbias is None else dbias), None
+            dbias = dbias.view(ctx.bias_shape)
+        return dx, dw, dscale, dbias, None
 
 
 def wn_contraction(x, weight, scale, bias, spec):
