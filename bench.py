@@ -162,6 +162,9 @@ def run_ours(args, rank, world, local):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: the product path needs a CUDA device (there is no CPU fallback)")
+    if args.precision:
+        _lib.set_precision(args.precision)
+    prec_name = [k for k, v in _lib.PRECISION_NAMES.items() if v == _lib.default_precision][0]
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     data_seed = dp.seed_everything(SEED, rank)
@@ -225,6 +228,9 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     _lib.timed.enabled = False
     per_kernel = _lib.timer_summary()
+    if args.kernel_table and rank == 0:
+        with open(args.kernel_table, "w") as fh:
+            json.dump({k: {"launches": c, "ms": m} for k, (c, m) in sorted(per_kernel.items())}, fh, indent=1)
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses
     h_real = torch.rand(B, 3, H, W).pin_memory()
@@ -255,7 +261,7 @@ def run_ours(args, rank, world, local):
     roofline = None
     if fam:
         def flops(tag):
-            dims = dict(kv.split("=") for kv in tag.split()[1:])
+            dims = dict(kv.split("=") for kv in tag.split() if "=" in kv)
             return 2.0 * int(dims["M"]) * int(dims["N"]) * int(dims["K"])
         top = max(fam.items(), key=lambda kv: kv[1][0] * kv[1][1])
         tag, (cnt, ms) = top
@@ -279,9 +285,11 @@ def run_ours(args, rank, world, local):
     print(json.dumps({
         "metric": "G-LIS train images/sec at 80x80 bs64/GPU", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32-faithful) + f32", "bf16": "bf16"}[prec_name],
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "lis_depth": "all", "precision": "fp32 FFMA contractions",
+                   "lis_depth": "all", "precision": prec_name,
                    "l2": "inputs larger than L2: ~%.0f MB of activations + 36 MB of weights touched per step"
                          % act_mb,
                    "gflop_per_step": GFLOP_PER_STEP,
@@ -299,6 +307,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

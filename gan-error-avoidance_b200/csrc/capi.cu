@@ -1,6 +1,8 @@
 // C-ABI dispatch for the convolution-shaped entry points + error plumbing.
 #include <stdarg.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace glis {
@@ -17,6 +19,12 @@ void set_error(const char* fmt, ...) {
 int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                       float* out, cudaStream_t st);
 int simt_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st);
+
+int tc_conv_supported(const glis_geom_t* g);
+int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                    __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
+int split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t numel, cudaStream_t st);
 
 }  // namespace glis
 
@@ -57,4 +65,33 @@ extern "C" int glis_conv_wgrad(const glis_geom_t* g, const float* small, const f
       set_error("glis_conv_wgrad: precision %d needs the split-bf16 entry points", precision);
       return GLIS_E_UNSUPPORTED;
   }
+}
+
+extern "C" int glis_conv_tc_supported(const glis_geom_t* g) {
+  if (validate_geom(g, "glis_conv_tc_supported") != GLIS_OK) return 0;
+  return tc_conv_supported(g);
+}
+
+extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x_lo, const void* w_hi,
+                                      const void* w_lo, const glis_epilogue_t* ep, float* out_f32, void* out_hi,
+                                      void* out_lo, int precision, void* stream) {
+  int rc = validate_geom(g, "glis_conv_forward_bf16");
+  if (rc != GLIS_OK) return rc;
+  GLIS_REQUIRE(precision == GLIS_PREC_BF16X3 || precision == GLIS_PREC_BF16, GLIS_E_BADARG,
+               "glis_conv_forward_bf16: precision must be GLIS_PREC_BF16X3 or GLIS_PREC_BF16");
+  GLIS_REQUIRE(out_f32 || out_hi, GLIS_E_BADARG, "glis_conv_forward_bf16: no output tensor");
+  glis_epilogue_t none = {nullptr, GLIS_ACT_NONE, nullptr, nullptr, nullptr};
+  if (!ep) ep = &none;
+  GLIS_REQUIRE(ep->act == GLIS_ACT_NONE || ep->act == GLIS_ACT_SIGMOID ||
+                   (ep->act == GLIS_ACT_TPRELU && ep->act_a && ep->act_b),
+               GLIS_E_BADARG, "glis_conv_forward_bf16: bad activation descriptor");
+  return tc_conv_forward(g, (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (const __nv_bfloat16*)w_hi,
+                         (const __nv_bfloat16*)w_lo, ep, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                         precision, (cudaStream_t)stream);
+}
+
+extern "C" int glis_split_bf16(const float* x, void* hi, void* lo, int64_t numel, void* stream) {
+  GLIS_REQUIRE(x && hi && numel >= 0, GLIS_E_BADARG, "glis_split_bf16: bad arguments");
+  if (numel == 0) return GLIS_OK;
+  return split_planes(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, numel, (cudaStream_t)stream);
 }

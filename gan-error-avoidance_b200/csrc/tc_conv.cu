@@ -1,0 +1,405 @@
+// tcgen05 implicit-GEMM convolution / transposed convolution (forward and data gradient).
+//
+//   D[co, pix] = sum_{tap} sum_{ci}  W[tap][co][ci] * X[gather(pix, tap)][ci]
+//
+// M = 128 output channels (TMEM lanes), N = one tile of output pixels (<= 256 TMEM columns),
+// K walked as (tap, 64-channel block).  Both operands are K-major bf16 in 128-byte-swizzled
+// shared memory, staged by TMA:
+//   * weights  : 3-D map (Ci, Co, taps), box 64 x 128 x 1;
+//   * pixels   : the NHWC activation tensor seen through a map whose box IS the im2col
+//                gather of one tap — for the strided (GLIS_CONV) relation a 5-D view
+//                (stride*C, W/stride, stride, H/stride, N) in which a tap is a fixed
+//                (parity, shift) pair; for the transposed (GLIS_TCONV) relation the plain
+//                4-D (C, W, H, N) view shifted by the tap, one launch slice per output phase.
+//     Zero padding is TMA out-of-bounds fill; ragged channel counts likewise.
+// fp32 fidelity comes from a bf16 hi/lo split of both operands: three MMAs per k-step
+// (hi*hi + hi*lo + lo*hi), ~2^-16 relative (GLIS_PREC_BF16X3); one MMA in GLIS_PREC_BF16.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias / TPReLU / sigmoid -> global, plus the
+// optional bf16 hi/lo planes the next tensor-core layer consumes).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace glis {
+
+using namespace sm100;
+
+constexpr int TC_BM = 128;       // channels per CTA (UMMA M)
+constexpr int TC_BK = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 4;
+
+struct TcConvParams {
+  glis_geom_t g;
+  int tw, th, tn;    // pixel tile on the (phase) output grid; tw spans the full width
+  int n_mma;         // UMMA N: tw*th*tn rounded up to 16
+  int tmem_cols;     // power of two >= n_mma
+  int kblocks;       // ceil(Ci / 64)
+  int passes;        // 3 (bf16x3) or 1
+  int stages;
+  int tiles_h;       // ceil(Hq_max / th)
+  const float* bias; int act; const float* act_a; const float* act_b;
+  float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+};
+
+struct TcPhase { int ry, rx, Hq, Wq, nth, ntw, py, px; };
+
+__device__ __forceinline__ TcPhase tc_phase(const glis_geom_t& g, int z) {
+  TcPhase p;
+  if (g.relation == GLIS_CONV) {
+    p.ry = p.rx = 0; p.Hq = g.Ho; p.Wq = g.Wo; p.nth = g.KH; p.ntw = g.KW; p.py = p.px = 0;
+  } else {
+    p.py = z / g.stride_w; p.px = z % g.stride_w;
+    p.ry = ((p.py - g.pad_h) % g.stride_h + g.stride_h) % g.stride_h;
+    p.rx = ((p.px - g.pad_w) % g.stride_w + g.stride_w) % g.stride_w;
+    p.Hq = g.Ho > p.ry ? (g.Ho - p.ry + g.stride_h - 1) / g.stride_h : 0;
+    p.Wq = g.Wo > p.rx ? (g.Wo - p.rx + g.stride_w - 1) / g.stride_w : 0;
+    p.nth = g.KH > p.py ? (g.KH - p.py + g.stride_h - 1) / g.stride_h : 0;
+    p.ntw = g.KW > p.px ? (g.KW - p.px + g.stride_w - 1) / g.stride_w : 0;
+  }
+  return p;
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+  int q = a / b;
+  return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+               const TcConvParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const glis_geom_t& g = P.g;
+  const TcPhase ph = tc_phase(g, blockIdx.z);
+  const int tile_h = blockIdx.x % P.tiles_h, tile_n = blockIdx.x / P.tiles_h;
+  const int qy0 = tile_h * P.th, n0 = tile_n * P.tn;
+  const int co0 = blockIdx.y * TC_BM;
+  const int ntaps = ph.nth * ph.ntw;
+  const int ksteps = ntaps * P.kblocks;
+  const bool empty_tile = (qy0 >= ph.Hq) || ph.Wq <= 0 || ksteps == 0;
+
+  // ---- shared memory carve-up (1024-byte aligned operand tiles)
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)P.n_mma * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + TC_MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
+    if (P.passes == 3) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (!empty_tile) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        const uint32_t box_rows = (uint32_t)(P.tw * P.th * P.tn);
+        const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + box_rows * 128u);
+        int s = 0; uint32_t parity = 0;
+        for (int t = 0; t < ntaps; ++t) {
+          const int jh = t / ph.ntw, jw = t - jh * ph.ntw;
+          int kh, kw, cpar = 0, c1, c2 = 0, c3;
+          if (g.relation == GLIS_CONV) {
+            kh = jh; kw = jw;
+            const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
+            const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
+            const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
+            cpar = parx * g.Ci;
+            c1 = (ex - parx) / g.stride_w;          // + qx0 (= 0)
+            c2 = pary;
+            c3 = qy0 + (ey - pary) / g.stride_h;
+          } else {
+            kh = ph.py + jh * g.stride_h; kw = ph.px + jw * g.stride_w;
+            c1 = (ph.rx + g.pad_w - kw) / g.stride_w;   // exact inside a phase
+            c3 = qy0 + (ph.ry + g.pad_h - kh) / g.stride_h;
+          }
+          const int tap = kh * g.KW + kw;
+          for (int kb = 0; kb < P.kblocks; ++kb) {
+            mbar_wait(&empty_bar[s], parity ^ 1);
+            uint8_t* st = base + (size_t)s * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, co0, tap);
+            if (g.relation == GLIS_CONV)
+              tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, n0);
+            else
+              tma_load_4d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], kb * TC_BK, c1, c3, n0);
+            if (P.passes == 3) {
+              tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, co0, tap);
+              if (g.relation == GLIS_CONV)
+                tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, n0);
+              else
+                tma_load_4d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], kb * TC_BK, c1, c3, n0);
+            }
+            if (++s == P.stages) { s = 0; parity ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, P.n_mma, 0, 0);
+        int s = 0; uint32_t parity = 0;
+        uint32_t accumulate = 0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[s], parity);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(base + (size_t)s * stage_bytes), a_lo = a_hi + a_bytes;
+          const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            const uint32_t off = kk * 32;  // 16 bf16 along K inside the swizzled 128-byte row
+            const uint64_t dah = umma_smem_desc(a_hi + off, 16, 1024), dbh = umma_smem_desc(b_hi + off, 16, 1024);
+            if (P.passes == 3) {
+              const uint64_t dal = umma_smem_desc(a_lo + off, 16, 1024), dbl = umma_smem_desc(b_lo + off, 16, 1024);
+              umma_bf16(tmem_base, dah, dbl, idesc, accumulate);
+              umma_bf16(tmem_base, dal, dbh, idesc, 1);
+              umma_bf16(tmem_base, dah, dbh, idesc, 1);
+            } else {
+              umma_bf16(tmem_base, dah, dbh, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          if (++s == P.stages) { s = 0; parity ^= 1; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      // ===================== epilogue (warps 2..5) =====================
+      const int q = warp & 3;  // TMEM lane quarter this warp may access
+      const int co = co0 + q * 32 + lane;
+      const bool ch_ok = co < g.Co;
+      float bias = 0.f, ta = 0.f, tb = 0.f;
+      if (ch_ok) {
+        if (P.bias) bias = __ldg(P.bias + co);
+        if (P.act == GLIS_ACT_TPRELU) { ta = __ldg(P.act_a + co); tb = __ldg(P.act_b + co); }
+      }
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+      const int cols = P.tw * P.th * P.tn;
+      const int per_img = P.tw * P.th;
+      for (int cb = 0; cb < cols; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = cb + j;
+          const int in_ = col / per_img, r = col - in_ * per_img;
+          const int ih = r / P.tw, iw = r - ih * P.tw;
+          const int n = n0 + in_, qy = qy0 + ih, qx = iw;
+          const bool ok = ch_ok && col < cols && n < g.N && qy < ph.Hq && qx < ph.Wq;
+          if (ok) {
+            int oy = qy, ox = qx;
+            if (g.relation == GLIS_TCONV) { oy = qy * g.stride_h + ph.ry; ox = qx * g.stride_w + ph.rx; }
+            const size_t idx = (((size_t)n * g.Ho + oy) * g.Wo + ox) * g.Co + co;
+            const float y = __uint_as_float(v[j]) + bias;
+            if (P.preact) P.preact[idx] = y;
+            float o = y;
+            if (P.act == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
+            else if (P.act == GLIS_ACT_SIGMOID) { o = 1.f / (1.f + __expf(-y)); }
+            if (P.out_f32) P.out_f32[idx] = o;
+            if (P.out_hi) {
+              __nv_bfloat16 hi, lo;
+              split_bf16(o, hi, lo);
+              P.out_hi[idx] = hi;
+              if (P.out_lo) P.out_lo[idx] = lo;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// fp32 -> bf16 hi/lo planes (same element order)
+__global__ void split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t numel) {
+  const int64_t n4 = numel >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, l;
+    split_bf16(x[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;  // benign race: every thread resolves the same pointer
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first;
+// strides in bytes for dims 1..rank-1.
+int make_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  GLIS_REQUIRE(enc != nullptr, GLIS_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GLIS_REQUIRE(r == CUDA_SUCCESS, GLIS_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return GLIS_OK;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Reasons the tensor-core path does not apply (the caller then uses the fp32 kernel).
+int tc_conv_supported(const glis_geom_t* g) {
+  if (g->Ci % TC_BK != 0) return 0;                       // K blocks of 64 channels
+  if (g->dil_h != 1 || g->dil_w != 1) return 0;
+  if (g->relation == GLIS_CONV) {
+    if (g->Hi % g->stride_h != 0 || g->Wi % g->stride_w != 0) return 0;  // parity view of the input
+    if ((int64_t)g->stride_w * g->Ci > 0x7fffffff) return 0;
+  }
+  int Wq = g->Wo;
+  if (g->relation == GLIS_TCONV) Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
+  if (Wq > 128) return 0;                                 // one tile row must fit the MMA N
+  if (g->KH * g->KW * (g->Ci / TC_BK) < 1) return 0;
+  return 1;
+}
+
+int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                    __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st) {
+  GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: geometry not tileable for tcgen05");
+  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
+  GLIS_REQUIRE(x_hi && w_hi && (passes == 1 || (x_lo && w_lo)), GLIS_E_BADARG,
+               "glis_conv_forward_bf16: missing hi/lo operand planes");
+  TcConvParams P;
+  P.g = *g;
+  int nphase = 1, Hq = g->Ho, Wq = g->Wo;
+  if (g->relation == GLIS_TCONV) {
+    nphase = g->stride_h * g->stride_w;
+    Hq = (g->Ho + g->stride_h - 1) / g->stride_h;
+    Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
+  }
+  // ---- pixel tile: full rows; whole images when they are small
+  const int NMAX = 128;
+  P.tw = Wq;
+  if (Wq * Hq <= NMAX) {
+    P.th = Hq;
+    P.tn = NMAX / (Wq * Hq);
+    if (P.tn > g->N) P.tn = g->N;
+  } else {
+    P.tn = 1;
+    int best_th = 1; long best_cost = -1;
+    for (int th = 1; th <= NMAX / Wq && th <= Hq; ++th) {
+      const long cost = (long)((Hq + th - 1) / th) * (round_up(Wq * th, 16) + 24);  // +24: per-tile fixed cost
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
+    }
+    P.th = best_th;
+  }
+  P.n_mma = round_up(P.tw * P.th * P.tn, 16);
+  P.tmem_cols = 32;
+  while (P.tmem_cols < P.n_mma) P.tmem_cols *= 2;
+  P.kblocks = g->Ci / TC_BK;
+  P.passes = passes;
+  P.tiles_h = (Hq + P.th - 1) / P.th;
+  const int tiles_n = (g->N + P.tn - 1) / P.tn;
+  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: tile does not fit shared memory");
+  P.stages = stages;
+  P.bias = ep->bias; P.act = ep->act; P.act_a = ep->act_a; P.act_b = ep->act_b; P.preact = ep->preact;
+  P.out_f32 = out_f32; P.out_hi = out_hi; P.out_lo = out_lo;
+
+  // ---- tensor maps
+  CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;
+  const int T = g->KH * g->KW;
+  {
+    const uint64_t dims[3] = {(uint64_t)g->Ci, (uint64_t)g->Co, (uint64_t)T};
+    const uint64_t strides[2] = {(uint64_t)g->Ci * 2, (uint64_t)g->Ci * g->Co * 2};
+    const uint32_t box[3] = {TC_BK, TC_BM, 1};
+    int rc = make_bf16_map(&mw_hi, w_hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_bf16_map(&mw_lo, passes == 3 ? w_lo : w_hi, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (g->relation == GLIS_CONV) {
+    const uint64_t C = g->Ci, W = g->Wi, H = g->Hi, sw = g->stride_w, sh = g->stride_h;
+    const uint64_t dims[5] = {sw * C, W / sw, sh, H / sh, (uint64_t)g->N};
+    const uint64_t strides[4] = {sw * C * 2, W * C * 2, sh * W * C * 2, H * W * C * 2};
+    const uint32_t box[5] = {TC_BK, (uint32_t)P.tw, 1, (uint32_t)P.th, (uint32_t)P.tn};
+    int rc = make_bf16_map(&mx_hi, x_hi, 5, dims, strides, box);
+    if (rc) return rc;
+    rc = make_bf16_map(&mx_lo, passes == 3 ? x_lo : x_hi, 5, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    const uint64_t C = g->Ci, W = g->Wi, H = g->Hi;
+    const uint64_t dims[4] = {C, W, H, (uint64_t)g->N};
+    const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const uint32_t box[4] = {TC_BK, (uint32_t)P.tw, (uint32_t)P.th, (uint32_t)P.tn};
+    int rc = make_bf16_map(&mx_hi, x_hi, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_bf16_map(&mx_lo, passes == 3 ? x_lo : x_hi, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_kernel): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(P.tiles_h * tiles_n, (g->Co + TC_BM - 1) / TC_BM, nphase);
+  tc_conv_kernel<<<grid, TC_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);
+  GLIS_CHECK_LAUNCH("glis_conv_forward_bf16");
+  return GLIS_OK;
+}
+
+int split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t numel, cudaStream_t st) {
+  int blocks = (int)((numel / 4 + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  split_planes_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, numel);
+  GLIS_CHECK_LAUNCH("glis_split_bf16");
+  return GLIS_OK;
+}
+
+}  // namespace glis

@@ -3,6 +3,7 @@
 //   backward: dw[o] = (s/n)(G[o] - c w[o] <G[o],w[o]>/n^2),  ds[o] = <G[o],w[o]>/n
 // (closed forms: SURVEY.md App. E; reference: WeightNormalizedConv.py:29-49, WeightNormalizedLinear.py:30-39)
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace glis {
 
@@ -54,6 +55,34 @@ __global__ void wn_pack_kernel(const float* __restrict__ w, const float* __restr
   }
 }
 
+// bf16 hi/lo packs for the tensor-core kernels (K-major operands):
+//   fwd [t][o][i] for the launch that reads Cin and writes Cout, bwd [t][i][o] for its data gradient.
+__global__ void wn_pack_bf16_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                    const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T,
+                                    __nv_bfloat16* __restrict__ fwd_hi, __nv_bfloat16* __restrict__ fwd_lo,
+                                    __nv_bfloat16* __restrict__ bwd_hi, __nv_bfloat16* __restrict__ bwd_lo) {
+  const int64_t total = (int64_t)T * Cin * Cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    if (fwd_hi) {  // [t][o][i]
+      const int i = (int)(e % Cin); const int64_t r = e / Cin; const int o = (int)(r % Cout); const int t = (int)(r / Cout);
+      const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
+      __nv_bfloat16 h, l;
+      sm100::split_bf16(__ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a, h, l);
+      fwd_hi[e] = h;
+      if (fwd_lo) fwd_lo[e] = l;
+    }
+    if (bwd_hi) {  // [t][i][o]
+      const int o = (int)(e % Cout); const int64_t r = e / Cout; const int i = (int)(r % Cin); const int t = (int)(r / Cin);
+      const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
+      __nv_bfloat16 h, l;
+      sm100::split_bf16(__ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a, h, l);
+      bwd_hi[e] = h;
+      if (bwd_lo) bwd_lo[e] = l;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(WN_NT)
 wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                   const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
@@ -96,6 +125,26 @@ extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis,
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
     wn_pack_kernel<<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi);
     GLIS_CHECK_LAUNCH("glis_wn_prepare(pack)");
+  }
+  return GLIS_OK;
+}
+
+extern "C" int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                                    float c, float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo,
+                                    void* stream) {
+  GLIS_REQUIRE(w && norm, GLIS_E_BADARG, "glis_wn_prepare_bf16: w/norm is NULL");
+  GLIS_REQUIRE(Cout > 0 && Cin > 0 && T > 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
+               "glis_wn_prepare_bf16: bad shape (Cout=%d Cin=%d T=%d axis=%d)", Cout, Cin, T, out_axis);
+  GLIS_REQUIRE((fwd_hi || !fwd_lo) && (bwd_hi || !bwd_lo), GLIS_E_BADARG, "glis_wn_prepare_bf16: lo plane without hi");
+  cudaStream_t st = (cudaStream_t)stream;
+  wn_norm_kernel<<<Cout, WN_NT, 0, st>>>(w, out_axis, Cout, Cin, T, c, norm);
+  GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(norm)");
+  if (fwd_hi || bwd_hi) {
+    const int64_t total = (int64_t)T * Cin * Cout;
+    const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+    wn_pack_bf16_kernel<<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
+                                               (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi, (__nv_bfloat16*)bwd_lo);
+    GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(pack)");
   }
   return GLIS_OK;
 }

@@ -36,6 +36,10 @@ SIGNATURES = {
     "glis_wn_project": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "glis_conv_forward": [C.POINTER(Geom), _vp, _vp, C.POINTER(Epilogue), _vp, _i, _vp],
     "glis_conv_wgrad": [C.POINTER(Geom), _vp, _vp, _vp, _i, _vp],
+    "glis_split_bf16": [_vp, _vp, _vp, _i64, _vp],
+    "glis_wn_prepare_bf16": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "glis_conv_tc_supported": [C.POINTER(Geom)],
+    "glis_conv_forward_bf16": [C.POINTER(Geom), _vp, _vp, _vp, _vp, C.POINTER(Epilogue), _vp, _vp, _vp, _i, _vp],
     "glis_tprelu_forward": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_tprelu_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_channel_sum": [_vp, _vp, _i64, _i, _i, _i, _vp],
@@ -96,6 +100,26 @@ KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 
 launch_count = 0     # kernels this process enqueued through the C ABI
 _timers = {}         # tag -> list of (start_event, end_event); see `timed`
+
+
+def ptr16(t):
+    """Device pointer of a dense bf16 CUDA tensor (or NULL for None)."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.bfloat16:
+        raise RuntimeError("glis_b200: expected a CUDA bfloat16 plane")
+    return C.c_void_p(t.data_ptr())
+
+
+PRECISION_NAMES = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+default_precision = PRECISION_NAMES[os.environ.get("GLIS_PRECISION", "bf16x3")]
+
+
+def set_precision(name):
+    """Contraction arithmetic of the layers that tile for tcgen05: 'fp32' (FFMA everywhere),
+    'bf16x3' (split-bf16, fp32-faithful; default) or 'bf16' (single pass)."""
+    global default_precision
+    default_precision = PRECISION_NAMES[name]
 
 
 def call(name, *args, kernels=None):

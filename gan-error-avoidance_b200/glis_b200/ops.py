@@ -35,11 +35,15 @@ class ContractionSpec(object):
     """Static description of one WN layer's contraction (conv / transposed conv / linear)."""
 
     def __init__(self, transposed, kernel_size, stride, padding, dilation, output_padding=(0, 0),
-                 linear=False, precision=L.PREC_FP32):
+                 linear=False, precision=None):
         self.transposed, self.linear = bool(transposed), bool(linear)
         self.kernel_size, self.stride, self.padding = tuple(kernel_size), tuple(stride), tuple(padding)
         self.dilation, self.output_padding = tuple(dilation), tuple(output_padding)
-        self.precision = precision
+        self._precision = precision
+
+    @property
+    def precision(self):
+        return L.default_precision if self._precision is None else self._precision
 
     @property
     def norm_factor(self):
@@ -86,9 +90,40 @@ def wn_prepare(weight, scale, spec, want_io=True, want_oi=True):
     return norm, io, oi
 
 
-def conv_forward(spec, relation, x_nhwc, wpack, out_shape_nchw, bias=None, act=L.ACT_NONE,
-                 act_a=None, act_b=None, preact=None):
-    """Launch one gather-GEMM; ``x_nhwc`` and the result are NHWC-dense (or 2-D)."""
+def wn_prepare_bf16(weight, scale, spec, want_fwd=True, want_bwd=True, lo=True):
+    """norm [Cout] and K-major bf16 (hi, lo) packs: fwd [T][Cout][Cin], bwd [T][Cin][Cout]."""
+    out_axis = 1 if spec.transposed else 0
+    cout, cin = weight.shape[out_axis], weight.shape[1 - out_axis]
+    t = weight.numel() // (cout * cin)
+    w = weight.detach().contiguous()
+    dev = w.device
+    norm = torch.empty(cout, device=dev, dtype=torch.float32)
+
+    def plane(shape, want):
+        return torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
+
+    fh, fl = plane((t, cout, cin), want_fwd), plane((t, cout, cin), want_fwd and lo)
+    bh, bl = plane((t, cin, cout), want_bwd), plane((t, cin, cout), want_bwd and lo)
+    sc = None if scale is None else scale.detach().contiguous()
+    L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), out_axis, cout, cin, t, spec.norm_factor, L.ptr(norm),
+           L.ptr16(fh), L.ptr16(fl), L.ptr16(bh), L.ptr16(bl), L.stream(),
+           kernels=2 if (want_fwd or want_bwd) else 1)
+    return norm, (fh, fl), (bh, bl)
+
+
+def split_bf16(x, lo=True):
+    """(hi, lo) bf16 planes of a dense fp32 tensor, same memory order."""
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo_t = torch.empty_like(x, dtype=torch.bfloat16) if lo else None
+    L.call("glis_split_bf16", L.ptr(x), L.ptr16(hi), L.ptr16(lo_t), x.numel(), L.stream())
+    return hi, lo_t
+
+
+def tc_supported(g):
+    return bool(L.load().glis_conv_tc_supported(C.byref(g)))
+
+
+def _launch_geom(spec, relation, x_nhwc, out_shape_nchw):
     if x_nhwc.dim() == 4:
         n, ci, hi, wi = x_nhwc.shape
         _, co, ho, wo = out_shape_nchw
@@ -98,14 +133,45 @@ def conv_forward(spec, relation, x_nhwc, wpack, out_shape_nchw, bias=None, act=L
         hi = wi = ho = wo = 1
         co = out_shape_nchw[1]
         out = torch.empty((n, co), device=x_nhwc.device, dtype=torch.float32)
-    g = spec.geom(relation, n, hi, wi, ci, ho, wo, co)
+    return spec.geom(relation, n, hi, wi, ci, ho, wo, co), out
+
+
+def _tag(relation, g):
+    if relation == L.CONV:
+        return "conv_forward M=%d N=%d K=%d" % (g.N * g.Ho * g.Wo, g.Co, g.Ci * g.KH * g.KW)
+    return "tconv_forward M=%d N=%d K=%d" % (g.N * g.Hi * g.Wi, g.Co * g.KH * g.KW, g.Ci)
+
+
+def conv_forward(spec, relation, x_nhwc, wpack, out_shape_nchw, bias=None, act=L.ACT_NONE,
+                 act_a=None, act_b=None, preact=None):
+    """fp32 FFMA gather-GEMM; ``x_nhwc`` and the result are NHWC-dense (or 2-D)."""
+    g, out = _launch_geom(spec, relation, x_nhwc, out_shape_nchw)
     ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact))
-    with L.timed("conv_forward M=%d N=%d K=%d" % (n * ho * wo, co, ci * g.KH * g.KW)
-                 if relation == L.CONV else
-                 "tconv_forward M=%d N=%d K=%d" % (n * hi * wi, co * g.KH * g.KW, ci)):
+    with L.timed(_tag(relation, g) + " fp32"):
         L.call("glis_conv_forward", C.byref(g), L.ptr(x_nhwc), L.ptr(wpack), C.byref(ep), L.ptr(out),
-               spec.precision, L.stream())
+               L.PREC_FP32, L.stream())
     return out
+
+
+def conv_forward_tc(spec, relation, x_planes, wpack_planes, out_shape_nchw, like, precision, bias=None,
+                    act=L.ACT_NONE, act_a=None, act_b=None, preact=None):
+    """tcgen05 implicit GEMM on split-bf16 planes; returns the fp32 NHWC result."""
+    g, out = _launch_geom(spec, relation, like, out_shape_nchw)
+    ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact))
+    with L.timed(_tag(relation, g) + " tc"):
+        L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(x_planes[0]), L.ptr16(x_planes[1]),
+               L.ptr16(wpack_planes[0]), L.ptr16(wpack_planes[1]), C.byref(ep), L.ptr(out), None, None,
+               precision, L.stream())
+    return out
+
+
+def _use_tc(spec, relation, in_shape, out_shape):
+    """Whether the launch reading NCHW-shaped ``in_shape`` and writing ``out_shape`` runs on tcgen05."""
+    if spec.precision == L.PREC_FP32 or len(in_shape) != 4:
+        return False  # batch-sized linears stay on the FFMA kernel
+    n, ci, hi, wi = in_shape
+    _, co, ho, wo = out_shape
+    return tc_supported(spec.geom(relation, n, hi, wi, ci, ho, wo, co))
 
 
 class WNContraction(torch.autograd.Function):
@@ -121,7 +187,6 @@ class WNContraction(torch.autograd.Function):
     def forward(ctx, x, weight, scale, bias, spec):
         xc = _nhwc(x)
         need_dx = ctx.needs_input_grad[0]
-        norm, pack_io, pack_oi = wn_prepare(weight, scale, spec, True, need_dx)
         out_axis = 1 if spec.transposed else 0
         cout = weight.shape[out_axis]
         if xc.dim() == 4:
@@ -135,16 +200,31 @@ class WNContraction(torch.autograd.Function):
             raise RuntimeError("glis_b200: input has %d channels, weight expects %d"
                                % (ci, weight.shape[1 - out_axis]))
         b = None if bias is None else bias.detach().reshape(-1).contiguous()
-        out = conv_forward(spec, L.TCONV if spec.transposed else L.CONV, xc, pack_io, shape, bias=b)
-        ctx.spec = spec
+        rel_f = L.TCONV if spec.transposed else L.CONV
+        rel_b = L.CONV if spec.transposed else L.TCONV
+        prec = spec.precision
+        tc_f = _use_tc(spec, rel_f, tuple(xc.shape), shape)
+        tc_b = need_dx and _use_tc(spec, rel_b, shape, tuple(xc.shape))
+        lo = prec == L.PREC_BF16X3
+        pack_oi = bwd_planes = None
+        if tc_f or tc_b:
+            norm, fwd_planes, bwd_planes = wn_prepare_bf16(weight, scale, spec, tc_f, tc_b, lo)
+        if not tc_f or (need_dx and not tc_b):
+            norm, pack_io, pack_oi = wn_prepare(weight, scale, spec, not tc_f, need_dx and not tc_b)
+        if tc_f:
+            out = conv_forward_tc(spec, rel_f, split_bf16(xc, lo), fwd_planes, shape, xc, prec, bias=b)
+        else:
+            out = conv_forward(spec, rel_f, xc, pack_io, shape, bias=b)
+        ctx.spec, ctx.tc_b, ctx.prec = spec, tc_b, prec
         ctx.has_scale, ctx.has_bias = scale is not None, bias is not None
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
-        ctx.save_for_backward(xc, weight, scale, norm, pack_oi)
+        saved_b = bwd_planes if tc_b else (None, None)
+        ctx.save_for_backward(xc, weight, scale, norm, pack_oi, saved_b[0], saved_b[1])
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        xc, weight, scale, norm, pack_oi = ctx.saved_tensors
+        xc, weight, scale, norm, pack_oi, bwd_hi, bwd_lo = ctx.saved_tensors
         spec = ctx.spec
         dyc = _nhwc(dy)
         out_axis = 1 if spec.transposed else 0
@@ -160,7 +240,11 @@ class WNContraction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
             rel = L.CONV if spec.transposed else L.TCONV
-            dx = conv_forward(spec, rel, dyc, pack_oi, tuple(xc.shape))
+            if ctx.tc_b:
+                dx = conv_forward_tc(spec, rel, split_bf16(dyc, ctx.prec == L.PREC_BF16X3), (bwd_hi, bwd_lo),
+                                     tuple(xc.shape), dyc, ctx.prec)
+            else:
+                dx = conv_forward(spec, rel, dyc, pack_oi, tuple(xc.shape))
 
         dw = dscale = dbias = None
         if ctx.needs_input_grad[1] or (ctx.has_scale and ctx.needs_input_grad[2]):
@@ -171,8 +255,8 @@ class WNContraction(torch.autograd.Function):
             else:                 # small = dy (Cout), big = x (Cin)
                 g = spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
                 small, big = dyc, xc
-            with L.timed("conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)):
-                L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), spec.precision,
+            with L.timed("conv_wgrad M=%d N=%d K=%d fp32" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)):
+                L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
                        L.stream())
             dw = torch.empty_like(graw)
             if ctx.has_scale:

@@ -102,6 +102,32 @@ int glis_wn_project(const float* G, const float* w, const float* scale, const fl
 int glis_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
                       const glis_epilogue_t* ep, float* out, int precision, void* stream);
 
+/* ---- tensor-core (tcgen05) contractions on split-bf16 operands -----------------------
+ * An fp32 value x is carried as two bf16 planes hi = bf16(x), lo = bf16(x - hi) with the same
+ * element order (NHWC).  GLIS_PREC_BF16X3 multiplies (hi+lo)*(hi+lo) minus the lo*lo term with
+ * three MMAs per k-step (~2^-16 relative, the fp32-faithful mode); GLIS_PREC_BF16 uses hi only. */
+
+/* fp32 -> hi/lo planes (lo may be NULL). */
+int glis_split_bf16(const float* x, void* hi, void* lo, int64_t numel, void* stream);
+
+/* As glis_wn_prepare, but emitting K-major bf16 packs: fwd [T][Cout][Cin] for the launch that
+ * reads Cin and writes Cout, bwd [T][Cin][Cout] for its data gradient (any may be NULL). */
+int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                         float c, float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo,
+                         void* stream);
+
+/* 1 if glis_conv_forward_bf16 can tile this geometry (Ci % 64 == 0, no dilation, input
+ * divisible by the stride for GLIS_CONV, output rows <= 128 pixels), else 0. */
+int glis_conv_tc_supported(const glis_geom_t* g);
+
+/* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
+ * TMEM, epilogue fused.  x planes [N,Hi,Wi,Ci] bf16, w packs [KH*KW][Co][Ci] bf16.  Outputs
+ * (each optional, at least one of out_f32 / out_hi): fp32 NHWC, and the hi/lo planes of the
+ * activated output for the next tensor-core layer. */
+int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x_lo, const void* w_hi,
+                           const void* w_lo, const glis_epilogue_t* ep, float* out_f32, void* out_hi,
+                           void* out_lo, int precision, void* stream);
+
 /* Raw weight gradient in master layout: G[a][b][tap] = sum_pix small[pix][a] * big[pix*s-p+k][b].
  * conv layer:  small = dy (Ca=Cout), big = x (Cb=Cin);  transposed: small = x (Ca=Cin), big = dy.
  * `g` describes the gather small(out grid: Ho,Wo,Co=Ca) <- big(Hi,Wi,Ci=Cb), relation GLIS_CONV.
