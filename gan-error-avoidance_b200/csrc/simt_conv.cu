@@ -40,14 +40,20 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 
 __global__ void __launch_bounds__(NT)
 gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __restrict__ wp,
-                const glis_epilogue_t ep, float* __restrict__ out) {
-  const PhaseInfo ph = decode_phase(g, blockIdx.z);
+                const glis_epilogue_t ep, float* __restrict__ out, int ksplit, int k_per_split) {
+  // blockIdx.z = phase * ksplit + split; with ksplit > 1 the partial sums are added atomically
+  // into a zero-filled `out` (only used when the epilogue is bias-only).
+  const int split = blockIdx.z % ksplit;
+  const PhaseInfo ph = decode_phase(g, blockIdx.z / ksplit);
   const int P = g.N * ph.Hq * ph.Wq;  // output pixels of this phase
   const int m0 = blockIdx.x * BM;
   if (m0 >= P) return;
   const int n0 = blockIdx.y * BN;
   const int ntaps = ph.nth * ph.ntw;
-  const int K = ntaps * g.Ci;
+  const int Kall = ntaps * g.Ci;
+  const int kbeg = split * k_per_split;
+  const int K = min(Kall, kbeg + k_per_split);
+  if (kbeg >= K && ksplit > 1) return;
 
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -75,7 +81,7 @@ gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  for (int k0 = kbeg; k0 < K; k0 += BK) {
     {  // A tile
       const int kk = k0 + a_k;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -149,6 +155,11 @@ gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* 
       const int co = n0 + tx * 4 + j;
       if (co >= g.Co) continue;
       float y = acc[i][j];
+      if (ksplit > 1) {
+        if (ep.bias && split == 0) y += __ldg(ep.bias + co);
+        atomicAdd(out + base + co, y);
+        continue;
+      }
       if (ep.bias) y += __ldg(ep.bias + co);
       if (ep.preact) ep.preact[base + co] = y;
       float o = y;
@@ -264,8 +275,24 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
     const int Hq = cdiv(g->Ho, g->stride_h), Wq = cdiv(g->Wo, g->stride_w);
     maxP = g->N * Hq * Wq;
   }
-  dim3 grid(cdiv(maxP, BM), cdiv(g->Co, BN), nphase);
-  gather_gemm_fwd<<<grid, NT, 0, st>>>(*g, in, wpack, *ep, out);
+  // Thin grids with a long contraction (batch-sized linears, the 1-channel head): split K.
+  int ksplit = 1, k_per_split = 1 << 30;
+  const int blocks = cdiv(maxP, BM) * cdiv(g->Co, BN) * nphase;
+  const int Kmax = cdiv(g->KH, g->relation == GLIS_TCONV ? g->stride_h : 1) *
+                   cdiv(g->KW, g->relation == GLIS_TCONV ? g->stride_w : 1) * g->Ci;
+  if (blocks < 74 && Kmax >= 1024 && ep->act == GLIS_ACT_NONE && !ep->preact) {
+    ksplit = min(cdiv(Kmax, 256), cdiv(148 * 2, blocks));
+    k_per_split = cdiv(cdiv(Kmax, ksplit), BK) * BK;
+    ksplit = cdiv(Kmax, k_per_split);
+    if (ksplit > 1) {
+      cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)g->N * g->Ho * g->Wo * g->Co, st);
+      GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward: memset failed: %s", cudaGetErrorString(e));
+    } else {
+      k_per_split = 1 << 30;
+    }
+  }
+  dim3 grid(cdiv(maxP, BM), cdiv(g->Co, BN), nphase * ksplit);
+  gather_gemm_fwd<<<grid, NT, 0, st>>>(*g, in, wpack, *ep, out, ksplit, k_per_split);
   GLIS_CHECK_LAUNCH("glis_conv_forward(fp32)");
   return GLIS_OK;
 }

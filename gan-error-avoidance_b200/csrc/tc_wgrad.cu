@@ -1,0 +1,259 @@
+// tcgen05 weight gradient of a (transposed) convolution:
+//
+//   G[a][b][tap] += sum_{pix} S[pix][a] * B[pix*stride - pad + tap][b]
+//
+// S = the tensor on the coarse grid (dy of a conv layer / x of a transposed layer), B = the
+// tensor on the fine grid.  Per CTA: one tap, 128 a-channels (TMEM lanes) x NB <= 128
+// b-channels (TMEM columns); the contraction runs over pixels, so BOTH operands are
+// "MN-major": a shared-memory row is one pixel's 64 contiguous channels (exactly what an
+// NHWC TMA box delivers), 8-pixel groups are 1024 B apart, 64-channel groups one tile apart.
+// The gather of B for the tap is again just a shifted box of the stride-parity view.
+// K is split across blockIdx.x; partial sums are added atomically into G (master layout).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace glis {
+
+using namespace sm100;
+
+int make_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box);
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_STAGES = 4;
+
+struct TcWgradParams {
+  glis_geom_t g;
+  int tw, th, tn;       // pixel tile on the coarse grid (full rows)
+  int rows;             // tw*th*tn  (valid smem rows per 64-channel group)
+  int kp;               // rows rounded up to 16 (smem rows per group; tail rows are zero)
+  int nb;               // b-channels per CTA: 64 or 128
+  int n_btiles;         // ceil(Cb / nb)
+  int passes, stages;
+  int tiles_h, tiles_total, tiles_per_split;
+  float* G;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_constant__ CUtensorMap map_s_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const TcWgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const glis_geom_t& g = P.g;
+  const int Ca = g.Co, Cb = g.Ci, T = g.KH * g.KW;
+  const int tap = blockIdx.z, kh = tap / g.KW, kw = tap - kh * g.KW;
+  const int a_tile = blockIdx.y / P.n_btiles, b_tile = blockIdx.y - a_tile * P.n_btiles;
+  const int a0 = a_tile * 128, b0 = b_tile * P.nb;
+  const int t_beg = blockIdx.x * P.tiles_per_split;
+  const int t_end = min(P.tiles_total, t_beg + P.tiles_per_split);
+  const int ksteps = t_end - t_beg;
+
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t grp_bytes = (uint32_t)P.kp * 128;   // one 64-channel group of one plane
+  const int a_groups = 2, b_groups = P.nb / 64;
+  const uint32_t plane_a = a_groups * grp_bytes, plane_b = b_groups * grp_bytes;
+  const uint32_t stage_bytes = 2 * (plane_a + plane_b);   // [A_hi][A_lo][B_hi][B_lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WG_MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * WG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = P.nb <= 64 ? 64 : 128;
+
+  // zero the tail rows (never written by TMA) of every group so they contribute nothing
+  if (P.kp > P.rows) {
+    const int tail16 = (P.kp - P.rows) * 8;  // 16-byte chunks per group
+    const int groups_per_stage = 2 * (a_groups + b_groups);
+    for (int i = threadIdx.x; i < P.stages * groups_per_stage * tail16; i += WG_THREADS) {
+      const int gi = i / tail16, c = i - gi * tail16;
+      uint4* p = reinterpret_cast<uint4*>(base + (size_t)gi * grp_bytes + (size_t)P.rows * 128) + c;
+      *p = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_s_hi); tma_prefetch_desc(&map_b_hi);
+    if (P.passes == 3) { tma_prefetch_desc(&map_s_lo); tma_prefetch_desc(&map_b_lo); }
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (ksteps > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // tap -> (parity, shift) of the fine-grid gather
+        const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
+        const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
+        const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
+        const int fy = (ey - pary) / g.stride_h, fx = (ex - parx) / g.stride_w;
+        const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (uint32_t)(a_groups + b_groups) * (uint32_t)P.rows * 128u;
+        int s = 0; uint32_t parity = 0;
+        for (int t = t_beg; t < t_end; ++t) {
+          const int tile_h = t % P.tiles_h, tile_n = t / P.tiles_h;
+          const int y0 = tile_h * P.th, n0 = tile_n * P.tn;
+          mbar_wait(&empty_bar[s], parity ^ 1);
+          uint8_t* st = base + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          for (int pl = 0; pl < (P.passes == 3 ? 2 : 1); ++pl) {
+            const CUtensorMap* ms = pl ? &map_s_lo : &map_s_hi;
+            const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
+            uint8_t* sa = st + pl * plane_a;
+            uint8_t* sb = st + 2 * plane_a + pl * plane_b;
+            for (int gi = 0; gi < a_groups; ++gi)
+              tma_load_4d(sa + gi * grp_bytes, ms, &full_bar[s], a0 + gi * 64, 0, y0, n0);
+            for (int gi = 0; gi < b_groups; ++gi)
+              tma_load_5d(sb + gi * grp_bytes, mb, &full_bar[s], parx * Cb + b0 + gi * 64, fx, pary, y0 + fy, n0);
+          }
+          if (++s == P.stages) { s = 0; parity ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, P.nb, 1, 1);  // both operands MN-major
+        int s = 0; uint32_t parity = 0, accumulate = 0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[s], parity);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(base + (size_t)s * stage_bytes), a_lo = a_hi + plane_a;
+          const uint32_t b_hi = a_hi + 2 * plane_a, b_lo = b_hi + plane_b;
+          for (int k16 = 0; k16 < P.kp / 16; ++k16) {
+            const uint32_t off = k16 * 2048;  // 16 pixel rows of 128 B
+            const uint64_t dah = umma_smem_desc(a_hi + off, grp_bytes, 1024), dbh = umma_smem_desc(b_hi + off, grp_bytes, 1024);
+            if (P.passes == 3) {
+              const uint64_t dal = umma_smem_desc(a_lo + off, grp_bytes, 1024), dbl = umma_smem_desc(b_lo + off, grp_bytes, 1024);
+              umma_bf16(tmem_base, dah, dbl, idesc, accumulate);
+              umma_bf16(tmem_base, dal, dbh, idesc, 1);
+              umma_bf16(tmem_base, dah, dbh, idesc, 1);
+            } else {
+              umma_bf16(tmem_base, dah, dbh, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == P.stages) { s = 0; parity ^= 1; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int a = a0 + q * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+      for (int cb = 0; cb < P.nb; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld_wait();
+        if (a < Ca) {
+          float* row = P.G + (size_t)a * Cb * T + tap;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int b = b0 + cb + j;
+            if (b < Cb) atomicAdd(row + (size_t)b * T, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int tc_wgrad_supported(const glis_geom_t* g) {
+  if (g->relation != GLIS_CONV) return 0;
+  if (g->Co % 8 != 0 || g->Ci % 8 != 0 || g->Ci < 64 || g->Co < 64) return 0;
+  if (g->Hi % g->stride_h != 0 || g->Wi % g->stride_w != 0) return 0;
+  if (g->Wo > 64) return 0;  // one coarse row per K tile at least
+  return 1;
+}
+
+int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo, const __nv_bfloat16* b_hi,
+             const __nv_bfloat16* b_lo, float* G, int precision, cudaStream_t st) {
+  GLIS_REQUIRE(tc_wgrad_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: geometry not tileable for tcgen05");
+  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
+  GLIS_REQUIRE(s_hi && b_hi && (passes == 1 || (s_lo && b_lo)), GLIS_E_BADARG,
+               "glis_conv_wgrad_bf16: missing hi/lo operand planes");
+  TcWgradParams P;
+  P.g = *g;
+  const int KMAX = 64;
+  P.tw = g->Wo;
+  if (g->Wo * g->Ho <= KMAX) {
+    P.th = g->Ho;
+    P.tn = KMAX / (g->Wo * g->Ho);
+    if (P.tn > g->N) P.tn = g->N;
+  } else {
+    P.tn = 1;
+    int best = 1; double best_eff = -1;
+    for (int th = 1; th <= KMAX / g->Wo && th <= g->Ho; ++th) {
+      const int kp = (g->Wo * th + 15) / 16 * 16;
+      const double eff = (double)g->Ho * g->Wo / ((double)((g->Ho + th - 1) / th) * (kp + 8));
+      if (eff > best_eff) { best_eff = eff; best = th; }
+    }
+    P.th = best;
+  }
+  P.rows = P.tw * P.th * P.tn;
+  P.kp = (P.rows + 15) / 16 * 16;
+  P.nb = g->Ci > 64 ? 128 : 64;
+  P.n_btiles = (g->Ci + P.nb - 1) / P.nb;
+  const int n_atiles = (g->Co + 127) / 128;
+  P.passes = passes;
+  P.tiles_h = (g->Ho + P.th - 1) / P.th;
+  P.tiles_total = P.tiles_h * ((g->N + P.tn - 1) / P.tn);
+  const int T = g->KH * g->KW;
+  const int ctas = n_atiles * P.n_btiles * T;
+  int splits = (148 * 2 + ctas - 1) / ctas;
+  const int max_splits = (P.tiles_total + 7) / 8;  // at least 8 K-tiles per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  P.tiles_per_split = (P.tiles_total + splits - 1) / splits;
+  splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
+  const size_t stage_bytes = 2 * (size_t)(2 + P.nb / 64) * P.kp * 128;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: tile does not fit shared memory");
+  P.stages = stages;
+  P.G = G;
+
+  CUtensorMap ms_hi, ms_lo, mb_hi, mb_lo;
+  {
+    const uint64_t C = g->Co, W = g->Wo, H = g->Ho;
+    const uint64_t dims[4] = {C, W, H, (uint64_t)g->N};
+    const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)P.tw, (uint32_t)P.th, (uint32_t)P.tn};
+    int rc = make_bf16_map(&ms_hi, s_hi, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_bf16_map(&ms_lo, passes == 3 ? s_lo : s_hi, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t C = g->Ci, W = g->Wi, H = g->Hi, sw = g->stride_w, sh = g->stride_h;
+    const uint64_t dims[5] = {sw * C, W / sw, sh, H / sh, (uint64_t)g->N};
+    const uint64_t strides[4] = {sw * C * 2, W * C * 2, sh * W * C * 2, H * W * C * 2};
+    const uint32_t box[5] = {64, (uint32_t)P.tw, 1, (uint32_t)P.th, (uint32_t)P.tn};
+    int rc = make_bf16_map(&mb_hi, b_hi, 5, dims, strides, box);
+    if (rc) return rc;
+    rc = make_bf16_map(&mb_lo, passes == 3 ? b_lo : b_hi, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_wgrad_kernel): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(splits, n_atiles * P.n_btiles, T);
+  tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(ms_hi, ms_lo, mb_hi, mb_lo, P);
+  GLIS_CHECK_LAUNCH("glis_conv_wgrad_bf16");
+  return GLIS_OK;
+}
+
+}  // namespace glis

@@ -211,20 +211,22 @@ class WNContraction(torch.autograd.Function):
             norm, fwd_planes, bwd_planes = wn_prepare_bf16(weight, scale, spec, tc_f, tc_b, lo)
         if not tc_f or (need_dx and not tc_b):
             norm, pack_io, pack_oi = wn_prepare(weight, scale, spec, not tc_f, need_dx and not tc_b)
+        x_planes = (None, None)
         if tc_f:
-            out = conv_forward_tc(spec, rel_f, split_bf16(xc, lo), fwd_planes, shape, xc, prec, bias=b)
+            x_planes = split_bf16(xc, lo)
+            out = conv_forward_tc(spec, rel_f, x_planes, fwd_planes, shape, xc, prec, bias=b)
         else:
             out = conv_forward(spec, rel_f, xc, pack_io, shape, bias=b)
         ctx.spec, ctx.tc_b, ctx.prec = spec, tc_b, prec
         ctx.has_scale, ctx.has_bias = scale is not None, bias is not None
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         saved_b = bwd_planes if tc_b else (None, None)
-        ctx.save_for_backward(xc, weight, scale, norm, pack_oi, saved_b[0], saved_b[1])
+        ctx.save_for_backward(xc, weight, scale, norm, pack_oi, saved_b[0], saved_b[1], x_planes[0], x_planes[1])
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        xc, weight, scale, norm, pack_oi, bwd_hi, bwd_lo = ctx.saved_tensors
+        xc, weight, scale, norm, pack_oi, bwd_hi, bwd_lo, x_hi, x_lo = ctx.saved_tensors
         spec = ctx.spec
         dyc = _nhwc(dy)
         out_axis = 1 if spec.transposed else 0
@@ -237,12 +239,14 @@ class WNContraction(torch.autograd.Function):
             n, h, w, ho, wo = xc.shape[0], 1, 1, 1, 1
 
         dx = None
+        want_lo = ctx.prec == L.PREC_BF16X3
+        dy_planes = None
         if ctx.needs_input_grad[0]:
             # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
             rel = L.CONV if spec.transposed else L.TCONV
             if ctx.tc_b:
-                dx = conv_forward_tc(spec, rel, split_bf16(dyc, ctx.prec == L.PREC_BF16X3), (bwd_hi, bwd_lo),
-                                     tuple(xc.shape), dyc, ctx.prec)
+                dy_planes = split_bf16(dyc, want_lo)
+                dx = conv_forward_tc(spec, rel, dy_planes, (bwd_hi, bwd_lo), tuple(xc.shape), dyc, ctx.prec)
             else:
                 dx = conv_forward(spec, rel, dyc, pack_oi, tuple(xc.shape))
 
@@ -255,9 +259,19 @@ class WNContraction(torch.autograd.Function):
             else:                 # small = dy (Cout), big = x (Cin)
                 g = spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
                 small, big = dyc, xc
-            with L.timed("conv_wgrad M=%d N=%d K=%d fp32" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)):
-                L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
-                       L.stream())
+            tag = "conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)
+            if ctx.prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
+                if dy_planes is None:
+                    dy_planes = split_bf16(dyc, want_lo)
+                xp = (x_hi, x_lo) if x_hi is not None else split_bf16(xc, want_lo)
+                sp, bp = (xp, dy_planes) if spec.transposed else (dy_planes, xp)
+                with L.timed(tag + " tc"):
+                    L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
+                           L.ptr16(bp[1]), L.ptr(graw), ctx.prec, L.stream())
+            else:
+                with L.timed(tag + " fp32"):
+                    L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
+                           L.stream())
             dw = torch.empty_like(graw)
             if ctx.has_scale:
                 dscale = torch.empty(cout, device=dw.device, dtype=torch.float32)

@@ -136,6 +136,14 @@ int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x
 int glis_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G,
                     int precision, void* stream);
 
+/* 1 if glis_conv_wgrad_bf16 can tile this geometry (channels multiples of 8 and >= 64, fine
+ * grid divisible by the stride, coarse rows <= 64 pixels). */
+int glis_wgrad_tc_supported(const glis_geom_t* g);
+
+/* glis_conv_wgrad on tcgen05 (both operands MN-major straight from the NHWC planes); adds into G. */
+int glis_conv_wgrad_bf16(const glis_geom_t* g, const void* small_hi, const void* small_lo,
+                         const void* big_hi, const void* big_lo, float* G, int precision, void* stream);
+
 /* ---- pointwise / reductions -------------------------------------------------------
  * TPReLU forward (common/modules/TPReLU.py:16-18) on a tensor whose channel of element i is
  * (i / inner) % C  (inner = 1 for NHWC and (B,C); H*W for NCHW-contiguous). a_raw is clamped here. */
