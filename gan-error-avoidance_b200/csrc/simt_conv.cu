@@ -175,6 +175,96 @@ gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* 
   }
 }
 
+// Forward launch for image-side layers with at most 4 output channels and many pixels
+// (G's last transposed conv 64 -> 3, D's first-layer data gradient 64 -> 3).  The 64x64 tile
+// above would idle 61 of 64 columns; here 8 lanes share one output pixel, each owning an
+// interleaved quarter-cache-line slice of the input channels (coalesced 128-byte reads per
+// tap), the partial sums meet in three shuffles and lane 0 applies the epilogue.
+constexpr int SC_NT = 256;
+__global__ void __launch_bounds__(SC_NT)
+small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __restrict__ wp,
+               const glis_epilogue_t ep, float* __restrict__ out) {
+  // [tap][j][c4] -> (co0..co3) of input channel 4*c4 + j: the 8 lanes of a pixel group read 8
+  // consecutive float4 (bank-conflict free), all groups on the same tap read the same ones.
+  extern __shared__ float4 w4[];
+  const int T = g.KH * g.KW, C4 = g.Ci / 4;
+  for (int i = threadIdx.x; i < T * g.Ci; i += SC_NT) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = wp + (int64_t)i * g.Co;
+    v.x = __ldg(src);
+    if (g.Co > 1) v.y = __ldg(src + 1);
+    if (g.Co > 2) v.z = __ldg(src + 2);
+    if (g.Co > 3) v.w = __ldg(src + 3);
+    const int tap = i / g.Ci, ci = i - tap * g.Ci;
+    w4[(tap * 4 + (ci & 3)) * C4 + (ci >> 2)] = v;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;                   // lane within the pixel group
+  const int64_t P = (int64_t)g.N * g.Ho * g.Wo;
+  const int64_t groups = (int64_t)gridDim.x * (SC_NT / 8);
+  for (int64_t pix = (int64_t)blockIdx.x * (SC_NT / 8) + (threadIdx.x >> 3);; pix += groups) {
+    // all 8 lanes of a group share `pix`; whole warps leave together only when every group is done
+    const bool live = pix < P;
+    if (__all_sync(0xffffffffu, !live)) break;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0, oy = 0, ox = 0;
+    if (live) {
+      ox = (int)(pix % g.Wo); const int64_t t = pix / g.Wo; oy = (int)(t % g.Ho); n = (int)(t / g.Ho);
+      int kh0 = 0, kw0 = 0, sth = 1, stw = 1;
+      if (g.relation == GLIS_TCONV) {
+        kh0 = (oy + g.pad_h) % g.stride_h; kw0 = (ox + g.pad_w) % g.stride_w; sth = g.stride_h; stw = g.stride_w;
+      }
+      for (int kh = kh0; kh < g.KH; kh += sth) {
+        int iy;
+        if (g.relation == GLIS_CONV) iy = oy * g.stride_h - g.pad_h + kh * g.dil_h;
+        else iy = (oy + g.pad_h - kh) / g.stride_h;  // numerator >= 0 is checked below
+        if (g.relation == GLIS_TCONV && oy + g.pad_h - kh < 0) continue;
+        if (iy < 0 || iy >= g.Hi) continue;
+        for (int kw = kw0; kw < g.KW; kw += stw) {
+          int ix;
+          if (g.relation == GLIS_CONV) ix = ox * g.stride_w - g.pad_w + kw * g.dil_w;
+          else ix = (ox + g.pad_w - kw) / g.stride_w;
+          if (g.relation == GLIS_TCONV && ox + g.pad_w - kw < 0) continue;
+          if (ix < 0 || ix >= g.Wi) continue;
+          const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)n * g.Hi + iy) * g.Wi + ix) * g.Ci);
+          const float4* wt = w4 + (kh * g.KW + kw) * g.Ci;
+          for (int c4 = sub; c4 < C4; c4 += 8) {
+            const float4 x = __ldg(src + c4);
+            const float4 w0 = wt[c4], w1 = wt[C4 + c4], w2 = wt[2 * C4 + c4], w3 = wt[3 * C4 + c4];
+            a0 = fmaf(x.x, w0.x, a0); a1 = fmaf(x.x, w0.y, a1); a2 = fmaf(x.x, w0.z, a2); a3 = fmaf(x.x, w0.w, a3);
+            a0 = fmaf(x.y, w1.x, a0); a1 = fmaf(x.y, w1.y, a1); a2 = fmaf(x.y, w1.z, a2); a3 = fmaf(x.y, w1.w, a3);
+            a0 = fmaf(x.z, w2.x, a0); a1 = fmaf(x.z, w2.y, a1); a2 = fmaf(x.z, w2.z, a2); a3 = fmaf(x.z, w2.w, a3);
+            a0 = fmaf(x.w, w3.x, a0); a1 = fmaf(x.w, w3.y, a1); a2 = fmaf(x.w, w3.z, a2); a3 = fmaf(x.w, w3.w, a3);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (live && sub == 0) {
+      const float acc[4] = {a0, a1, a2, a3};
+      const int64_t base = pix * g.Co;
+      for (int co = 0; co < g.Co; ++co) {
+        float y = acc[co];
+        if (ep.bias) y += __ldg(ep.bias + co);
+        if (ep.preact) ep.preact[base + co] = y;
+        float o = y;
+        if (ep.act == GLIS_ACT_TPRELU) {
+          const float b = __ldg(ep.act_b + co), a = __ldg(ep.act_a + co);
+          const float tt = y - b;
+          o = (tt > 0.f ? tt : a * tt) + b;
+        } else if (ep.act == GLIS_ACT_SIGMOID) {
+          o = 1.f / (1.f + expf(-y));
+        }
+        out[base + co] = o;
+      }
+    }
+  }
+}
+
 // Weight gradient: G[a][b][tap] += sum_pix small[pix][a] * big[gather(pix,tap)][b]
 // Block tile 64 (a) x 64 (flattened tap*Cb + b), K = pixels of `small`, split over blockIdx.z.
 __global__ void __launch_bounds__(NT)
@@ -269,6 +359,23 @@ int validate_geom(const glis_geom_t* g, const char* who) {
 
 int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                       float* out, cudaStream_t st) {
+  {
+    const int64_t pixels = (int64_t)g->N * g->Ho * g->Wo;
+    const size_t wsmem = (size_t)g->KH * g->KW * g->Ci * sizeof(float4);
+    if (g->Co <= 4 && g->Ci % 32 == 0 && pixels >= 4096 && wsmem <= 96 * 1024 &&
+        (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(small_cout_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+      }
+      int64_t want = (pixels + SC_NT / 8 - 1) / (SC_NT / 8);
+      const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+      small_cout_fwd<<<blocks, SC_NT, wsmem, st>>>(*g, in, wpack, *ep, out);
+      GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, small Cout)");
+      return GLIS_OK;
+    }
+  }
   int nphase = 1, maxP = g->N * g->Ho * g->Wo;
   if (g->relation == GLIS_TCONV) {
     nphase = g->stride_h * g->stride_w;

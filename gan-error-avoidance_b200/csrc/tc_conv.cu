@@ -39,6 +39,9 @@ struct TcConvParams {
   int passes;        // 3 (bf16x3) or 1
   int stages;
   int tiles_h;       // ceil(Hq_max / th)
+  int tiles_x;       // pixel tiles per (phase, channel tile) = tiles_h * ceil(N / tn)
+  int tiles_co;      // ceil(Co / 128)
+  int total_tiles;   // tiles_x * tiles_co * phases
   const float* bias; int act; const float* act_a; const float* act_b;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
 };
@@ -66,19 +69,38 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
+// One output tile of the persistent kernel.
+struct TcTile {
+  TcPhase ph;
+  int qy0, n0, co0, ntaps, ksteps;
+  bool empty;
+};
+
+__device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int id) {
+  TcTile t;
+  const int per_phase = P.tiles_x * P.tiles_co;
+  const int z = id / per_phase, rem = id - z * per_phase;
+  const int y = rem / P.tiles_x, x = rem - y * P.tiles_x;
+  t.ph = tc_phase(P.g, z);
+  const int tile_h = x % P.tiles_h, tile_n = x / P.tiles_h;
+  t.qy0 = tile_h * P.th;
+  t.n0 = tile_n * P.tn;
+  t.co0 = y * TC_BM;
+  t.ntaps = t.ph.nth * t.ph.ntw;
+  t.ksteps = t.ntaps * P.kblocks;
+  t.empty = (t.qy0 >= t.ph.Hq) || t.ph.Wq <= 0 || t.ksteps == 0;
+  return t;
+}
+
+// Persistent: each CTA walks tiles id = blockIdx.x, blockIdx.x + gridDim.x, ...  The smem
+// ring runs across tile boundaries and the accumulator is double-buffered in TMEM, so the
+// epilogue of tile i overlaps the TMA + MMA main loop of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                const TcConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const glis_geom_t& g = P.g;
-  const TcPhase ph = tc_phase(g, blockIdx.z);
-  const int tile_h = blockIdx.x % P.tiles_h, tile_n = blockIdx.x / P.tiles_h;
-  const int qy0 = tile_h * P.th, n0 = tile_n * P.tn;
-  const int co0 = blockIdx.y * TC_BM;
-  const int ntaps = ph.nth * ph.ntw;
-  const int ksteps = ntaps * P.kblocks;
-  const bool empty_tile = (qy0 >= ph.Hq) || ph.Wq <= 0 || ksteps == 0;
 
   // ---- shared memory carve-up (1024-byte aligned operand tiles)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,8 +109,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC_MAX_STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -96,7 +119,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
     if (P.passes == 3) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
@@ -104,16 +127,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)P.tmem_cols / 2;
 
-  if (!empty_tile) {
-    if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        const uint32_t box_rows = (uint32_t)(P.tw * P.th * P.tn);
-        const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + box_rows * 128u);
-        int s = 0; uint32_t parity = 0;
-        for (int t = 0; t < ntaps; ++t) {
-          const int jh = t / ph.ntw, jw = t - jh * ph.ntw;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t box_rows = (uint32_t)(P.tw * P.th * P.tn);
+      const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + box_rows * 128u);
+      int s = 0; uint32_t parity = 0;
+      for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+        const TcTile tl = tc_tile(P, id);
+        if (tl.empty) continue;
+        for (int t = 0; t < tl.ntaps; ++t) {
+          const int jh = t / tl.ph.ntw, jw = t - jh * tl.ph.ntw;
           int kh, kw, cpar = 0, c1, c2 = 0, c3;
           if (g.relation == GLIS_CONV) {
             kh = jh; kw = jw;
@@ -121,42 +147,50 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
             const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
             cpar = parx * g.Ci;
-            c1 = (ex - parx) / g.stride_w;          // + qx0 (= 0)
+            c1 = (ex - parx) / g.stride_w;
             c2 = pary;
-            c3 = qy0 + (ey - pary) / g.stride_h;
+            c3 = tl.qy0 + (ey - pary) / g.stride_h;
           } else {
-            kh = ph.py + jh * g.stride_h; kw = ph.px + jw * g.stride_w;
-            c1 = (ph.rx + g.pad_w - kw) / g.stride_w;   // exact inside a phase
-            c3 = qy0 + (ph.ry + g.pad_h - kh) / g.stride_h;
+            kh = tl.ph.py + jh * g.stride_h; kw = tl.ph.px + jw * g.stride_w;
+            c1 = (tl.ph.rx + g.pad_w - kw) / g.stride_w;   // exact inside a phase
+            c3 = tl.qy0 + (tl.ph.ry + g.pad_h - kh) / g.stride_h;
           }
           const int tap = kh * g.KW + kw;
           for (int kb = 0; kb < P.kblocks; ++kb) {
             mbar_wait(&empty_bar[s], parity ^ 1);
             uint8_t* st = base + (size_t)s * stage_bytes;
             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, co0, tap);
+            tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0, tap);
             if (g.relation == GLIS_CONV)
-              tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, n0);
+              tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
             else
-              tma_load_4d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], kb * TC_BK, c1, c3, n0);
+              tma_load_4d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], kb * TC_BK, c1, c3, tl.n0);
             if (P.passes == 3) {
-              tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, co0, tap);
+              tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0, tap);
               if (g.relation == GLIS_CONV)
-                tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, n0);
+                tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
               else
-                tma_load_4d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], kb * TC_BK, c1, c3, n0);
+                tma_load_4d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], kb * TC_BK, c1, c3, tl.n0);
             }
             if (++s == P.stages) { s = 0; parity ^= 1; }
           }
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(TC_BM, P.n_mma, 0, 0);
-        int s = 0; uint32_t parity = 0;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, P.n_mma, 0, 0);
+      int s = 0; uint32_t parity = 0;
+      uint32_t acc = 0, acc_phase = 0;  // bit a of acc_phase = parity of tmem_empty_bar[a] to wait for
+      for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+        const TcTile tl = tc_tile(P, id);
+        if (tl.empty) continue;
+        mbar_wait(&tmem_empty_bar[acc], ((acc_phase >> acc) & 1u) ^ 1u);  // epilogue drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * acc_stride;
         uint32_t accumulate = 0;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = 0; ks < tl.ksteps; ++ks) {
           mbar_wait(&full_bar[s], parity);
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(base + (size_t)s * stage_bytes), a_lo = a_hi + a_bytes;
@@ -167,47 +201,52 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             const uint64_t dah = umma_smem_desc(a_hi + off, 16, 1024), dbh = umma_smem_desc(b_hi + off, 16, 1024);
             if (P.passes == 3) {
               const uint64_t dal = umma_smem_desc(a_lo + off, 16, 1024), dbl = umma_smem_desc(b_lo + off, 16, 1024);
-              umma_bf16(tmem_base, dah, dbl, idesc, accumulate);
-              umma_bf16(tmem_base, dal, dbh, idesc, 1);
-              umma_bf16(tmem_base, dah, dbh, idesc, 1);
+              umma_bf16(tmem_d, dah, dbl, idesc, accumulate);
+              umma_bf16(tmem_d, dal, dbh, idesc, 1);
+              umma_bf16(tmem_d, dah, dbh, idesc, 1);
             } else {
-              umma_bf16(tmem_base, dah, dbh, idesc, accumulate);
+              umma_bf16(tmem_d, dah, dbh, idesc, accumulate);
             }
             accumulate = 1;
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
           if (++s == P.stages) { s = 0; parity ^= 1; }
         }
-        umma_commit(tmem_full_bar);
+        umma_commit(&tmem_full_bar[acc]);
+        acc_phase ^= (1u << acc);
+        acc ^= 1u;
       }
-    } else {
-      // ===================== epilogue (warps 2..5) =====================
-      const int q = warp & 3;  // TMEM lane quarter this warp may access
-      const int co = co0 + q * 32 + lane;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int cols = P.tw * P.th * P.tn;
+    uint32_t acc = 0, full_phase = 0;
+    for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+      const TcTile tl = tc_tile(P, id);
+      if (tl.empty) continue;
+      const int co = tl.co0 + q * 32 + lane;
       const bool ch_ok = co < g.Co;
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias) bias = __ldg(P.bias + co);
         if (P.act == GLIS_ACT_TPRELU) { ta = __ldg(P.act_a + co); tb = __ldg(P.act_b + co); }
       }
-      mbar_wait(tmem_full_bar, 0);
+      mbar_wait(&tmem_full_bar[acc], (full_phase >> acc) & 1u);
       tc_fence_after_sync();
-      const int cols = P.tw * P.th * P.tn;
-      const int per_img = P.tw * P.th;
+      const uint32_t tmem_d = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      int iw = 0, ih = 0, in_ = 0;  // position of column `col` inside the pixel tile
       for (int cb = 0; cb < cols; cb += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+        tmem_ld_32x32(tmem_d + (uint32_t)cb, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int col = cb + j;
-          const int in_ = col / per_img, r = col - in_ * per_img;
-          const int ih = r / P.tw, iw = r - ih * P.tw;
-          const int n = n0 + in_, qy = qy0 + ih, qx = iw;
-          const bool ok = ch_ok && col < cols && n < g.N && qy < ph.Hq && qx < ph.Wq;
+          const int n = tl.n0 + in_, qy = tl.qy0 + ih, qx = iw;
+          const bool ok = ch_ok && (cb + j) < cols && n < g.N && qy < tl.ph.Hq && qx < tl.ph.Wq;
           if (ok) {
             int oy = qy, ox = qx;
-            if (g.relation == GLIS_TCONV) { oy = qy * g.stride_h + ph.ry; ox = qx * g.stride_w + ph.rx; }
+            if (g.relation == GLIS_TCONV) { oy = qy * g.stride_h + tl.ph.ry; ox = qx * g.stride_w + tl.ph.rx; }
             const size_t idx = (((size_t)n * g.Ho + oy) * g.Wo + ox) * g.Co + co;
             const float y = __uint_as_float(v[j]) + bias;
             if (P.preact) P.preact[idx] = y;
@@ -222,8 +261,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
               if (P.out_lo) P.out_lo[idx] = lo;
             }
           }
+          if (++iw == P.tw) { iw = 0; if (++ih == P.th) { ih = 0; ++in_; } }
         }
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      full_phase ^= (1u << acc);
+      acc ^= 1u;
     }
   }
   tc_fence_before_sync();
@@ -290,6 +335,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Reasons the tensor-core path does not apply (the caller then uses the fp32 kernel).
 int tc_conv_supported(const glis_geom_t* g) {
   if (g->Ci % TC_BK != 0) return 0;                       // K blocks of 64 channels
+  if (g->Co < 32) return 0;                               // 3- and 1-channel outputs: < 25 % of the 128 MMA rows
   if (g->dil_h != 1 || g->dil_w != 1) return 0;
   if (g->relation == GLIS_CONV) {
     if (g->Hi % g->stride_h != 0 || g->Wi % g->stride_w != 0) return 0;  // parity view of the input
@@ -334,12 +380,15 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     P.th = best_th;
   }
   P.n_mma = round_up(P.tw * P.th * P.tn, 16);
-  P.tmem_cols = 32;
-  while (P.tmem_cols < P.n_mma) P.tmem_cols *= 2;
+  P.tmem_cols = 64;  // two accumulators of tmem_cols / 2 columns each
+  while (P.tmem_cols < 2 * P.n_mma) P.tmem_cols *= 2;
   P.kblocks = g->Ci / TC_BK;
   P.passes = passes;
   P.tiles_h = (Hq + P.th - 1) / P.th;
   const int tiles_n = (g->N + P.tn - 1) / P.tn;
+  P.tiles_x = P.tiles_h * tiles_n;
+  P.tiles_co = (g->Co + TC_BM - 1) / TC_BM;
+  P.total_tiles = P.tiles_x * P.tiles_co * nphase;
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -381,13 +430,21 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   }
 
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  GLIS_REQUIRE(P.tmem_cols <= 512, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: accumulators exceed TMEM");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(P.tiles_h * tiles_n, (g->Co + TC_BM - 1) / TC_BM, nphase);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
   tc_conv_kernel<<<grid, TC_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16");
   return GLIS_OK;
