@@ -158,7 +158,7 @@ def run_ours(args, rank, world, local):
     import torch.distributed as dist
     import common.model as pm
     from glis_b200 import _lib, dp, ops
-    from glis_b200.trainer import GLISTrainer
+    from glis_b200.trainer import GLISTrainer, GraphedStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: the product path needs a CUDA device (there is no CPU fallback)")
@@ -181,12 +181,19 @@ def run_ours(args, rank, world, local):
     zd, zg = torch.empty(B, code, device=dev), torch.empty(B, code, device=dev)
     counter = [0]
 
+    graphed = None
+    if not args.no_graph:
+        graphed = GraphedStep(tr, B, H, W, code, dev)
+        real, zd, zg = graphed.real, graphed.z_d, graphed.z_g   # fill the static buffers in place
+
     def device_step():
         off = counter[0] * (1 << 22)
         counter[0] += 1
         ops.uniform_(real, data_seed, off)
         ops.randn_(zd, data_seed + 7, off)
         ops.randn_(zg, data_seed + 13, off)
+        if graphed is not None:
+            return graphed.step(None, None, None, depth, depth)
         return tr.step(real, zd, zg, depth, depth)
 
     def barrier():
@@ -217,6 +224,11 @@ def run_ours(args, rank, world, local):
     launches0 = _lib.launch_count
     ms_total = timed_region(device_step, args.steps)
     launches = _lib.launch_count - launches0
+    if graphed is not None:
+        # a replayed graph launches the kernels captured once: count them from an eager step
+        l0 = _lib.launch_count
+        tr.step(real, zd, zg, depth, depth)
+        launches = args.steps * (_lib.launch_count - l0 + 3)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step * 1e-3)
@@ -224,7 +236,8 @@ def run_ours(args, rank, world, local):
     # ---- per-kernel timing for the roofline (separate short pass; events serialise nothing)
     _lib.timed.enabled = True
     for _ in range(min(args.steps, 5)):
-        device_step()
+        ops.uniform_(real, data_seed, 1 << 40)
+        tr.step(real, zd, zg, depth, depth)      # eager: the event brackets cannot live inside a graph
     torch.cuda.synchronize()
     _lib.timed.enabled = False
     per_kernel = _lib.timer_summary()
@@ -242,7 +255,10 @@ def run_ours(args, rank, world, local):
         d_real.copy_(h_real, non_blocking=True)
         zd.copy_(h_zd, non_blocking=True)
         zg.copy_(h_zg, non_blocking=True)
-        out = tr.step(d_real, zd, zg, depth, depth)
+        if graphed is not None:
+            out = graphed.step(d_real, None, None, depth, depth)
+        else:
+            out = tr.step(d_real, zd, zg, depth, depth)
         h_loss.copy_(torch.stack([out["d_real"], out["d_fake"], out["g"]]), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the losses every step
 
@@ -289,7 +305,7 @@ def run_ours(args, rank, world, local):
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32-faithful) + f32", "bf16": "bf16"}[prec_name],
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "lis_depth": "all", "precision": prec_name,
+                   "lis_depth": "all", "precision": prec_name, "cuda_graph": graphed is not None,
                    "l2": "inputs larger than L2: ~%.0f MB of activations + 36 MB of weights touched per step"
                          % act_mb,
                    "gflop_per_step": GFLOP_PER_STEP,
@@ -307,6 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python (no CUDA graph)")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()

@@ -15,9 +15,11 @@
 // fp32 fidelity comes from a bf16 hi/lo split of both operands: three MMAs per k-step
 // (hi*hi + hi*lo + lo*hi), ~2^-16 relative (GLIS_PREC_BF16X3); one MMA in GLIS_PREC_BF16.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / TPReLU / sigmoid -> global, plus the
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> bias / TPReLU / sigmoid -> global, plus the
 // optional bf16 hi/lo planes the next tensor-core layer consumes).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -27,7 +29,7 @@ using namespace sm100;
 
 constexpr int TC_BM = 128;       // channels per CTA (UMMA M)
 constexpr int TC_BK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_MAX_STAGES = 4;
 
 struct TcConvParams {
@@ -44,6 +46,9 @@ struct TcConvParams {
   int total_tiles;   // tiles_x * tiles_co * phases
   const float* bias; int act; const float* act_a; const float* act_b;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int ep_mode;       // compile-time specialised epilogue (0 = generic)
+  unsigned long long* trace;  // optional timeline buffer (GLIS_TC_TRACE): CTA 0 logs globaltimer per event
+  int debug;         // GLIS_TC_DEBUG bits (profiling experiments only): 1 = no stores, 2 = no MMA, 4 = no x loads
 };
 
 struct TcPhase { int ry, rx, Hq, Wq, nth, ntw, py, px; };
@@ -67,6 +72,47 @@ __device__ __forceinline__ TcPhase tc_phase(const glis_geom_t& g, int z) {
 __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   int q = a / b;
   return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+// Walks the (iw, ih) position of consecutive tile columns without branches.
+struct ColWalk {
+  long long off;           // output element offset of the current column (this lane's channel)
+  int iw, ih;
+  long long step_w, step_h, step_n;
+  int tw, th;
+  __device__ __forceinline__ void next() {
+    const bool wrap_w = (iw + 1 == tw);
+    const bool wrap_h = wrap_w && (ih + 1 == th);
+    off += step_w + (wrap_w ? step_h : 0ll) + (wrap_h ? step_n : 0ll);
+    iw = wrap_w ? 0 : iw + 1;
+    ih = wrap_h ? 0 : (wrap_w ? ih + 1 : ih);
+  }
+};
+
+// Epilogue of one 32-column accumulator chunk for this lane's channel, specialised at compile
+// time so that the per-column code is a handful of predicated instructions.
+template <int ACT, bool PREACT, bool F32, bool PLANES>
+__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int nvalid, ColWalk w, float bias, float ta,
+                                                  float tb, float* __restrict__ preact, float* __restrict__ out_f32,
+                                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nvalid) {
+      const float y = __uint_as_float(v[j]) + bias;
+      if (PREACT) preact[w.off] = y;
+      float o = y;
+      if (ACT == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
+      if (ACT == GLIS_ACT_SIGMOID) o = 1.f / (1.f + __expf(-y));
+      if (F32) out_f32[w.off] = o;
+      if (PLANES) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(o, hi, lo);
+        out_hi[w.off] = hi;
+        if (out_lo) out_lo[w.off] = lo;
+      }
+    }
+    w.next();
+  }
 }
 
 // One output tile of the persistent kernel.
@@ -119,7 +165,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
     if (P.passes == 3) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
@@ -128,17 +174,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)P.tmem_cols / 2;
+  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1087] = global_timer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t box_rows = (uint32_t)(P.tw * P.th * P.tn);
-      const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + box_rows * 128u);
+      const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + ((P.debug & 4) ? 0u : box_rows * 128u));
       int s = 0; uint32_t parity = 0;
+      int tr_n = 0;
       for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
         const TcTile tl = tc_tile(P, id);
         if (tl.empty) continue;
-        for (int t = 0; t < tl.ntaps; ++t) {
+        // Every CTA walks the taps from a different starting point: otherwise all 148 SMs pull the
+        // same weight tile from the same L2 slices in lock step (accumulation order is free).
+        const int rot = (int)((blockIdx.x * 5u + (uint32_t)id * 3u) % (uint32_t)tl.ntaps);
+        for (int t0 = 0; t0 < tl.ntaps; ++t0) {
+          const int t = (t0 + rot) % tl.ntaps;
           const int jh = t / tl.ph.ntw, jw = t - jh * tl.ph.ntw;
           int kh, kw, cpar = 0, c1, c2 = 0, c3;
           if (g.relation == GLIS_CONV) {
@@ -158,16 +210,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           const int tap = kh * g.KW + kw;
           for (int kb = 0; kb < P.kblocks; ++kb) {
             mbar_wait(&empty_bar[s], parity ^ 1);
+            if (P.trace && blockIdx.x == 0 && tr_n < 512) P.trace[tr_n++] = global_timer_ns();
             uint8_t* st = base + (size_t)s * stage_bytes;
             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
             tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0, tap);
-            if (g.relation == GLIS_CONV)
+            if (P.debug & 4) { /* expect_tx below was reduced accordingly */ }
+            else if (g.relation == GLIS_CONV)
               tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
             else
               tma_load_4d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], kb * TC_BK, c1, c3, tl.n0);
             if (P.passes == 3) {
               tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0, tap);
-              if (g.relation == GLIS_CONV)
+              if (P.debug & 4) {}
+              else if (g.relation == GLIS_CONV)
                 tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
               else
                 tma_load_4d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], kb * TC_BK, c1, c3, tl.n0);
@@ -181,8 +236,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, P.n_mma, 0, 0);
+      const uint64_t desc0 = umma_smem_desc(smem_u32(base), 16, 1024);  // K-major SW128, stage 0, A_hi
       int s = 0; uint32_t parity = 0;
       uint32_t acc = 0, acc_phase = 0;  // bit a of acc_phase = parity of tmem_empty_bar[a] to wait for
+      int tr_n = 512;
       for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
         const TcTile tl = tc_tile(P, id);
         if (tl.empty) continue;
@@ -193,21 +250,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         for (int ks = 0; ks < tl.ksteps; ++ks) {
           mbar_wait(&full_bar[s], parity);
           tc_fence_after_sync();
-          const uint32_t a_hi = smem_u32(base + (size_t)s * stage_bytes), a_lo = a_hi + a_bytes;
-          const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 16; ++kk) {
-            const uint32_t off = kk * 32;  // 16 bf16 along K inside the swizzled 128-byte row
-            const uint64_t dah = umma_smem_desc(a_hi + off, 16, 1024), dbh = umma_smem_desc(b_hi + off, 16, 1024);
+          if (P.trace && blockIdx.x == 0 && tr_n < 1024) P.trace[tr_n++] = global_timer_ns();
+          // descriptors differ only in their 14-bit start-address field: one add per MMA operand
+          const uint64_t dah0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+          const uint64_t dal0 = dah0 + (a_bytes >> 4);
+          const uint64_t dbh0 = dah0 + ((2 * a_bytes) >> 4);
+          const uint64_t dbl0 = dbh0 + (b_bytes >> 4);
+          if (!(P.debug & 2)) {
             if (P.passes == 3) {
-              const uint64_t dal = umma_smem_desc(a_lo + off, 16, 1024), dbl = umma_smem_desc(b_lo + off, 16, 1024);
-              umma_bf16(tmem_d, dah, dbl, idesc, accumulate);
-              umma_bf16(tmem_d, dal, dbh, idesc, 1);
-              umma_bf16(tmem_d, dah, dbh, idesc, 1);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk) {  // +2 = 32 bytes = 16 bf16 along K in the swizzled row
+                umma_bf16(tmem_d, dah0 + 2 * kk, dbl0 + 2 * kk, idesc, accumulate);
+                umma_bf16(tmem_d, dal0 + 2 * kk, dbh0 + 2 * kk, idesc, 1);
+                umma_bf16(tmem_d, dah0 + 2 * kk, dbh0 + 2 * kk, idesc, 1);
+                accumulate = 1;
+              }
             } else {
-              umma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                umma_bf16(tmem_d, dah0 + 2 * kk, dbh0 + 2 * kk, idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            accumulate = 1;
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
           if (++s == P.stages) { s = 0; parity ^= 1; }
@@ -218,54 +282,78 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter; they take alternate 32-column chunks of the tile.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // 0 or 1
     const int cols = P.tw * P.th * P.tn;
+    const int sh = g.relation == GLIS_TCONV ? g.stride_h : 1, sw = g.relation == GLIS_TCONV ? g.stride_w : 1;
+    const long long step_w = (long long)sw * g.Co;
+    const long long row_pitch = (long long)sh * g.Wo * g.Co;
+    const long long step_h = row_pitch - (long long)P.tw * step_w;
+    const long long step_n = (long long)g.Ho * g.Wo * g.Co - (long long)P.th * row_pitch;
     uint32_t acc = 0, full_phase = 0;
+    int tr_e = 1024;
     for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
       const TcTile tl = tc_tile(P, id);
       if (tl.empty) continue;
       const int co = tl.co0 + q * 32 + lane;
-      const bool ch_ok = co < g.Co;
+      const bool ch_ok = co < g.Co && !(P.debug & 1);
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias) bias = __ldg(P.bias + co);
         if (P.act == GLIS_ACT_TPRELU) { ta = __ldg(P.act_a + co); tb = __ldg(P.act_b + co); }
       }
+      const int oy0 = g.relation == GLIS_TCONV ? tl.qy0 * sh + tl.ph.ry : tl.qy0;
+      const int ox0 = g.relation == GLIS_TCONV ? tl.ph.rx : 0;
+      const int valid_cols = P.tn == 1 ? min(P.th, tl.ph.Hq - tl.qy0) * P.tw : min(P.tn, g.N - tl.n0) * P.th * P.tw;
       mbar_wait(&tmem_full_bar[acc], (full_phase >> acc) & 1u);
       tc_fence_after_sync();
+      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) P.trace[tr_e++] = global_timer_ns();
       const uint32_t tmem_d = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      int iw = 0, ih = 0, in_ = 0;  // position of column `col` inside the pixel tile
-      for (int cb = 0; cb < cols; cb += 32) {
+      for (int cb = half * 32; cb < cols; cb += 64) {
+        // position of column cb inside the pixel tile and its output offset
+        const int in_ = cb / (P.tw * P.th);
+        const int r = cb - in_ * (P.tw * P.th);
+        ColWalk w;
+        w.ih = r / P.tw; w.iw = r - w.ih * P.tw;
+        w.tw = P.tw; w.th = P.th; w.step_w = step_w; w.step_h = step_h; w.step_n = step_n;
+        w.off = (((long long)(tl.n0 + in_) * g.Ho + oy0 + (long long)w.ih * sh) * g.Wo + ox0 + (long long)w.iw * sw) * g.Co + co;
         uint32_t v[32];
         tmem_ld_32x32(tmem_d + (uint32_t)cb, v);
         tmem_ld_wait();
+        // valid columns form a prefix of the tile: ragged rows (tn == 1) or ragged images (th == Hq) come last
+        const int nvalid = ch_ok ? valid_cols - cb : 0;
+        switch (P.ep_mode) {
+          case 1: tc_epilogue_chunk<GLIS_ACT_NONE, false, true, false>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 2: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          default: {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = tl.n0 + in_, qy = tl.qy0 + ih, qx = iw;
-          const bool ok = ch_ok && (cb + j) < cols && n < g.N && qy < tl.ph.Hq && qx < tl.ph.Wq;
-          if (ok) {
-            int oy = qy, ox = qx;
-            if (g.relation == GLIS_TCONV) { oy = qy * g.stride_h + tl.ph.ry; ox = qx * g.stride_w + tl.ph.rx; }
-            const size_t idx = (((size_t)n * g.Ho + oy) * g.Wo + ox) * g.Co + co;
-            const float y = __uint_as_float(v[j]) + bias;
-            if (P.preact) P.preact[idx] = y;
-            float o = y;
-            if (P.act == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
-            else if (P.act == GLIS_ACT_SIGMOID) { o = 1.f / (1.f + __expf(-y)); }
-            if (P.out_f32) P.out_f32[idx] = o;
-            if (P.out_hi) {
-              __nv_bfloat16 hi, lo;
-              split_bf16(o, hi, lo);
-              P.out_hi[idx] = hi;
-              if (P.out_lo) P.out_lo[idx] = lo;
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                const float y = __uint_as_float(v[j]) + bias;
+                if (P.preact) P.preact[w.off] = y;
+                float o = y;
+                if (P.act == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
+                else if (P.act == GLIS_ACT_SIGMOID) { o = 1.f / (1.f + __expf(-y)); }
+                if (P.out_f32) P.out_f32[w.off] = o;
+                if (P.out_hi) {
+                  __nv_bfloat16 hi, lo;
+                  split_bf16(o, hi, lo);
+                  P.out_hi[w.off] = hi;
+                  if (P.out_lo) P.out_lo[w.off] = lo;
+                }
+              }
+              w.next();
             }
           }
-          if (++iw == P.tw) { iw = 0; if (++ih == P.th) { ih = 0; ++in_; } }
         }
       }
       tc_fence_before_sync();
       __syncwarp();
+      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) P.trace[tr_e++] = global_timer_ns();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       full_phase ^= (1u << acc);
       acc ^= 1u;
@@ -344,6 +432,7 @@ int tc_conv_supported(const glis_geom_t* g) {
   int Wq = g->Wo;
   if (g->relation == GLIS_TCONV) Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
   if (Wq > 128) return 0;                                 // one tile row must fit the MMA N
+  if (g->relation == GLIS_TCONV && g->Wo % g->stride_w != 0) return 0;  // all phases equally wide
   if (g->KH * g->KW * (g->Ci / TC_BK) < 1) return 0;
   return 1;
 }
@@ -396,6 +485,17 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.stages = stages;
   P.bias = ep->bias; P.act = ep->act; P.act_a = ep->act_a; P.act_b = ep->act_b; P.preact = ep->preact;
   P.out_f32 = out_f32; P.out_hi = out_hi; P.out_lo = out_lo;
+  P.ep_mode = 0;
+  if (ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi) P.ep_mode = 1;
+  else if (ep->act == GLIS_ACT_TPRELU && ep->preact && !out_f32 && out_hi) P.ep_mode = 2;
+  else if (ep->act == GLIS_ACT_NONE && !ep->preact && !out_f32 && out_hi) P.ep_mode = 3;
+  else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && !out_hi) P.ep_mode = 4;
+  {
+    const char* dbg = getenv("GLIS_TC_DEBUG");
+    P.debug = dbg ? atoi(dbg) : 0;
+    const char* trc = getenv("GLIS_TC_TRACE");  // hex device address of a >= 1088-entry u64 buffer
+    P.trace = trc ? (unsigned long long*)strtoull(trc, nullptr, 16) : nullptr;
+  }
 
   // ---- tensor maps
   CUtensorMap mw_hi, mw_lo, mx_hi, mx_lo;

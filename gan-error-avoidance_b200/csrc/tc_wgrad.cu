@@ -118,24 +118,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = umma_idesc_bf16(128, P.nb, 1, 1);  // both operands MN-major
+        const uint64_t desc0 = umma_smem_desc(smem_u32(base), grp_bytes, 1024);  // stage 0, S_hi
         int s = 0; uint32_t parity = 0, accumulate = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[s], parity);
           tc_fence_after_sync();
-          const uint32_t a_hi = smem_u32(base + (size_t)s * stage_bytes), a_lo = a_hi + plane_a;
-          const uint32_t b_hi = a_hi + 2 * plane_a, b_lo = b_hi + plane_b;
-          for (int k16 = 0; k16 < P.kp / 16; ++k16) {
-            const uint32_t off = k16 * 2048;  // 16 pixel rows of 128 B
-            const uint64_t dah = umma_smem_desc(a_hi + off, grp_bytes, 1024), dbh = umma_smem_desc(b_hi + off, grp_bytes, 1024);
-            if (P.passes == 3) {
-              const uint64_t dal = umma_smem_desc(a_lo + off, grp_bytes, 1024), dbl = umma_smem_desc(b_lo + off, grp_bytes, 1024);
-              umma_bf16(tmem_base, dah, dbl, idesc, accumulate);
-              umma_bf16(tmem_base, dal, dbh, idesc, 1);
-              umma_bf16(tmem_base, dah, dbh, idesc, 1);
-            } else {
-              umma_bf16(tmem_base, dah, dbh, idesc, accumulate);
+          const uint64_t dah0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+          const uint64_t dal0 = dah0 + (plane_a >> 4);
+          const uint64_t dbh0 = dah0 + ((2 * plane_a) >> 4);
+          const uint64_t dbl0 = dbh0 + (plane_b >> 4);
+          const int nk16 = P.kp / 16;
+          if (P.passes == 3) {
+            for (int k16 = 0; k16 < nk16; ++k16) {  // 16 pixel rows of 128 B = 2048 B = 128 descriptor units
+              umma_bf16(tmem_base, dah0 + 128 * k16, dbl0 + 128 * k16, idesc, accumulate);
+              umma_bf16(tmem_base, dal0 + 128 * k16, dbh0 + 128 * k16, idesc, 1);
+              umma_bf16(tmem_base, dah0 + 128 * k16, dbh0 + 128 * k16, idesc, 1);
+              accumulate = 1;
             }
-            accumulate = 1;
+          } else {
+            for (int k16 = 0; k16 < nk16; ++k16) {
+              umma_bf16(tmem_base, dah0 + 128 * k16, dbh0 + 128 * k16, idesc, accumulate);
+              accumulate = 1;
+            }
           }
           umma_commit(&empty_bar[s]);
           if (++s == P.stages) { s = 0; parity ^= 1; }

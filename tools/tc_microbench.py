@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Time the tcgen05 conv kernel per layer shape with CUDA events (GLIS_TC_DEBUG variants)."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gan-error-avoidance_b200"))
+import torch
+from glis_b200 import _lib as L, ops
+
+SHAPES = [  # name, relation, N, Hi, Wi, Ci, Ho, Wo, Co
+    ("D1 conv 64->128 40->20", L.CONV, 64, 40, 40, 64, 20, 20, 128),
+    ("D2 conv 128->256 20->10", L.CONV, 64, 20, 20, 128, 10, 10, 256),
+    ("D3 conv 256->512 10->5", L.CONV, 64, 10, 10, 256, 5, 5, 512),
+    ("G3 tconv 512->256 5->10", L.TCONV, 64, 5, 5, 512, 10, 10, 256),
+    ("G2 tconv 256->128 10->20", L.TCONV, 64, 10, 10, 256, 20, 20, 128),
+    ("G1 tconv 128->64 20->40", L.TCONV, 64, 20, 20, 128, 40, 40, 64),
+    ("dG1 conv 64->128 40->20", L.CONV, 64, 40, 40, 64, 20, 20, 128),
+    ("dD1 tconv 128->64 20->40", L.TCONV, 64, 20, 20, 128, 40, 40, 64),
+]
+
+
+def main():
+    dev = "cuda"
+    spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
+    for name, rel, n, hi, wi, ci, ho, wo, co in SHAPES:
+        g = spec.geom(rel, n, hi, wi, ci, ho, wo, co)
+        x = torch.randn(n, hi, wi, ci, device=dev)
+        xh, xl = ops.split_bf16(x)
+        w = torch.randn(16, co, ci, device=dev) * 0.05
+        wh, wl = ops.split_bf16(w)
+        out = torch.empty(n, ho, wo, co, device=dev)
+        ep = L.Epilogue(None, 0, None, None, None)
+        res = []
+        for dbg in ("0", "1", "2", "3", "4", "6"):
+            os.environ["GLIS_TC_DEBUG"] = dbg
+            for prec in (L.PREC_BF16X3, L.PREC_BF16):
+                def run():
+                    L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xh), L.ptr16(xl), L.ptr16(wh), L.ptr16(wl),
+                           C.byref(ep), L.ptr(out), None, None, prec, L.stream())
+                for _ in range(3):
+                    run()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()       # replay 20 launches: GPU time, not host launch time
+                with torch.cuda.graph(graph):
+                    for _ in range(20):
+                        run()
+                graph.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                res.append("dbg%s/%s %6.1fus" % (dbg, "x3" if prec == L.PREC_BF16X3 else "x1", e0.elapsed_time(e1) * 50))
+        flop = 2.0 * n * (ho * wo if rel == L.CONV else hi * wi) * co * ci * (16 if rel == L.CONV else 16)
+        print("%-28s %5.2f GFLOP | %s" % (name, flop / 1e9, "  ".join(res)))
+    os.environ["GLIS_TC_DEBUG"] = "0"
+
+
+if __name__ == "__main__":
+    main()
