@@ -1,0 +1,72 @@
+"""Data-parallel host logic on CPU: bucket planning, the gloo world-size-2 gradient exchange and
+the cross-rank agreement of the stochastic LIS depth."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def test_plan_buckets_cover_buffer_back_to_front():
+    from glis_b200.dp import plan_buckets
+    assert plan_buckets(0, 4) == []
+    assert plan_buckets(10, 4) == [(6, 4), (2, 4), (0, 2)]
+    assert plan_buckets(8, 100) == [(0, 8)]
+    for numel, b in ((1, 1), (17, 5), (1000, 64), (9_000_001, 1 << 20)):
+        plan = plan_buckets(numel, b)
+        assert plan[0][0] + plan[0][1] == numel and plan[-1][0] == 0          # starts at the end
+        assert sum(n for _, n in plan) == numel and all(0 < n <= b for _, n in plan)
+        for (o1, n1), (o2, n2) in zip(plan, plan[1:]):
+            assert o2 + n2 == o1                                                  # contiguous, no overlap
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, results):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from glis_b200 import dp
+    from common.model import GeneratorLearnedInputSpace
+    r, w, _ = dp.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    data_seed = dp.seed_everything(1234, rank)
+    # identical weights on every rank, distinct data seeds
+    gen = GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 3, "fractional")
+    wsum = float(sum(p.double().sum() for p in gen.parameters()))
+    depths = [gen.lis_depth(None) for _ in range(64)]
+    # gradient exchange: sum over ranks, scale 1/world, bucketed
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    sync = dp.GradSync(world, bucket_mb=0.001)  # 262 elements per bucket -> 4 buckets
+    gscale = sync(flat, "gen")
+    results[rank] = dict(data_seed=data_seed, wsum=wsum, depths=depths, flat=flat.clone(), gscale=gscale,
+                         bytes=sync.bytes_reduced)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_exchange_and_depth_agreement():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    a, b = results[0], results[1]
+    assert a["data_seed"] != b["data_seed"]
+    assert a["wsum"] == b["wsum"]                       # same initial weights
+    assert a["depths"] == b["depths"] and len(set(a["depths"])) > 1   # same stochastic schedule, not constant
+    want = torch.arange(1000, dtype=torch.float32) * 3  # (1 + 2) * i
+    assert torch.equal(a["flat"], want) and torch.equal(b["flat"], want)
+    assert a["gscale"] == 0.5 and a["bytes"] == 4000
