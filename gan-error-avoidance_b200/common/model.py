@@ -11,11 +11,42 @@ import random
 
 import torch.nn as nn
 
-from glis_b200.naming import DottedSequential
+from glis_b200 import ops
+from glis_b200.naming import DottedSequential as _DottedSequential
 from .modules import (TPReLU, View, WeightNormalizedConv2d, WeightNormalizedConvTranspose2d,
                       WeightNormalizedLinear)
+from .modules.WeightNormalizedConv import _WeightNormalizedConvNd
 
 __all__ = ["build_discriminator", "build_generator", "GeneratorLearnedInputSpace", "build_reverser"]
+
+
+def run_layers(layers, x):
+    """Apply ``layers`` in order, running every (weight-normalized layer, TPReLU) pair as ONE
+    operator: the TPReLU moves into the contraction's epilogue (``ops.wn_contraction_tprelu``).
+    Module structure, parameters and results are those of calling the modules one by one."""
+    layers = list(layers)
+    i = 0
+    while i < len(layers):
+        m = layers[i]
+        nxt = layers[i + 1] if i + 1 < len(layers) else None
+        fusable = (isinstance(m, (_WeightNormalizedConvNd, WeightNormalizedLinear)) and isinstance(nxt, TPReLU)
+                   and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() in (2, 4))
+        if fusable:
+            spec = m._spec() if isinstance(m, _WeightNormalizedConvNd) else m._spec
+            x = ops.wn_contraction_tprelu(x, m.weight, m.scale, m.bias, nxt.weight, nxt.bias, spec)
+            i += 2
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
+class DottedSequential(_DottedSequential):
+    """Sequential container with reference-compatible dotted child names whose forward fuses
+    (WN layer, TPReLU) pairs."""
+
+    def forward(self, input):
+        return run_layers(self._modules.values(), input)
 
 
 def _require_even(w, h, what):
@@ -200,8 +231,6 @@ class GeneratorLearnedInputSpace(nn.Module):
         for i in range(self.lis_depth(n_execute_lis_layers)):
             x = x + self.lis_layers[i](x)
             lis_results.append(x)
-        for layer in self.initial_linear:
-            x = layer(x)
-        for layer in self.conv_layers:
-            x = layer(x)
+        x = run_layers(self.initial_linear, x)
+        x = run_layers(self.conv_layers, x)
         return x, lis_results

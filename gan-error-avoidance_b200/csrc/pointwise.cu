@@ -2,6 +2,7 @@
 // the BCE / MSE losses with their gradients, fused RMSprop, and the Philox generators.
 // All are grid-stride kernels sized to a multiple of the 148 SMs.
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace glis {
 
@@ -42,8 +43,9 @@ constexpr int SMEM_CH = 2048;  // channels staged in shared memory per accumulat
 
 __global__ void __launch_bounds__(PW_NT)
 tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
-                  const float* __restrict__ dout, float* __restrict__ dx, float* __restrict__ da,
-                  float* __restrict__ db, int64_t numel, int C, int inner) {
+                  const float* __restrict__ dout, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
+                  __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ da, float* __restrict__ db, int64_t numel,
+                  int C, int inner) {
   __shared__ float sa[SMEM_CH], sb[SMEM_CH];
   const bool staged = C <= SMEM_CH;
   if (staged) {
@@ -63,7 +65,14 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
       const float ar = __ldg(a_raw + c), bb = __ldg(b + c), a = clamp01(ar);
       const float t = x[i] - bb, g = dout[i];
       const bool neg = !(t > 0.f);
-      dx[i] = neg ? a * g : g;
+      const float d = neg ? a * g : g;
+      if (dx) dx[i] = d;
+      if (dx_hi) {
+        __nv_bfloat16 h, l;
+        sm100::split_bf16(d, h, l);
+        dx_hi[i] = h;
+        if (dx_lo) dx_lo[i] = l;
+      }
       if (neg) {
         ga = (ar >= 0.f && ar <= 1.f) ? g * t : 0.f;
         gb = g * (1.f - a);
@@ -78,6 +87,60 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
       if (sa[c] != 0.f) atomicAdd(da + c, sa[c]);
       if (sb[c] != 0.f) atomicAdd(db + c, sb[c]);
     }
+  }
+}
+
+// NHWC fast path (inner == 1, C % 4 == 0, C/4 <= 256): a thread owns four fixed channels and
+// walks rows, so the per-channel sums live in registers and meet global memory once per thread.
+__global__ void __launch_bounds__(PW_NT)
+tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
+                       const float* __restrict__ dout, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
+                       __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ da, float* __restrict__ db,
+                       int64_t rows, int C) {
+  __shared__ float s_a[1024], s_b[1024];
+  for (int c = threadIdx.x; c < C; c += PW_NT) { s_a[c] = 0.f; s_b[c] = 0.f; }
+  __syncthreads();
+  const int c4n = C >> 2;                       // float4 groups per row
+  const int rows_per_iter = PW_NT / c4n;        // rows handled by the block per iteration
+  const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  if (rl < rows_per_iter) {
+    const float4 ar = __ldg(reinterpret_cast<const float4*>(a_raw) + cg);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + cg);
+    const float av[4] = {clamp01(ar.x), clamp01(ar.y), clamp01(ar.z), clamp01(ar.w)};
+    const float arv[4] = {ar.x, ar.y, ar.z, ar.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < rows; r += (int64_t)gridDim.x * rows_per_iter) {
+      const int64_t i4 = r * c4n + cg;
+      const float4 xv = reinterpret_cast<const float4*>(x)[i4];
+      const float4 gv = reinterpret_cast<const float4*>(dout)[i4];
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = xs[j] - bv[j];
+        const bool neg = !(t > 0.f);
+        d[j] = neg ? av[j] * gs[j] : gs[j];
+        if (neg) { sa[j] = fmaf(gs[j], t, sa[j]); sb[j] += gs[j]; }
+      }
+      if (dx) reinterpret_cast<float4*>(dx)[i4] = make_float4(d[0], d[1], d[2], d[3]);
+      if (dx_hi) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm100::split_bf16(d[j], h[j], l[j]);
+        reinterpret_cast<uint2*>(dx_hi)[i4] = *reinterpret_cast<uint2*>(h);
+        if (dx_lo) reinterpret_cast<uint2*>(dx_lo)[i4] = *reinterpret_cast<uint2*>(l);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // block-level: the row groups of this block meet in shared memory
+      if (arv[j] >= 0.f && arv[j] <= 1.f && sa[j] != 0.f) atomicAdd(&s_a[cg * 4 + j], sa[j]);
+      if (sb[j] != 0.f) atomicAdd(&s_b[cg * 4 + j], sb[j] * (1.f - av[j]));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += PW_NT) {   // one global atomic per channel per block
+    if (s_a[c] != 0.f) atomicAdd(da + c, s_a[c]);
+    if (s_b[c] != 0.f) atomicAdd(db + c, s_b[c]);
   }
 }
 
@@ -247,9 +310,34 @@ extern "C" int glis_tprelu_backward(const float* x, const float* a_raw, const fl
   GLIS_REQUIRE(x && a_raw && b && dout && dx && da && db, GLIS_E_BADARG, "glis_tprelu_backward: NULL pointer");
   GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_backward: bad sizes");
   if (numel == 0) return GLIS_OK;
-  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, dout, dx, da, db, numel,
-                                                                            C, inner);
+  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, dout, dx, nullptr, nullptr,
+                                                                            da, db, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_tprelu_backward");
+  return GLIS_OK;
+}
+
+extern "C" int glis_tprelu_backward_planes(const float* x, const float* a_raw, const float* b, const float* dout,
+                                           float* dx, void* dx_hi, void* dx_lo, float* da, float* db, int64_t numel,
+                                           int C, int inner, void* stream) {
+  GLIS_REQUIRE(x && a_raw && b && dout && da && db && (dx || dx_hi), GLIS_E_BADARG,
+               "glis_tprelu_backward_planes: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_backward_planes: bad sizes");
+  if (numel == 0) return GLIS_OK;
+  const bool aligned = ((((uintptr_t)x) | ((uintptr_t)dout) | ((uintptr_t)dx) | ((uintptr_t)a_raw) | ((uintptr_t)b)) & 15) == 0 &&
+                       ((((uintptr_t)dx_hi) | ((uintptr_t)dx_lo)) & 7) == 0;
+  if (inner == 1 && C % 4 == 0 && C / 4 <= PW_NT && aligned) {
+    const int64_t rows = numel / C;
+    const int rows_per_iter = PW_NT / (C / 4);
+    int64_t want = (rows + rows_per_iter * 8 - 1) / (rows_per_iter * 8);
+    const int blocks = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+    tprelu_bwd_nhwc_kernel<<<blocks, PW_NT, 0, (cudaStream_t)stream>>>(
+        x, a_raw, b, dout, dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, da, db, rows, C);
+    GLIS_CHECK_LAUNCH("glis_tprelu_backward_planes(nhwc)");
+    return GLIS_OK;
+  }
+  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+      x, a_raw, b, dout, dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, da, db, numel, C, inner);
+  GLIS_CHECK_LAUNCH("glis_tprelu_backward_planes");
   return GLIS_OK;
 }
 

@@ -10,6 +10,7 @@
 // K = (tap,ci) walked in chunks of 16.  A transposed convolution is decomposed into
 // stride_h*stride_w output phases (blockIdx.z) so that no multiply is spent on zeros.
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace glis {
 
@@ -171,6 +172,12 @@ gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* 
         o = 1.f / (1.f + expf(-y));
       }
       out[base + co] = o;
+      if (ep.out_hi) {
+        __nv_bfloat16 h, l;
+        sm100::split_bf16(o, h, l);
+        reinterpret_cast<__nv_bfloat16*>(ep.out_hi)[base + co] = h;
+        if (ep.out_lo) reinterpret_cast<__nv_bfloat16*>(ep.out_lo)[base + co] = l;
+      }
     }
   }
 }
@@ -201,6 +208,7 @@ small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* _
   __syncthreads();
   const int sub = threadIdx.x & 7;                   // lane within the pixel group
   const int64_t P = (int64_t)g.N * g.Ho * g.Wo;
+  const bool phase_major = g.relation == GLIS_TCONV && g.Ho % g.stride_h == 0 && g.Wo % g.stride_w == 0;
   const int64_t groups = (int64_t)gridDim.x * (SC_NT / 8);
   for (int64_t pix = (int64_t)blockIdx.x * (SC_NT / 8) + (threadIdx.x >> 3);; pix += groups) {
     // all 8 lanes of a group share `pix`; whole warps leave together only when every group is done
@@ -209,7 +217,18 @@ small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* _
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int n = 0, oy = 0, ox = 0;
     if (live) {
-      ox = (int)(pix % g.Wo); const int64_t t = pix / g.Wo; oy = (int)(t % g.Ho); n = (int)(t / g.Ho);
+      if (phase_major) {
+        // pixels of one output phase are consecutive: every group of a warp then walks the same
+        // taps (shared-memory weight reads become broadcasts) and neighbouring input pixels
+        const int Hq = g.Ho / g.stride_h, Wq = g.Wo / g.stride_w;
+        const int64_t per_phase = (int64_t)g.N * Hq * Wq;
+        const int phase = (int)(pix / per_phase);
+        const int64_t r = pix - (int64_t)phase * per_phase;
+        const int qx = (int)(r % Wq); const int64_t t = r / Wq; const int qy = (int)(t % Hq); n = (int)(t / Hq);
+        oy = qy * g.stride_h + phase / g.stride_w; ox = qx * g.stride_w + phase % g.stride_w;
+      } else {
+        ox = (int)(pix % g.Wo); const int64_t t = pix / g.Wo; oy = (int)(t % g.Ho); n = (int)(t / g.Ho);
+      }
       int kh0 = 0, kw0 = 0, sth = 1, stw = 1;
       if (g.relation == GLIS_TCONV) {
         kh0 = (oy + g.pad_h) % g.stride_h; kw0 = (ox + g.pad_w) % g.stride_w; sth = g.stride_h; stw = g.stride_w;
@@ -246,7 +265,7 @@ small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* _
     }
     if (live && sub == 0) {
       const float acc[4] = {a0, a1, a2, a3};
-      const int64_t base = pix * g.Co;
+      const int64_t base = (((int64_t)n * g.Ho + oy) * g.Wo + ox) * g.Co;
       for (int co = 0; co < g.Co; ++co) {
         float y = acc[co];
         if (ep.bias) y += __ldg(ep.bias + co);

@@ -329,6 +329,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           case 2: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           default: {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -490,6 +491,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && !out_f32 && out_hi) P.ep_mode = 2;
   else if (ep->act == GLIS_ACT_NONE && !ep->preact && !out_f32 && out_hi) P.ep_mode = 3;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && !out_hi) P.ep_mode = 4;
+  else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && out_hi) P.ep_mode = 5;
   {
     const char* dbg = getenv("GLIS_TC_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;

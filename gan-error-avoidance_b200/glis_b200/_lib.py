@@ -25,7 +25,7 @@ class Geom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("act_a", C.c_void_p),
-                ("act_b", C.c_void_p), ("preact", C.c_void_p)]
+                ("act_b", C.c_void_p), ("preact", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p)]
 
 
 _vp, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
@@ -44,6 +44,7 @@ SIGNATURES = {
     "glis_conv_wgrad_bf16": [C.POINTER(Geom), _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "glis_tprelu_forward": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_tprelu_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "glis_tprelu_backward_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_channel_sum": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "glis_bce_logits": [_vp, _f, _i, _f, _vp, _vp, _vp, _vp],
     "glis_mse_scaled": [_vp, _vp, _i64, _f, _vp, _vp, _i, _vp],

@@ -74,43 +74,98 @@ class ContractionSpec(object):
         return g
 
 
+# ---------------------------------------------------------------------------- packed weights
+PARAM_EPOCH = [0]   # bumped whenever parameters change outside torch's version counters
+
+
+def bump_param_epoch():
+    """Invalidate cached weight packs (called after the fused RMSprop kernel and after every
+    CUDA-graph replay, which update parameters without touching ``Tensor._version``)."""
+    PARAM_EPOCH[0] += 1
+
+
+class PackedWeights(object):
+    """Everything derived from one WN layer's (weight, scale) by ``glis_wn_prepare*``: the
+    per-channel norm and the fp32 / split-bf16 GEMM-order packs.  Built lazily per kind and
+    cached on the weight Parameter until the parameters change (once per optimizer step)."""
+
+    def __init__(self, weight, scale, spec):
+        self.weight, self.scale, self.spec = weight, scale, spec
+        self.out_axis = 1 if spec.transposed else 0
+        self.cout, self.cin = weight.shape[self.out_axis], weight.shape[1 - self.out_axis]
+        self.t = weight.numel() // (self.cout * self.cin)
+        self.norm = None
+        self.io = self.oi = None            # fp32 [T][Cin][Cout], [T][Cout][Cin]
+        self.fwd = self.bwd = None          # bf16 (hi, lo): [T][Cout][Cin], [T][Cin][Cout]
+
+    def _w(self):
+        w = self.weight.detach().contiguous()
+        sc = None if self.scale is None else self.scale.detach().contiguous()
+        return w, sc
+
+    def need_fp32(self, io, oi):
+        io, oi = io and self.io is None, oi and self.oi is None
+        if not (io or oi) and self.norm is not None:
+            return
+        w, sc = self._w()
+        dev = w.device
+        if self.norm is None:
+            self.norm = torch.empty(self.cout, device=dev, dtype=torch.float32)
+        a = torch.empty(self.t, self.cin, self.cout, device=dev, dtype=torch.float32) if io else None
+        b = torch.empty(self.t, self.cout, self.cin, device=dev, dtype=torch.float32) if oi else None
+        L.call("glis_wn_prepare", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
+               self.spec.norm_factor, L.ptr(self.norm), L.ptr(a), L.ptr(b), L.stream(),
+               kernels=2 if (io or oi) else 1)
+        if io:
+            self.io = a
+        if oi:
+            self.oi = b
+
+    def need_bf16(self, fwd, bwd, lo):
+        fwd, bwd = fwd and self.fwd is None, bwd and self.bwd is None
+        if not (fwd or bwd):
+            return
+        w, sc = self._w()
+        dev = w.device
+        if self.norm is None:
+            self.norm = torch.empty(self.cout, device=dev, dtype=torch.float32)
+
+        def plane(shape, want):
+            return torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
+
+        fh, fl = plane((self.t, self.cout, self.cin), fwd), plane((self.t, self.cout, self.cin), fwd and lo)
+        bh, bl = plane((self.t, self.cin, self.cout), bwd), plane((self.t, self.cin, self.cout), bwd and lo)
+        L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
+               self.spec.norm_factor, L.ptr(self.norm), L.ptr16(fh), L.ptr16(fl), L.ptr16(bh), L.ptr16(bl),
+               L.stream(), kernels=2)
+        if fwd:
+            self.fwd = (fh, fl)
+        if bwd:
+            self.bwd = (bh, bl)
+
+
+def packed_weights(weight, scale, spec):
+    key = (PARAM_EPOCH[0], getattr(weight, "_glis_epoch", 0), weight.data_ptr(), weight._version,
+           None if scale is None else scale._version, spec.precision, spec.transposed, spec.stride)
+    cached = getattr(weight, "_glis_packed", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    pw = PackedWeights(weight, scale, spec)
+    try:
+        weight._glis_packed = (key, pw)
+    except AttributeError:
+        pass
+    return pw
+
+
 def wn_prepare(weight, scale, spec, want_io=True, want_oi=True):
-    """norm [Cout], pack_io [T][Cin][Cout], pack_oi [T][Cout][Cin] of the effective weights."""
-    out_axis = 1 if spec.transposed else 0
-    cout = weight.shape[out_axis]
-    cin = weight.shape[1 - out_axis]
-    t = weight.numel() // (cout * cin)
-    w = weight.detach().contiguous()
-    norm = torch.empty(cout, device=w.device, dtype=torch.float32)
-    io = torch.empty(t, cin, cout, device=w.device, dtype=torch.float32) if want_io else None
-    oi = torch.empty(t, cout, cin, device=w.device, dtype=torch.float32) if want_oi else None
-    sc = None if scale is None else scale.detach().contiguous()
-    L.call("glis_wn_prepare", L.ptr(w), L.ptr(sc), out_axis, cout, cin, t, spec.norm_factor,
-           L.ptr(norm), L.ptr(io), L.ptr(oi), L.stream(), kernels=2 if (want_io or want_oi) else 1)
-    return norm, io, oi
+    """(norm [Cout], pack_io [T][Cin][Cout], pack_oi [T][Cout][Cin]) of the effective weights (uncached)."""
+    pw = PackedWeights(weight, scale, spec)
+    pw.need_fp32(want_io, want_oi)
+    return pw.norm, pw.io, pw.oi
 
 
-def wn_prepare_bf16(weight, scale, spec, want_fwd=True, want_bwd=True, lo=True):
-    """norm [Cout] and K-major bf16 (hi, lo) packs: fwd [T][Cout][Cin], bwd [T][Cin][Cout]."""
-    out_axis = 1 if spec.transposed else 0
-    cout, cin = weight.shape[out_axis], weight.shape[1 - out_axis]
-    t = weight.numel() // (cout * cin)
-    w = weight.detach().contiguous()
-    dev = w.device
-    norm = torch.empty(cout, device=dev, dtype=torch.float32)
-
-    def plane(shape, want):
-        return torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
-
-    fh, fl = plane((t, cout, cin), want_fwd), plane((t, cout, cin), want_fwd and lo)
-    bh, bl = plane((t, cin, cout), want_bwd), plane((t, cin, cout), want_bwd and lo)
-    sc = None if scale is None else scale.detach().contiguous()
-    L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), out_axis, cout, cin, t, spec.norm_factor, L.ptr(norm),
-           L.ptr16(fh), L.ptr16(fl), L.ptr16(bh), L.ptr16(bl), L.stream(),
-           kernels=2 if (want_fwd or want_bwd) else 1)
-    return norm, (fh, fl), (bh, bl)
-
-
+# ---------------------------------------------------------------------------- split-bf16 planes
 def split_bf16(x, lo=True):
     """(hi, lo) bf16 planes of a dense fp32 tensor, same memory order."""
     hi = torch.empty_like(x, dtype=torch.bfloat16)
@@ -119,20 +174,36 @@ def split_bf16(x, lo=True):
     return hi, lo_t
 
 
+def attach_planes(t, planes):
+    """Remember the hi/lo planes a producer kernel already wrote for ``t`` (consumed by the next
+    tensor-core layer instead of re-splitting)."""
+    if planes is not None and planes[0] is not None:
+        t._glis_planes = (planes[0], planes[1], t.data_ptr(), t._version)
+    return t
+
+
+def planes_of(t, lo=True):
+    """Planes of ``t``: the attached ones if still valid, else a fresh split."""
+    tag = getattr(t, "_glis_planes", None)
+    if tag is not None and tag[2] == t.data_ptr() and tag[3] == t._version and (tag[1] is not None or not lo):
+        return tag[0], tag[1]
+    return split_bf16(t, lo)
+
+
 def tc_supported(g):
     return bool(L.load().glis_conv_tc_supported(C.byref(g)))
 
 
-def _launch_geom(spec, relation, x_nhwc, out_shape_nchw):
-    if x_nhwc.dim() == 4:
-        n, ci, hi, wi = x_nhwc.shape
+def _launch_geom(spec, relation, in_shape, out_shape_nchw, like):
+    if len(in_shape) == 4:
+        n, ci, hi, wi = in_shape
         _, co, ho, wo = out_shape_nchw
-        out = _empty_nhwc(n, co, ho, wo, x_nhwc)
+        out = _empty_nhwc(n, co, ho, wo, like)
     else:
-        n, ci = x_nhwc.shape
+        n, ci = in_shape
         hi = wi = ho = wo = 1
         co = out_shape_nchw[1]
-        out = torch.empty((n, co), device=x_nhwc.device, dtype=torch.float32)
+        out = torch.empty((n, co), device=like.device, dtype=torch.float32)
     return spec.geom(relation, n, hi, wi, ci, ho, wo, co), out
 
 
@@ -140,29 +211,6 @@ def _tag(relation, g):
     if relation == L.CONV:
         return "conv_forward M=%d N=%d K=%d" % (g.N * g.Ho * g.Wo, g.Co, g.Ci * g.KH * g.KW)
     return "tconv_forward M=%d N=%d K=%d" % (g.N * g.Hi * g.Wi, g.Co * g.KH * g.KW, g.Ci)
-
-
-def conv_forward(spec, relation, x_nhwc, wpack, out_shape_nchw, bias=None, act=L.ACT_NONE,
-                 act_a=None, act_b=None, preact=None):
-    """fp32 FFMA gather-GEMM; ``x_nhwc`` and the result are NHWC-dense (or 2-D)."""
-    g, out = _launch_geom(spec, relation, x_nhwc, out_shape_nchw)
-    ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact))
-    with L.timed(_tag(relation, g) + " fp32"):
-        L.call("glis_conv_forward", C.byref(g), L.ptr(x_nhwc), L.ptr(wpack), C.byref(ep), L.ptr(out),
-               L.PREC_FP32, L.stream())
-    return out
-
-
-def conv_forward_tc(spec, relation, x_planes, wpack_planes, out_shape_nchw, like, precision, bias=None,
-                    act=L.ACT_NONE, act_a=None, act_b=None, preact=None):
-    """tcgen05 implicit GEMM on split-bf16 planes; returns the fp32 NHWC result."""
-    g, out = _launch_geom(spec, relation, like, out_shape_nchw)
-    ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact))
-    with L.timed(_tag(relation, g) + " tc"):
-        L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(x_planes[0]), L.ptr16(x_planes[1]),
-               L.ptr16(wpack_planes[0]), L.ptr16(wpack_planes[1]), C.byref(ep), L.ptr(out), None, None,
-               precision, L.stream())
-    return out
 
 
 def _use_tc(spec, relation, in_shape, out_shape):
@@ -174,122 +222,231 @@ def _use_tc(spec, relation, in_shape, out_shape):
     return tc_supported(spec.geom(relation, n, hi, wi, ci, ho, wo, co))
 
 
+def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_NONE, act_a=None, act_b=None,
+           want_preact=False, want_planes=False):
+    """One gather-GEMM launch (tensor cores when the geometry tiles, FFMA otherwise).
+
+    ``x``: fp32 NHWC-dense (or 2-D) input; ``forward_pack`` selects the layer's forward
+    ([T][Cout][Cin] K-major / [T][Cin][Cout] fp32) or data-gradient packs.
+    Returns (out_fp32, preact or None, (hi, lo) planes of out or None).
+    """
+    in_shape = tuple(x.shape)
+    prec = spec.precision
+    lo = prec == L.PREC_BF16X3
+    g, out = _launch_geom(spec, relation, in_shape, out_shape, x)
+    preact = torch.empty_like(out) if want_preact else None
+    use_tc = _use_tc(spec, relation, in_shape, out_shape)
+    planes = None
+    if want_planes and prec != L.PREC_FP32 and out.dim() == 4 and g.Co > 4:
+        planes = (torch.empty_like(out, dtype=torch.bfloat16),
+                  torch.empty_like(out, dtype=torch.bfloat16) if lo else None)
+    if use_tc:
+        pw.need_bf16(forward_pack, not forward_pack, lo)
+        wp = pw.fwd if forward_pack else pw.bwd
+        xp = planes_of(x, lo)
+        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None)
+        with L.timed(_tag(relation, g) + " tc"):
+            L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
+                   L.ptr16(wp[1]), C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
+                   L.ptr16(planes[1]) if planes else None, prec, L.stream())
+    else:
+        pw.need_fp32(forward_pack, not forward_pack)
+        wp = pw.io if forward_pack else pw.oi
+        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact),
+                        L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None)
+        with L.timed(_tag(relation, g) + " fp32"):
+            L.call("glis_conv_forward", C.byref(g), L.ptr(x), L.ptr(wp), C.byref(ep), L.ptr(out), L.PREC_FP32,
+                   L.stream())
+    return out, preact, planes
+
+
+def conv_forward(spec, relation, x_nhwc, wpack, out_shape_nchw, bias=None, act=L.ACT_NONE,
+                 act_a=None, act_b=None, preact=None):
+    """fp32 FFMA gather-GEMM on an explicit fp32 pack (kept for direct kernel tests)."""
+    g, out = _launch_geom(spec, relation, tuple(x_nhwc.shape), out_shape_nchw, x_nhwc)
+    ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None)
+    with L.timed(_tag(relation, g) + " fp32"):
+        L.call("glis_conv_forward", C.byref(g), L.ptr(x_nhwc), L.ptr(wpack), C.byref(ep), L.ptr(out),
+               L.PREC_FP32, L.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------- the WN layer operator
+def _layer_shapes(xc, weight, spec):
+    out_axis = 1 if spec.transposed else 0
+    cout = weight.shape[out_axis]
+    if xc.dim() == 4:
+        n, ci, h, w = xc.shape
+        ho, wo = spec.out_hw(h, w)
+        shape = (n, cout, ho, wo)
+    else:
+        shape = (xc.shape[0], cout)
+        ci = xc.shape[1]
+    if ci != weight.shape[1 - out_axis]:
+        raise RuntimeError("glis_b200: input has %d channels, weight expects %d"
+                           % (ci, weight.shape[1 - out_axis]))
+    return shape
+
+
+def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape):
+    """dgrad + wgrad + weight-norm projection + bias gradient of one WN layer.
+    ``dyc``: fp32 gradient w.r.t. the layer's affine output (NHWC-dense)."""
+    weight, scale = pw.weight, pw.scale
+    cout, cin, t = pw.cout, pw.cin, pw.t
+    prec = spec.precision
+    lo = prec == L.PREC_BF16X3
+    if dy_planes is not None:
+        attach_planes(dyc, dy_planes)
+    if xc.dim() == 4:
+        n, _, h, w = xc.shape
+        ho, wo = dyc.shape[2], dyc.shape[3]
+    else:
+        n, h, w, ho, wo = xc.shape[0], 1, 1, 1, 1
+
+    dx = None
+    if need_dx:
+        # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
+        rel = L.CONV if spec.transposed else L.TCONV
+        dx, _, _ = launch(spec, rel, dyc, tuple(xc.shape), pw, forward_pack=False)
+
+    dw = dscale = dbias = None
+    if need_dw or need_dscale:
+        graw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        if spec.transposed:   # small = x (Cin), big = dy (Cout)
+            g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin)
+            small, big = xc, dyc
+        else:                 # small = dy (Cout), big = x (Cin)
+            g = spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
+            small, big = dyc, xc
+        tag = "conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)
+        if prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
+            sp, bp = planes_of(small, lo), planes_of(big, lo)
+            with L.timed(tag + " tc"):
+                L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
+                       L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
+        else:
+            with L.timed(tag + " fp32"):
+                L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
+                       L.stream())
+        dw = torch.empty_like(graw)
+        if scale is not None:
+            dscale = torch.empty(cout, device=dw.device, dtype=torch.float32)
+        pw.need_fp32(False, False)  # the norm
+        wc = weight.detach().contiguous()
+        sc = None if scale is None else scale.detach().contiguous()
+        L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, cout, cin, t,
+               spec.norm_factor, L.ptr(dw), L.ptr(dscale), 0, L.stream())
+        if dscale is not None:
+            dscale = dscale.view_as(scale)
+    if need_dbias:
+        dbias = torch.empty(cout, device=dyc.device, dtype=torch.float32)
+        L.call("glis_channel_sum", L.ptr(dyc), L.ptr(dbias), dyc.numel(), cout, 1, 0, L.stream())
+        dbias = dbias.view(bias_shape)
+    return dx, dw, dscale, dbias
+
+
 class WNContraction(torch.autograd.Function):
     """``norm_scale_bias(F.conv2d / F.conv_transpose2d / F.linear (x, w))``.
 
     Reference: common/modules/WeightNormalizedConv.py:79-81, :96-99, :29-49 and
     common/modules/WeightNormalizedLinear.py:30-42.  The per-channel ``scale/norm`` is
-    folded into the packed weights (one pass over the parameters), the bias into the GEMM
-    epilogue; backward applies the closed-form projection of SURVEY.md App. E.
+    folded into the packed weights (one pass over the parameters per optimizer step), the
+    bias into the GEMM epilogue; backward applies the closed-form projection of SURVEY.md App. E.
     """
 
     @staticmethod
     def forward(ctx, x, weight, scale, bias, spec):
         xc = _nhwc(x)
-        need_dx = ctx.needs_input_grad[0]
-        out_axis = 1 if spec.transposed else 0
-        cout = weight.shape[out_axis]
-        if xc.dim() == 4:
-            n, ci, h, w = xc.shape
-            ho, wo = spec.out_hw(h, w)
-            shape = (n, cout, ho, wo)
-        else:
-            shape = (xc.shape[0], cout)
-            ci = xc.shape[1]
-        if ci != weight.shape[1 - out_axis]:
-            raise RuntimeError("glis_b200: input has %d channels, weight expects %d"
-                               % (ci, weight.shape[1 - out_axis]))
+        if getattr(x, "_glis_planes", None) is not None and xc is x:
+            pass  # planes travel with the tensor object
+        shape = _layer_shapes(xc, weight, spec)
+        pw = packed_weights(weight, scale, spec)
         b = None if bias is None else bias.detach().reshape(-1).contiguous()
         rel_f = L.TCONV if spec.transposed else L.CONV
-        rel_b = L.CONV if spec.transposed else L.TCONV
-        prec = spec.precision
-        tc_f = _use_tc(spec, rel_f, tuple(xc.shape), shape)
-        tc_b = need_dx and _use_tc(spec, rel_b, shape, tuple(xc.shape))
-        lo = prec == L.PREC_BF16X3
-        pack_oi = bwd_planes = None
-        if tc_f or tc_b:
-            norm, fwd_planes, bwd_planes = wn_prepare_bf16(weight, scale, spec, tc_f, tc_b, lo)
-        if not tc_f or (need_dx and not tc_b):
-            norm, pack_io, pack_oi = wn_prepare(weight, scale, spec, not tc_f, need_dx and not tc_b)
-        x_planes = (None, None)
-        if tc_f:
-            x_planes = split_bf16(xc, lo)
-            out = conv_forward_tc(spec, rel_f, x_planes, fwd_planes, shape, xc, prec, bias=b)
-        else:
-            out = conv_forward(spec, rel_f, xc, pack_io, shape, bias=b)
-        ctx.spec, ctx.tc_b, ctx.prec = spec, tc_b, prec
-        ctx.has_scale, ctx.has_bias = scale is not None, bias is not None
+        out, _, _ = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b)
+        ctx.spec, ctx.pw = spec, pw
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
-        saved_b = bwd_planes if tc_b else (None, None)
-        ctx.save_for_backward(xc, weight, scale, norm, pack_oi, saved_b[0], saved_b[1], x_planes[0], x_planes[1])
+        ctx.x_planes = getattr(xc, "_glis_planes", None)
+        ctx.save_for_backward(xc)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        xc, weight, scale, norm, pack_oi, bwd_hi, bwd_lo, x_hi, x_lo = ctx.saved_tensors
-        spec = ctx.spec
+        (xc,) = ctx.saved_tensors
+        if ctx.x_planes is not None:
+            xc._glis_planes = ctx.x_planes
         dyc = _nhwc(dy)
-        out_axis = 1 if spec.transposed else 0
-        cout, cin = weight.shape[out_axis], weight.shape[1 - out_axis]
-        t = weight.numel() // (cout * cin)
-        if xc.dim() == 4:
-            n, _, h, w = xc.shape
-            ho, wo = dyc.shape[2], dyc.shape[3]
-        else:
-            n, h, w, ho, wo = xc.shape[0], 1, 1, 1, 1
-
-        dx = None
-        want_lo = ctx.prec == L.PREC_BF16X3
-        dy_planes = None
-        if ctx.needs_input_grad[0]:
-            # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
-            rel = L.CONV if spec.transposed else L.TCONV
-            if ctx.tc_b:
-                dy_planes = split_bf16(dyc, want_lo)
-                dx = conv_forward_tc(spec, rel, dy_planes, (bwd_hi, bwd_lo), tuple(xc.shape), dyc, ctx.prec)
-            else:
-                dx = conv_forward(spec, rel, dyc, pack_oi, tuple(xc.shape))
-
-        dw = dscale = dbias = None
-        if ctx.needs_input_grad[1] or (ctx.has_scale and ctx.needs_input_grad[2]):
-            graw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-            if spec.transposed:   # small = x (Cin), big = dy (Cout)
-                g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin)
-                small, big = xc, dyc
-            else:                 # small = dy (Cout), big = x (Cin)
-                g = spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
-                small, big = dyc, xc
-            tag = "conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)
-            if ctx.prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
-                if dy_planes is None:
-                    dy_planes = split_bf16(dyc, want_lo)
-                xp = (x_hi, x_lo) if x_hi is not None else split_bf16(xc, want_lo)
-                sp, bp = (xp, dy_planes) if spec.transposed else (dy_planes, xp)
-                with L.timed(tag + " tc"):
-                    L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
-                           L.ptr16(bp[1]), L.ptr(graw), ctx.prec, L.stream())
-            else:
-                with L.timed(tag + " fp32"):
-                    L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
-                           L.stream())
-            dw = torch.empty_like(graw)
-            if ctx.has_scale:
-                dscale = torch.empty(cout, device=dw.device, dtype=torch.float32)
-            wc = weight.detach().contiguous()
-            sc = None if scale is None else scale.detach().contiguous()
-            L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(norm), out_axis, cout, cin, t,
-                   spec.norm_factor, L.ptr(dw), L.ptr(dscale), 0, L.stream())
-            if dscale is not None:
-                dscale = dscale.view_as(scale)
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            dbias = torch.empty(cout, device=dyc.device, dtype=torch.float32)
-            L.call("glis_channel_sum", L.ptr(dyc), L.ptr(dbias), dyc.numel(), cout, 1, 0, L.stream())
-            dbias = dbias.view(ctx.bias_shape)
+        ni = ctx.needs_input_grad
+        dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dyc, None, ni[0], ni[1],
+                                                ctx.pw.scale is not None and ni[2],
+                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape)
         return dx, dw, dscale, dbias, None
 
 
 def wn_contraction(x, weight, scale, bias, spec):
-    out = WNContraction.apply(x, weight, scale, bias, spec)
+    return WNContraction.apply(x, weight, scale, bias, spec)
+
+
+class WNContractionTPReLU(torch.autograd.Function):
+    """A WN layer followed by TPReLU as ONE forward kernel: the GEMM epilogue applies the bias and
+    the translated PReLU, stores the pre-activation for backward and (tensor-core mode) the bf16
+    hi/lo planes of the activated output for the next layer.  Backward runs the TPReLU gradient as
+    one pass that writes the layer's output gradient directly as planes.
+    Reference: the (conv, tprelu) pairs of common/model.py:31-45, :112-127, :222-251."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, bias, a_raw, b_t, spec):
+        xc = _nhwc(x)
+        shape = _layer_shapes(xc, weight, spec)
+        pw = packed_weights(weight, scale, spec)
+        b = None if bias is None else bias.detach().reshape(-1).contiguous()
+        a_c = a_raw.detach().clamp(0, 1)
+        rel_f = L.TCONV if spec.transposed else L.CONV
+        out, preact, planes = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_TPRELU,
+                                     act_a=a_c, act_b=b_t.detach().contiguous(), want_preact=True,
+                                     want_planes=True)
+        ctx.spec, ctx.pw = spec, pw
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.x_planes = getattr(xc, "_glis_planes", None)
+        ctx.save_for_backward(xc, preact, a_raw, b_t)
+        ctx.set_materialize_grads(False)   # no zero tensors for the (non-differentiable) plane outputs
+        if planes is None:
+            return out, None, None
+        ctx.mark_non_differentiable(planes[0])
+        if planes[1] is not None:
+            ctx.mark_non_differentiable(planes[1])
+        return out, planes[0], planes[1]
+
+    @staticmethod
+    def backward(ctx, dout, _dhi, _dlo):
+        xc, preact, a_raw, b_t = ctx.saved_tensors
+        if ctx.x_planes is not None:
+            xc._glis_planes = ctx.x_planes
+        spec = ctx.spec
+        c = a_raw.numel()
+        if dout is None:
+            dout = torch.zeros_like(preact)
+        doc = _nhwc(dout)
+        lo = spec.precision == L.PREC_BF16X3
+        want_planes = spec.precision != L.PREC_FP32 and doc.dim() == 4
+        dy = torch.empty_like(preact)
+        dy_hi = torch.empty_like(preact, dtype=torch.bfloat16) if want_planes else None
+        dy_lo = torch.empty_like(preact, dtype=torch.bfloat16) if (want_planes and lo) else None
+        da = torch.zeros(c, device=doc.device, dtype=torch.float32)
+        db = torch.zeros(c, device=doc.device, dtype=torch.float32)
+        L.call("glis_tprelu_backward_planes", L.ptr(preact), L.ptr(a_raw.detach()), L.ptr(b_t.detach()), L.ptr(doc),
+               L.ptr(dy), L.ptr16(dy_hi), L.ptr16(dy_lo), L.ptr(da), L.ptr(db), preact.numel(), c, 1, L.stream())
+        ni = ctx.needs_input_grad
+        dx, dw, dscale, dbias = _layer_backward(spec, ctx.pw, xc, dy, (dy_hi, dy_lo) if want_planes else None,
+                                                ni[0], ni[1], ctx.pw.scale is not None and ni[2],
+                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape)
+        return dx, dw, dscale, dbias, da, db, None
+
+
+def wn_contraction_tprelu(x, weight, scale, bias, a_raw, b_t, spec):
+    out, hi, lo = WNContractionTPReLU.apply(x, weight, scale, bias, a_raw, b_t, spec)
+    if hi is not None:
+        attach_planes(out, (hi, lo))
     return out
 
 
@@ -343,10 +500,17 @@ def tprelu(x, a_raw, b):
     return TPReLUFunction.apply(x, a_raw, b)
 
 
-def rmsprop_(p_flat, g_flat, v_flat, lr, alpha=0.9, eps=1e-6, gscale=1.0):
-    """Fused RMSprop over flat parameter / gradient / square-average buffers (g_lis/main.py:313-314)."""
+def rmsprop_(p_flat, g_flat, v_flat, lr, alpha=0.9, eps=1e-6, gscale=1.0, params=None):
+    """Fused RMSprop over flat parameter / gradient / square-average buffers (g_lis/main.py:313-314).
+    ``params``: the Parameters living in ``p_flat`` — their cached weight packs are invalidated;
+    without it every cached pack is."""
     L.call("glis_rmsprop", L.ptr(p_flat), L.ptr(g_flat), L.ptr(v_flat), p_flat.numel(), lr, alpha, eps, gscale,
            L.stream())
+    if params is None:
+        bump_param_epoch()
+    else:
+        for p in params:
+            p._glis_epoch = getattr(p, "_glis_epoch", 0) + 1
 
 
 def randn_(out, seed, offset=0):

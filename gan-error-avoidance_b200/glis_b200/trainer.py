@@ -58,7 +58,7 @@ class FlatParams(object):
                 p.grad = want
 
     def rmsprop_step(self, lr, alpha=0.9, eps=1e-6, gscale=1.0):
-        ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale)
+        ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale, params=self.params)
 
 
 class GLISTrainer(object):
@@ -83,15 +83,18 @@ class GLISTrainer(object):
         ones = torch.ones(B, 1, device=real.device)
         zeros = torch.zeros(B, 1, device=real.device)
 
-        # ---- D step
+        # ---- D step: real and generated batches go through D as ONE batch of 2B images.  The two
+        # BCE means are taken over their own halves, so the gradients are exactly the sum of the
+        # reference's two backward passes (g_lis/main.py:555-565) at half the kernel launches.
         self._set_dis_requires_grad(True)
         self.dis_flat.zero_grad()
-        loss_d_real = F.binary_cross_entropy(dis(real), ones)
-        loss_d_real.backward()
         with torch.no_grad():
             fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
-        loss_d_fake = F.binary_cross_entropy(dis(fake.detach()), zeros)
-        loss_d_fake.backward()
+        both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
+        p_both = dis(both)
+        loss_d_real = F.binary_cross_entropy(p_both[:B], ones)
+        loss_d_fake = F.binary_cross_entropy(p_both[B:], zeros)
+        (loss_d_real + loss_d_fake).backward()
         self.dis_flat.rebind_grads()
         gs = self.grad_sync(self.dis_flat.g, "dis") if self.grad_sync else 1.0
         self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
@@ -152,6 +155,7 @@ class GraphedStep(object):
             out = self.tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
         if self.pool is None:
             self.pool = graph.pool()
+        ops.bump_param_epoch()
         self.graphs[key] = (graph, out)
         return self.graphs[key]
 
@@ -181,4 +185,5 @@ class GraphedStep(object):
         if z_g is not None:
             self.z_g.copy_(z_g, non_blocking=True)
         entry[0].replay()
+        ops.bump_param_epoch()   # the replay updated the parameters behind torch's back
         return entry[1]

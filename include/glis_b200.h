@@ -67,6 +67,8 @@ typedef struct glis_epilogue {
   const float* act_a;  /* TPReLU slope, already clamped to [0,1] (per out-channel) */
   const float* act_b;  /* TPReLU translation (per out-channel) */
   float* preact;       /* if non-NULL, y (before act) is also stored here (NHWC) */
+  void* out_hi;        /* fp32 kernels only: if non-NULL, bf16 hi plane of the activated output */
+  void* out_lo;        /*   ... and its lo plane (may be NULL) — feeds the next tensor-core layer */
 } glis_epilogue_t;
 
 const char* glis_last_error(void);
@@ -153,6 +155,11 @@ int glis_tprelu_forward(const float* x, const float* a_raw, const float* b, floa
 int glis_tprelu_backward(const float* x, const float* a_raw, const float* b, const float* dout,
                          float* dx, float* da, float* db, int64_t numel, int C, int inner,
                          void* stream);
+/* As glis_tprelu_backward, writing dx as fp32 (dx may be NULL) and/or as bf16 hi/lo planes
+ * (dx_hi may be NULL; dx_lo may be NULL) so the tensor-core dgrad / wgrad can consume it directly. */
+int glis_tprelu_backward_planes(const float* x, const float* a_raw, const float* b, const float* dout,
+                                float* dx, void* dx_hi, void* dx_lo, float* da, float* db, int64_t numel,
+                                int C, int inner, void* stream);
 /* out[c] (+)= sum over elements of channel c (bias gradient: WeightNormalizedConv.py:47-48 backward). */
 int glis_channel_sum(const float* x, float* out, int64_t numel, int C, int inner, int accumulate,
                      void* stream);

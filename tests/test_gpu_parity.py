@@ -272,10 +272,12 @@ def test_golden_training_iterations(golden_dir, precision):
         g = _grp(s, "it%d" % it)
         f = lambda a: torch.from_numpy(a).float().to(DEV)
         out = tr.step(f(g["real"]), f(g["zd"]), f(g["zg"]), depth_d=int(kd), depth_g=int(kg))
+        # iteration 0 starts from identical weights; later ones inherit the (bounded) parameter drift below
+        ltol = FWD_TOL if it == 0 else (5e-4 if precision == "fp32" else 3e-3)
         for name in ("d_real", "d_fake", "g"):
-            assert abs(out[name].item() - float(g[name])) <= FWD_TOL * abs(float(g[name])), (it, name)
+            assert abs(out[name].item() - float(g[name])) <= ltol * abs(float(g[name])), (it, name)
         for i, l in enumerate(out["r"]):
-            assert abs(l.item() - float(g["r"][i])) <= FWD_TOL * abs(float(g["r"][i])), (it, "r", i)
+            assert abs(l.item() - float(g["r"][i])) <= ltol * abs(float(g["r"][i])), (it, "r", i)
         # lr = 1e-2 makes every RMSprop update O(lr): parameters must track to ~1e-3 of their scale
         # (sign-like early RMSprop steps amplify gradient error where |g| ~ eps; see _run_steps)
         ptol = 5e-3 if precision == "fp32" else 5e-2
