@@ -376,8 +376,16 @@ int validate_geom(const glis_geom_t* g, const char* who) {
   return GLIS_OK;
 }
 
+bool is_linear_geom(const glis_geom_t* g);
+int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
+                        float* out, cudaStream_t st);
+
 int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                       float* out, cudaStream_t st) {
+  if (is_linear_geom(g)) {
+    const int rc = simt_linear_forward(g, in, wpack, ep, out, st);
+    if (rc != GLIS_E_UNSUPPORTED) return rc;
+  }
   {
     const int64_t pixels = (int64_t)g->N * g->Ho * g->Wo;
     const size_t wsmem = (size_t)g->KH * g->KW * g->Ci * sizeof(float4);
