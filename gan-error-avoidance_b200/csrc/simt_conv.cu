@@ -284,6 +284,200 @@ small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* _
   }
 }
 
+// The case that matters (G level 0 / D level-0 data gradient): 4x4 kernel, stride 2, transposed
+// relation, CI input channels.  Every output pixel has exactly 2x2 taps; all of a lane's input
+// loads (CI/32 float4 per tap) are issued before the first FMA so that one pixel keeps
+// 4*CI/32 128-bit loads in flight.
+template <int CI>
+__global__ void __launch_bounds__(SC_NT)
+small_cout_tconv4x4s2(const glis_geom_t g, const float* __restrict__ in, const float* __restrict__ wp,
+                      const glis_epilogue_t ep, float* __restrict__ out) {
+  constexpr int C4 = CI / 4, R = CI / 32;
+  __shared__ float4 w4[16 * CI];   // [tap][j][c4]
+  for (int i = threadIdx.x; i < 16 * CI; i += SC_NT) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = wp + (int64_t)i * g.Co;
+    v.x = __ldg(src);
+    if (g.Co > 1) v.y = __ldg(src + 1);
+    if (g.Co > 2) v.z = __ldg(src + 2);
+    if (g.Co > 3) v.w = __ldg(src + 3);
+    const int tap = i / CI, ci = i - tap * CI;
+    w4[(tap * 4 + (ci & 3)) * C4 + (ci >> 2)] = v;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int Hq = g.Ho / 2, Wq = g.Wo / 2;
+  const int64_t per_phase = (int64_t)g.N * Hq * Wq, P = 4 * per_phase;
+  const int64_t groups = (int64_t)gridDim.x * (SC_NT / 8);
+  for (int64_t pix = (int64_t)blockIdx.x * (SC_NT / 8) + (threadIdx.x >> 3);; pix += groups) {
+    const bool live = pix < P;
+    if (__all_sync(0xffffffffu, !live)) break;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0, oy = 0, ox = 0;
+    if (live) {
+      const int phase = (int)(pix / per_phase);
+      const int64_t r = pix - (int64_t)phase * per_phase;
+      const int qx = (int)(r % Wq); const int64_t t = r / Wq; const int qy = (int)(t % Hq); n = (int)(t / Hq);
+      oy = 2 * qy + (phase >> 1); ox = 2 * qx + (phase & 1);
+      const int kh0 = (oy + g.pad_h) & 1, kw0 = (ox + g.pad_w) & 1;
+      const int iy0 = (oy + g.pad_h - kh0) >> 1, ix0 = (ox + g.pad_w - kw0) >> 1;   // taps kh0, kw0
+      float4 xv[4][R];
+      int tapi[4];
+#pragma unroll
+      for (int th = 0; th < 2; ++th)
+#pragma unroll
+        for (int tw = 0; tw < 2; ++tw) {
+          const int iy = iy0 - th, ix = ix0 - tw;     // taps kh0 + 2*th, kw0 + 2*tw
+          const bool ok = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+          const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)n * g.Hi + iy) * g.Wi + ix) * CI);
+          tapi[th * 2 + tw] = (kh0 + 2 * th) * 4 + (kw0 + 2 * tw);
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr)
+            xv[th * 2 + tw][rr] = ok ? __ldg(src + sub + 8 * rr) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        const float4* wt = w4 + tapi[tp] * CI;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const int c4 = sub + 8 * rr;
+          const float4 x = xv[tp][rr];
+          const float4 w0 = wt[c4], w1 = wt[C4 + c4], w2 = wt[2 * C4 + c4], w3 = wt[3 * C4 + c4];
+          a0 = fmaf(x.x, w0.x, a0); a1 = fmaf(x.x, w0.y, a1); a2 = fmaf(x.x, w0.z, a2); a3 = fmaf(x.x, w0.w, a3);
+          a0 = fmaf(x.y, w1.x, a0); a1 = fmaf(x.y, w1.y, a1); a2 = fmaf(x.y, w1.z, a2); a3 = fmaf(x.y, w1.w, a3);
+          a0 = fmaf(x.z, w2.x, a0); a1 = fmaf(x.z, w2.y, a1); a2 = fmaf(x.z, w2.z, a2); a3 = fmaf(x.z, w2.w, a3);
+          a0 = fmaf(x.w, w3.x, a0); a1 = fmaf(x.w, w3.y, a1); a2 = fmaf(x.w, w3.z, a2); a3 = fmaf(x.w, w3.w, a3);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (live && sub < g.Co) {   // lane c of the group finishes output channel c
+      const float acc = sub == 0 ? a0 : (sub == 1 ? a1 : (sub == 2 ? a2 : a3));
+      const int64_t idx = (((int64_t)n * g.Ho + oy) * g.Wo + ox) * g.Co + sub;
+      float y = acc;
+      if (ep.bias) y += __ldg(ep.bias + sub);
+      if (ep.preact) ep.preact[idx] = y;
+      float o = y;
+      if (ep.act == GLIS_ACT_TPRELU) {
+        const float b = __ldg(ep.act_b + sub), a = __ldg(ep.act_a + sub);
+        const float tt = y - b;
+        o = (tt > 0.f ? tt : a * tt) + b;
+      } else if (ep.act == GLIS_ACT_SIGMOID) {
+        o = 1.f / (1.f + expf(-y));
+      }
+      out[idx] = o;
+    }
+  }
+}
+
+// Forward launch for the image-side conv with <= 4 input channels (D / R level 0: 3 -> 64).
+// K = taps * Cin is only 48, so the layer is bound by writing its output.  One thread owns one
+// output pixel and all (<= 64) output channels: the 48 input values sit in registers, the
+// weights are read from shared memory as warp-wide broadcasts, and the thread writes whole
+// 256-byte runs of its pixel (fp32 output, pre-activation, bf16 planes).
+constexpr int SI_NT = 128, SI_MAXK = 64, SI_MAXCO = 64;
+// TKH/TKW/TCI > 0: kernel extent known at compile time (the 4x4x3 case) so the input gather
+// indexes registers directly; 0: runtime extent.
+template <int TKH, int TKW, int TCI>
+__global__ void __launch_bounds__(SI_NT)
+small_cin_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __restrict__ wp,
+              const glis_epilogue_t ep, float* __restrict__ out) {
+  __shared__ __align__(16) float Ws[SI_MAXK * SI_MAXCO];   // [k = tap*Ci + ci][co]
+  __shared__ float s_bias[SI_MAXCO], s_a[SI_MAXCO], s_b[SI_MAXCO];
+  const int K = g.KH * g.KW * g.Ci;
+  for (int i = threadIdx.x; i < K * g.Co; i += SI_NT) Ws[(i / g.Co) * SI_MAXCO + (i % g.Co)] = __ldg(wp + i);
+  for (int c = threadIdx.x; c < g.Co; c += SI_NT) {
+    s_bias[c] = ep.bias ? __ldg(ep.bias + c) : 0.f;
+    s_a[c] = ep.act == GLIS_ACT_TPRELU ? __ldg(ep.act_a + c) : 0.f;
+    s_b[c] = ep.act == GLIS_ACT_TPRELU ? __ldg(ep.act_b + c) : 0.f;
+  }
+  __syncthreads();
+  const int64_t P = (int64_t)g.N * g.Ho * g.Wo;
+  const int64_t pix = (int64_t)blockIdx.x * SI_NT + threadIdx.x;
+  if (pix >= P) return;
+  const int ox = (int)(pix % g.Wo); const int64_t t = pix / g.Wo; const int oy = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+
+  float x[SI_MAXK];
+#pragma unroll
+  for (int k = 0; k < SI_MAXK; ++k) x[k] = 0.f;
+  if (TKH > 0) {
+#pragma unroll
+    for (int kh = 0; kh < TKH; ++kh) {
+      const int iy = oy * g.stride_h - g.pad_h + kh * g.dil_h;
+#pragma unroll
+      for (int kw = 0; kw < TKW; ++kw) {
+        const int ix = ox * g.stride_w - g.pad_w + kw * g.dil_w;
+        const bool ok = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+        const float* src = in + (((int64_t)n * g.Hi + iy) * g.Wi + ix) * TCI;
+#pragma unroll
+        for (int ci = 0; ci < TCI; ++ci) x[(kh * TKW + kw) * TCI + ci] = ok ? __ldg(src + ci) : 0.f;
+      }
+    }
+  } else {
+    int k = 0;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int iy = oy * g.stride_h - g.pad_h + kh * g.dil_h;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int ix = ox * g.stride_w - g.pad_w + kw * g.dil_w;
+        const bool ok = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+        const float* src = in + (((int64_t)n * g.Hi + iy) * g.Wi + ix) * g.Ci;
+        for (int ci = 0; ci < g.Ci; ++ci, ++k) {
+          const float v = ok ? __ldg(src + ci) : 0.f;
+          // registers need compile-time indices: select into the unrolled array
+#pragma unroll
+          for (int kk = 0; kk < SI_MAXK; ++kk) if (kk == k) x[kk] = v;
+        }
+      }
+    }
+  }
+  const int64_t base = pix * g.Co;
+  for (int c0 = 0; c0 < g.Co; c0 += 16) {       // 16 channels at a time keeps the accumulators in registers
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SI_MAXK; ++k) {
+      if (k < K) {
+        const float4* wrow = reinterpret_cast<const float4*>(Ws + k * SI_MAXCO + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = wrow[q];
+          acc[4 * q + 0] = fmaf(x[k], w.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x[k], w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(x[k], w.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x[k], w.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    float y[16], o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      y[j] = acc[j] + s_bias[c0 + j];
+      o[j] = y[j];
+      if (ep.act == GLIS_ACT_TPRELU) { const float tt = y[j] - s_b[c0 + j]; o[j] = (tt > 0.f ? tt : s_a[c0 + j] * tt) + s_b[c0 + j]; }
+      else if (ep.act == GLIS_ACT_SIGMOID) o[j] = 1.f / (1.f + expf(-y[j]));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ep.preact) reinterpret_cast<float4*>(ep.preact + base + c0)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      reinterpret_cast<float4*>(out + base + c0)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+    if (ep.out_hi) {
+      __align__(16) __nv_bfloat16 h[16], l[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sm100::split_bf16(o[j], h[j], l[j]);
+      uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + base + c0);
+      dh[0] = reinterpret_cast<uint4*>(h)[0]; dh[1] = reinterpret_cast<uint4*>(h)[1];
+      if (ep.out_lo) {
+        uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + base + c0);
+        dl[0] = reinterpret_cast<uint4*>(l)[0]; dl[1] = reinterpret_cast<uint4*>(l)[1];
+      }
+    }
+  }
+}
+
 // Weight gradient: G[a][b][tap] += sum_pix small[pix][a] * big[gather(pix,tap)][b]
 // Block tile 64 (a) x 64 (flattened tap*Cb + b), K = pixels of `small`, split over blockIdx.z.
 __global__ void __launch_bounds__(NT)
@@ -386,6 +580,19 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
     const int rc = simt_linear_forward(g, in, wpack, ep, out, st);
     if (rc != GLIS_E_UNSUPPORTED) return rc;
   }
+  if (g->relation == GLIS_CONV && g->Ci <= 4 && g->KH * g->KW * g->Ci <= SI_MAXK && g->Co <= SI_MAXCO &&
+      g->Co % 16 == 0 && (int64_t)g->N * g->Ho * g->Wo >= 4096 &&
+      ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ep->preact) |
+        reinterpret_cast<uintptr_t>(ep->out_hi) | reinterpret_cast<uintptr_t>(ep->out_lo)) & 15) == 0) {
+    const int64_t pixels = (int64_t)g->N * g->Ho * g->Wo;
+    const unsigned blocks = (unsigned)((pixels + SI_NT - 1) / SI_NT);
+    if (g->KH == 4 && g->KW == 4 && g->Ci == 3)
+      small_cin_fwd<4, 4, 3><<<blocks, SI_NT, 0, st>>>(*g, in, wpack, *ep, out);
+    else
+      small_cin_fwd<0, 0, 0><<<blocks, SI_NT, 0, st>>>(*g, in, wpack, *ep, out);
+    GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, small Cin)");
+    return GLIS_OK;
+  }
   {
     const int64_t pixels = (int64_t)g->N * g->Ho * g->Wo;
     const size_t wsmem = (size_t)g->KH * g->KW * g->Ci * sizeof(float4);
@@ -398,6 +605,12 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
       }
       int64_t want = (pixels + SC_NT / 8 - 1) / (SC_NT / 8);
       const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+      if (g->relation == GLIS_TCONV && g->KH == 4 && g->KW == 4 && g->stride_h == 2 && g->stride_w == 2 &&
+          g->Ci == 64 && g->Ho % 2 == 0 && g->Wo % 2 == 0 && g->pad_h <= 2 && g->pad_w <= 2) {
+        small_cout_tconv4x4s2<64><<<blocks, SC_NT, 0, st>>>(*g, in, wpack, *ep, out);
+        GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, small Cout 4x4s2)");
+        return GLIS_OK;
+      }
       small_cout_fwd<<<blocks, SC_NT, wsmem, st>>>(*g, in, wpack, *ep, out);
       GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, small Cout)");
       return GLIS_OK;
