@@ -57,6 +57,27 @@ class FlatParams(object):
                     want.add_(p.grad)
                 p.grad = want
 
+    def optimizer_state_dict(self, lr, alpha=0.9, eps=1e-6):
+        """RMSprop state in ``torch.optim.RMSprop.state_dict()`` form — what the reference saves as
+        ``*_opt.pt`` (g_lis/main.py:345-349) — so checkpoints move both ways."""
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            state[i] = {"step": torch.tensor(0.0),
+                        "square_avg": self.v[o:o + p.numel()].view(p.shape).detach().cpu().clone()}
+        group = {"lr": lr, "momentum": 0, "alpha": alpha, "eps": eps, "centered": False, "weight_decay": 0,
+                 "capturable": False, "foreach": None, "maximize": False, "differentiable": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            entry = sd["state"].get(i)
+            seg = self.v[o:o + p.numel()]
+            if entry is None:          # never stepped in the saved run: legacy "skip" == zero state
+                seg.zero_()
+            else:
+                seg.copy_(entry["square_avg"].reshape(-1).to(seg.device, dtype=torch.float32))
+
     def rmsprop_step(self, lr, alpha=0.9, eps=1e-6, gscale=1.0):
         ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale, params=self.params)
 
@@ -131,7 +152,7 @@ class GraphedStep(object):
     stay valid until the next replay of the same graph.
     """
 
-    def __init__(self, trainer, batch, height, width, code, device, warmup=3):
+    def __init__(self, trainer, batch, height, width, code, device, warmup=2):
         self.tr = trainer
         self.real = torch.zeros(batch, 3, height, width, device=device).contiguous(
             memory_format=torch.channels_last)
@@ -143,16 +164,29 @@ class GraphedStep(object):
 
     def _capture(self, key):
         depth_d, depth_g = key
+        tr = self.tr
+        flats = [tr.gen_flat, tr.dis_flat]
+        # the warm-up iterations (lazy CUDA init, allocator) must not count as training:
+        # snapshot parameters, gradients and optimizer state, restore them before capturing
+        saved = [(f.p.clone(), f.g.clone(), f.v.clone()) for f in flats]
+        rng_state = tr.gen.rng.getstate() if hasattr(tr.gen.rng, "getstate") else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):          # warm-up off the capture stream (allocator, lazy init)
+        with torch.cuda.stream(side):
             for _ in range(self.warmup):
-                self.tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
+                tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        for f, (p, g, v) in zip(flats, saved):
+            f.p.copy_(p); f.g.copy_(g); f.v.copy_(v)
+        if rng_state is not None:
+            tr.gen.rng.setstate(rng_state)
+        # Every weight pack the step uses must be (re)built INSIDE the graph: a pack cached from the
+        # warm-up would be read at its capture-time address and go stale after the first replay.
+        ops.bump_param_epoch()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, pool=self.pool):
-            out = self.tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
+            out = tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
         if self.pool is None:
             self.pool = graph.pool()
         ops.bump_param_epoch()
@@ -169,14 +203,15 @@ class GraphedStep(object):
         key = (depth_d, depth_g)
         entry = self.graphs.get(key)
         if entry is None:
-            # NOTE: capturing runs `warmup` + 1 real training iterations on whatever is in the buffers
             if real is not None:
                 self.real.copy_(real)
             if z_d is not None:
                 self.z_d.copy_(z_d)
             if z_g is not None:
                 self.z_g.copy_(z_g)
-            entry = self._capture(key)
+            entry = self._capture(key)     # capturing records the kernels, it does not run them
+            entry[0].replay()
+            ops.bump_param_epoch()
             return entry[1]
         if real is not None:
             self.real.copy_(real, non_blocking=True)
@@ -187,3 +222,93 @@ class GraphedStep(object):
         entry[0].replay()
         ops.bump_param_epoch()   # the replay updated the parameters behind torch's back
         return entry[1]
+
+
+class RIterTrainer(object):
+    """The R-iterative trainer's outer iteration (r_iterative/main.py:428-535) on the sm_100a
+    kernels: plain generator, reverser R and discriminator, three flat RMSprop states.
+
+    Per hop r of the chain: G update, (r > 0) R update on
+    ``λ^r·MSE(code, first_code) + (1-λ^r)·BCE(dis(gen(code)), 1)``, D update.  The stochastic
+    ``do_train`` schedule (:445-451) is drawn from ``self.rng`` unless ``train_flags`` is given.
+    During the R update the generator's parameter gradients are not needed (the reference lets
+    them pile up and zero-fills them before the next G step), so they are not computed.
+    """
+
+    def __init__(self, gen, rev, dis, lr, lambda_r=0.9, r_iterations=3, alpha=0.9, eps=1e-6, rng=None):
+        import random as _random
+        self.gen, self.rev, self.dis = gen, rev, dis
+        self.lr, self.lambda_r, self.r_iterations, self.alpha, self.eps = lr, lambda_r, r_iterations, alpha, eps
+        self.gen_flat, self.rev_flat, self.dis_flat = FlatParams(gen), FlatParams(rev), FlatParams(dis)
+        self.rng = rng if rng is not None else _random
+
+    def draw_train_flags(self, always_train_all=False):
+        hops = 1 + self.r_iterations
+        if always_train_all:
+            return [True] * hops
+        flags, last = [], False
+        for r_idx in range(hops):
+            hit = self.rng.random() <= (r_idx + 1) / float(hops)
+            last = last or (r_idx == hops - 1) or hit
+            flags.append(last)
+        return flags
+
+    @staticmethod
+    def _requires_grad(flat, flag):
+        for p in flat.params:
+            p.requires_grad_(flag)
+
+    def step(self, first_code, reals, train_flags=None):
+        gen, rev, dis = self.gen, self.rev, self.dis
+        B = first_code.shape[0]
+        ones = torch.ones(B, 1, device=first_code.device)
+        zeros = torch.zeros(B, 1, device=first_code.device)
+        hops = 1 + self.r_iterations
+        if train_flags is None:
+            train_flags = [True] * hops
+        reals = list(reals)
+        out, last_images, last_code = [], None, None
+        for r_idx in range(hops):
+            code = first_code if last_images is None else rev(last_images.detach())
+            if not train_flags[r_idx]:
+                with torch.no_grad():
+                    last_images = gen(code.detach())
+                last_code = code
+                out.append(None)
+                continue
+            rec = {}
+            # ---- G
+            self.gen_flat.zero_grad()
+            self._requires_grad(self.dis_flat, False)
+            generated = gen(code.detach())
+            loss_g = F.binary_cross_entropy(dis(generated), ones)
+            loss_g.backward()
+            self.gen_flat.rebind_grads()
+            self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps)
+            rec["g"] = loss_g.detach()
+            # ---- R (through the updated G and the frozen D)
+            if last_code is not None:
+                self.rev_flat.zero_grad()
+                self._requires_grad(self.gen_flat, False)
+                loss_g2 = F.binary_cross_entropy(dis(gen(code)), ones)
+                loss_r = F.mse_loss(code, first_code.detach())
+                lar = self.lambda_r ** r_idx
+                (lar * loss_r + (1 - lar) * loss_g2).backward()
+                self._requires_grad(self.gen_flat, True)
+                self.rev_flat.rebind_grads()
+                self.rev_flat.rmsprop_step(self.lr, self.alpha, self.eps)
+                rec["r"] = loss_r.detach()
+            # ---- D (real and the hop's pre-update generated batch as one 2B batch)
+            self.dis_flat.zero_grad()
+            self._requires_grad(self.dis_flat, True)
+            both = torch.cat([reals.pop(0).contiguous(memory_format=torch.channels_last), generated.detach()], dim=0)
+            p_both = dis(both)
+            loss_d_real = F.binary_cross_entropy(p_both[:B], ones)
+            loss_d_fake = F.binary_cross_entropy(p_both[B:], zeros)
+            (loss_d_real + loss_d_fake).backward()
+            self.dis_flat.rebind_grads()
+            self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps)
+            rec["d_real"], rec["d_fake"] = loss_d_real.detach(), loss_d_fake.detach()
+            last_images, last_code = generated, code
+            out.append(rec)
+        return out

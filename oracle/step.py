@@ -95,3 +95,65 @@ class GLISOracleTrainer:
     def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
         return glis_iteration(self.gen, self.dis, self.gen_state, self.dis_state, real, z_d, z_g,
                               self.lr, self.lambda_r, depth_d, depth_g, self.alpha, self.eps)
+
+
+def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, reals, lr, lambda_r=0.9,
+                    r_iterations=3, train_flags=None, alpha=0.9, eps=1e-6):
+    """One outer iteration of the R-iterative trainer, restated from ``r_iterative/main.py:428-535``.
+
+    A chain of ``1 + r_iterations`` hops: hop 0 starts from ``first_code`` (noise), hop r > 0 from
+    ``rev(images of hop r-1)``.  A hop with ``train_flags[r]`` false only regenerates images
+    (:461-470); a trained hop does, in this order, a G update on ``BCE(dis(gen(code.detach())), 1)``
+    (:475-485), for r > 0 an R update on ``λ^r·MSE(code, first_code) + (1-λ^r)·BCE(dis(gen(code)), 1)``
+    with the already updated G (:487-497), and a D update on a fresh real batch and the hop's
+    (pre-update) generated images (:502-526).  ``train_flags=None`` means ``--always_train_all``.
+    ``reals``: one real batch per trained hop, in order.  Returns per-hop loss dicts (None if skipped).
+    """
+    B = first_code.size(0)
+    ones = torch.ones(B, 1, dtype=first_code.dtype)
+    zeros = torch.zeros(B, 1, dtype=first_code.dtype)
+    hops = 1 + r_iterations
+    if train_flags is None:
+        train_flags = [True] * hops
+    reals = list(reals)
+    out = []
+    last_images, last_code = None, None
+    for r_idx in range(hops):
+        code = first_code if last_images is None else rev(last_images.detach())
+        if not train_flags[r_idx]:
+            last_images = gen(code.detach())
+            last_code = code
+            out.append(None)
+            continue
+        rec = {}
+        # ---- G
+        _zero_fill(gen)
+        for p in dis.parameters():
+            p.requires_grad_(False)
+        generated = gen(code.detach())
+        loss_g = F.binary_cross_entropy(dis(generated), ones)
+        loss_g.backward()
+        rmsprop_update(list(gen.parameters()), gen_state, lr, alpha, eps)
+        rec["g"] = loss_g.item()
+        # ---- R
+        if last_code is not None:
+            _zero_fill(rev)
+            loss_g2 = F.binary_cross_entropy(dis(gen(code)), ones)
+            loss_r = F.mse_loss(code, first_code.detach())
+            lar = lambda_r ** r_idx
+            (lar * loss_r + (1 - lar) * loss_g2).backward()
+            rmsprop_update(list(rev.parameters()), rev_state, lr, alpha, eps)
+            rec["r"] = loss_r.item()
+        # ---- D
+        _zero_fill(dis)
+        for p in dis.parameters():
+            p.requires_grad_(True)
+        loss_d_real = F.binary_cross_entropy(dis(reals.pop(0)), ones)
+        loss_d_real.backward()
+        loss_d_fake = F.binary_cross_entropy(dis(generated.detach()), zeros)
+        loss_d_fake.backward()
+        rmsprop_update(list(dis.parameters()), dis_state, lr, alpha, eps)
+        rec["d_real"], rec["d_fake"] = loss_d_real.item(), loss_d_fake.item()
+        last_images, last_code = generated, code
+        out.append(rec)
+    return out
