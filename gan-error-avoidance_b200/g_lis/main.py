@@ -246,7 +246,7 @@ def main(argv=None):
         print(dis)
     if opt.ls:
         raise NotImplementedError("--ls (LSGAN loss) is not part of the accelerated path yet")
-    sync = dp.GradSync(world) if world > 1 else None
+    sync = dp.OverlappedGradSync(world) if world > 1 else None
     trainer = GLISTrainer(gen, dis, lr=opt.lr, lambda_r=opt.lambda_r, grad_sync=sync)
 
     if rank == 0:

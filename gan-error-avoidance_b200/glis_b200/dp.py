@@ -69,6 +69,93 @@ class GradSync(object):
         return 1.0 / self.world
 
 
+def plan_param_buckets(offsets, sizes, total, bucket_elems):
+    """Buckets of WHOLE parameters for the overlapped exchange: walk the parameters from the last
+    one (whose gradient backward produces first) towards the first, closing a bucket once it holds
+    at least ``bucket_elems`` elements.  Returns [(offset, length, [param indices])], first-ready
+    first; the buckets tile [0, total) (alignment padding rides along with its parameter)."""
+    buckets, members, end = [], [], total
+    for i in range(len(offsets) - 1, -1, -1):
+        members.append(i)
+        if end - offsets[i] >= bucket_elems or i == 0:
+            start = offsets[i] if i > 0 else 0
+            buckets.append((start, end - start, members))
+            members, end = [], start
+    return buckets
+
+
+class OverlappedGradSync(object):
+    """Bucketed gradient all-reduce launched from a side stream WHILE backward is still running.
+
+    One instance serves several flat buffers (``register(tag, flat)``).  Every parameter gets a
+    post-accumulate-grad hook; when the last parameter of a bucket has its gradient, the main
+    stream records an event, the side stream waits for it and issues that bucket's all-reduce, so
+    the exchange of the late layers overlaps the backward of the early ones.  ``finish(tag)``
+    flushes the buckets that never completed (a LIS module skipped by the stochastic depth keeps
+    its zero-filled gradient — identically on every rank, so the flush order is the same
+    everywhere), makes the main stream wait for the side stream and returns 1/world for the
+    fused RMSprop.  Everything is stream-ordered, so the whole thing can sit inside a CUDA graph.
+    """
+
+    def __init__(self, world, bucket_mb=8.0, group=None):
+        self.world, self.group = world, group
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.sets = {}
+        self.bytes_reduced = 0
+
+    def register(self, tag, flat):
+        plan = plan_param_buckets(flat.offsets, [p.numel() for p in flat.params], flat.numel, self.bucket_elems)
+        buckets = [(o, n) for o, n, _ in plan]
+        owner = [None] * len(flat.params)
+        for b, (_, _, members) in enumerate(plan):
+            for i in members:
+                owner[i] = b
+        st = {"flat": flat, "buckets": buckets, "owner": owner, "need": [len(m) for _, _, m in plan],
+              "left": [0] * len(buckets), "sent": [False] * len(buckets), "armed": False}
+        self.sets[tag] = st
+        for idx, p in enumerate(flat.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(st, idx))
+
+    def _make_hook(self, st, idx):
+        def hook(_param):
+            if not st["armed"] or self.world <= 1:
+                return
+            b = st["owner"][idx]
+            st["left"][b] -= 1
+            if st["left"][b] == 0 and not st["sent"][b]:
+                self._send(st, b)
+        return hook
+
+    def _send(self, st, b):
+        off, n = st["buckets"][b]
+        ready = torch.cuda.Event()
+        ready.record()                      # gradients of this bucket are complete on the main stream
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(st["flat"].g[off:off + n], op=dist.ReduceOp.SUM, group=self.group)
+        st["sent"][b] = True
+        self.bytes_reduced += 4 * n
+
+    def begin(self, tag):
+        """Call after zero_grad and before the backward pass that fills ``tag``'s gradients."""
+        st = self.sets[tag]
+        st["left"] = list(st["need"])
+        st["sent"] = [False] * len(st["buckets"])
+        st["armed"] = True
+
+    def finish(self, tag):
+        st = self.sets[tag]
+        st["armed"] = False
+        if self.world <= 1:
+            return 1.0
+        for b in range(len(st["buckets"])):
+            if not st["sent"][b]:
+                self._send(st, b)
+        torch.cuda.current_stream().wait_stream(self.side)
+        return 1.0 / self.world
+
+
 def seed_everything(seed, rank):
     """Weights and LIS-depth draws identical on every rank; data streams distinct."""
     random.seed(seed)

@@ -90,9 +90,26 @@ class GLISTrainer(object):
         self.lr, self.lambda_r, self.alpha, self.eps = lr, lambda_r, alpha, eps
         self.gen_flat = FlatParams(gen)
         self.dis_flat = FlatParams(dis)
-        # grad_sync(flat_grad_tensor, tag) -> gscale ; installed by the data-parallel wrapper
+        # data parallelism: either a callable (flat_grad_tensor, tag) -> gscale run after backward
+        # (dp.GradSync) or an object with register/begin/finish that overlaps the exchange with
+        # backward from a side stream (dp.OverlappedGradSync)
         self.grad_sync = grad_sync
+        self._overlapped = hasattr(grad_sync, "register")
+        if self._overlapped:
+            grad_sync.register("gen", self.gen_flat)
+            grad_sync.register("dis", self.dis_flat)
         self.launches = 0
+
+    def _sync_begin(self, tag):
+        if self._overlapped:
+            self.grad_sync.begin(tag)
+
+    def _sync_done(self, tag, flat):
+        if self.grad_sync is None:
+            return 1.0
+        if self._overlapped:
+            return self.grad_sync.finish(tag)
+        return self.grad_sync(flat.g, tag)
 
     def _set_dis_requires_grad(self, flag):
         for p in self.dis_flat.params:
@@ -115,9 +132,10 @@ class GLISTrainer(object):
         p_both = dis(both)
         loss_d_real = F.binary_cross_entropy(p_both[:B], ones)
         loss_d_fake = F.binary_cross_entropy(p_both[B:], zeros)
+        self._sync_begin("dis")
         (loss_d_real + loss_d_fake).backward()
         self.dis_flat.rebind_grads()
-        gs = self.grad_sync(self.dis_flat.g, "dis") if self.grad_sync else 1.0
+        gs = self._sync_done("dis", self.dis_flat)
         self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
 
         # ---- G step
@@ -132,9 +150,10 @@ class GLISTrainer(object):
                 l = F.mse_loss(u, z_g) * (self.lambda_r ** (i + 1))
                 loss_r.append(l.detach())
                 total = total + l
+        self._sync_begin("gen")
         total.backward()
         self.gen_flat.rebind_grads()
-        gs = self.grad_sync(self.gen_flat.g, "gen") if self.grad_sync else 1.0
+        gs = self._sync_done("gen", self.gen_flat)
         self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
         self._set_dis_requires_grad(True)
 

@@ -24,6 +24,21 @@ def test_plan_buckets_cover_buffer_back_to_front():
             assert o2 + n2 == o1                                                  # contiguous, no overlap
 
 
+def test_param_buckets_hold_whole_parameters():
+    """A bucket of the overlapped exchange may only be sent once EVERY parameter overlapping it has its
+    gradient, so buckets are unions of whole parameters (a large weight is never cut)."""
+    from glis_b200.dp import plan_param_buckets
+    offsets, sizes = [0, 8, 12, 1036, 1040, 1104], [6, 4, 1024, 4, 64, 300]   # 4-aligned layout, total 1404
+    plan = plan_param_buckets(offsets, sizes, 1404, 100)
+    assert plan[0] == (1104, 300, [5])                       # last parameter first
+    assert plan[1] == (12, 1092, [4, 3, 2])                  # the 1024-element weight stays whole
+    assert plan[2] == (0, 12, [1, 0])
+    assert sum(n for _, n, _ in plan) == 1404
+    assert sorted(i for _, _, m in plan for i in m) == list(range(6))
+    one = plan_param_buckets(offsets, sizes, 1404, 10 ** 9)
+    assert one == [(0, 1404, [5, 4, 3, 2, 1, 0])]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
