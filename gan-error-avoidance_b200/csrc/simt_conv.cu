@@ -165,7 +165,7 @@ gather_gemm_fwd(const glis_geom_t g, const float* __restrict__ in, const float* 
       if (ep.preact) ep.preact[base + co] = y;
       float o = y;
       if (ep.act == GLIS_ACT_TPRELU) {
-        const float b = __ldg(ep.act_b + co), a = __ldg(ep.act_a + co);
+        const float b = __ldg(ep.act_b + co), a = fminf(fmaxf(__ldg(ep.act_a + co), 0.f), 1.f);
         const float tt = y - b;
         o = (tt > 0.f ? tt : a * tt) + b;
       } else if (ep.act == GLIS_ACT_SIGMOID) {
@@ -272,7 +272,7 @@ small_cout_fwd(const glis_geom_t g, const float* __restrict__ in, const float* _
         if (ep.preact) ep.preact[base + co] = y;
         float o = y;
         if (ep.act == GLIS_ACT_TPRELU) {
-          const float b = __ldg(ep.act_b + co), a = __ldg(ep.act_a + co);
+          const float b = __ldg(ep.act_b + co), a = fminf(fmaxf(__ldg(ep.act_a + co), 0.f), 1.f);
           const float tt = y - b;
           o = (tt > 0.f ? tt : a * tt) + b;
         } else if (ep.act == GLIS_ACT_SIGMOID) {
@@ -363,7 +363,7 @@ small_cout_tconv4x4s2(const glis_geom_t g, const float* __restrict__ in, const f
       if (ep.preact) ep.preact[idx] = y;
       float o = y;
       if (ep.act == GLIS_ACT_TPRELU) {
-        const float b = __ldg(ep.act_b + sub), a = __ldg(ep.act_a + sub);
+        const float b = __ldg(ep.act_b + sub), a = fminf(fmaxf(__ldg(ep.act_a + sub), 0.f), 1.f);
         const float tt = y - b;
         o = (tt > 0.f ? tt : a * tt) + b;
       } else if (ep.act == GLIS_ACT_SIGMOID) {
@@ -392,7 +392,7 @@ small_cin_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __
   for (int i = threadIdx.x; i < K * g.Co; i += SI_NT) Ws[(i / g.Co) * SI_MAXCO + (i % g.Co)] = __ldg(wp + i);
   for (int c = threadIdx.x; c < g.Co; c += SI_NT) {
     s_bias[c] = ep.bias ? __ldg(ep.bias + c) : 0.f;
-    s_a[c] = ep.act == GLIS_ACT_TPRELU ? __ldg(ep.act_a + c) : 0.f;
+    s_a[c] = ep.act == GLIS_ACT_TPRELU ? fminf(fmaxf(__ldg(ep.act_a + c), 0.f), 1.f) : 0.f;
     s_b[c] = ep.act == GLIS_ACT_TPRELU ? __ldg(ep.act_b + c) : 0.f;
   }
   __syncthreads();

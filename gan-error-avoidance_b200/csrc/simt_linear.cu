@@ -80,7 +80,7 @@ linear_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Wp, int
       if (ep.preact) ep.preact[idx] = y;
       float o = y;
       if (ep.act == GLIS_ACT_TPRELU) {
-        const float b = __ldg(ep.act_b + n), a = __ldg(ep.act_a + n);
+        const float b = __ldg(ep.act_b + n), a = fminf(fmaxf(__ldg(ep.act_a + n), 0.f), 1.f);
         const float t = y - b;
         o = (t > 0.f ? t : a * t) + b;
       } else if (ep.act == GLIS_ACT_SIGMOID) {

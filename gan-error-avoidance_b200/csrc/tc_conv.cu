@@ -302,7 +302,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias) bias = __ldg(P.bias + co);
-        if (P.act == GLIS_ACT_TPRELU) { ta = __ldg(P.act_a + co); tb = __ldg(P.act_b + co); }
+        if (P.act == GLIS_ACT_TPRELU) { ta = fminf(fmaxf(__ldg(P.act_a + co), 0.f), 1.f); tb = __ldg(P.act_b + co); }
       }
       const int oy0 = g.relation == GLIS_TCONV ? tl.qy0 * sh + tl.ph.ry : tl.qy0;
       const int ox0 = g.relation == GLIS_TCONV ? tl.ph.rx : 0;

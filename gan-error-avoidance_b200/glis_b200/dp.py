@@ -115,7 +115,12 @@ class OverlappedGradSync(object):
               "left": [0] * len(buckets), "sent": [False] * len(buckets), "armed": False}
         self.sets[tag] = st
         for idx, p in enumerate(flat.params):
-            p.register_post_accumulate_grad_hook(self._make_hook(st, idx))
+            hook = self._make_hook(st, idx)
+            p.register_post_accumulate_grad_hook(hook)          # gradients accumulated by autograd
+            hooks = getattr(p, "_glis_grad_hooks", None)        # gradients the kernels add in place (ops._touch_hooks)
+            if hooks is None:
+                hooks = p._glis_grad_hooks = []
+            hooks.append(hook)
 
     def _make_hook(self, st, idx):
         def hook(_param):

@@ -288,7 +288,35 @@ def _layer_shapes(xc, weight, spec):
     return shape
 
 
-def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape):
+def _dense_grad(p):
+    """``p.grad`` if gradients may be added into it in place (flat-buffer parameters), else None."""
+    g = getattr(p, "grad", None)
+    if g is None or not getattr(p, "_glis_direct_grad", False) or not g.is_contiguous() or g.dtype != torch.float32:
+        return None
+    return g
+
+
+def _take_scratch(weight):
+    """Zero-filled buffer for the raw filter gradient: a slice of the owner's per-step scratch
+    (zeroed once per backward with the gradients) or a fresh zeros tensor."""
+    sc = getattr(weight, "_glis_scratch", None)
+    if sc is not None:
+        return sc
+    return torch.zeros_like(weight, memory_format=torch.contiguous_format)
+
+
+def _touch_hooks(*params):
+    """Gradients written in place bypass autograd's accumulation, hence its post-accumulate hooks
+    (the overlapped gradient exchange counts on them): fire them by hand."""
+    for p in params:
+        if p is None:
+            continue
+        for hook in getattr(p, "_glis_grad_hooks", ()):
+            hook(p)
+
+
+def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape,
+                    pw_bias=None):
     """dgrad + wgrad + weight-norm projection + bias gradient of one WN layer.
     ``dyc``: fp32 gradient w.r.t. the layer's affine output (NHWC-dense)."""
     weight, scale = pw.weight, pw.scale
@@ -311,7 +339,7 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
 
     dw = dscale = dbias = None
     if need_dw or need_dscale:
-        graw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        graw = _take_scratch(weight)
         if spec.transposed:   # small = x (Cin), big = dy (Cout)
             g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin)
             small, big = xc, dyc
@@ -328,20 +356,35 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
             with L.timed(tag + " fp32"):
                 L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
                        L.stream())
-        dw = torch.empty_like(graw)
-        if scale is not None:
-            dscale = torch.empty(cout, device=dw.device, dtype=torch.float32)
+        # Parameters owned by a FlatParams buffer carry a dense `.grad`: add into it in place and
+        # hand autograd nothing to accumulate (one kernel less per parameter); otherwise return it.
+        direct_w = _dense_grad(weight)
+        direct_s = _dense_grad(scale) if scale is not None else None
+        if direct_w is not None and (scale is None or direct_s is not None):
+            dw_buf, ds_buf, acc = direct_w, direct_s, 1
+        else:
+            dw_buf = torch.empty_like(graw)
+            ds_buf = torch.empty(cout, device=dw_buf.device, dtype=torch.float32) if scale is not None else None
+            acc = 0
         pw.need_fp32(False, False)  # the norm
         wc = weight.detach().contiguous()
         sc = None if scale is None else scale.detach().contiguous()
         L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, cout, cin, t,
-               spec.norm_factor, L.ptr(dw), L.ptr(dscale), 0, L.stream())
-        if dscale is not None:
-            dscale = dscale.view_as(scale)
+               spec.norm_factor, L.ptr(dw_buf), L.ptr(ds_buf), acc, L.stream())
+        if acc:
+            _touch_hooks(weight, scale)
+        else:
+            dw = dw_buf
+            dscale = None if ds_buf is None else ds_buf.view_as(scale)
     if need_dbias:
-        dbias = torch.empty(cout, device=dyc.device, dtype=torch.float32)
-        L.call("glis_channel_sum", L.ptr(dyc), L.ptr(dbias), dyc.numel(), cout, 1, 0, L.stream())
-        dbias = dbias.view(bias_shape)
+        direct_b = _dense_grad(pw_bias) if pw_bias is not None else None
+        if direct_b is not None:
+            L.call("glis_channel_sum", L.ptr(dyc), L.ptr(direct_b), dyc.numel(), cout, 1, 1, L.stream())
+            _touch_hooks(pw_bias)
+        else:
+            dbias = torch.empty(cout, device=dyc.device, dtype=torch.float32)
+            L.call("glis_channel_sum", L.ptr(dyc), L.ptr(dbias), dyc.numel(), cout, 1, 0, L.stream())
+            dbias = dbias.view(bias_shape)
     return dx, dw, dscale, dbias
 
 
@@ -364,7 +407,7 @@ class WNContraction(torch.autograd.Function):
         b = None if bias is None else bias.detach().reshape(-1).contiguous()
         rel_f = L.TCONV if spec.transposed else L.CONV
         out, _, _ = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b)
-        ctx.spec, ctx.pw = spec, pw
+        ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
         ctx.save_for_backward(xc)
@@ -379,7 +422,7 @@ class WNContraction(torch.autograd.Function):
         ni = ctx.needs_input_grad
         dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dyc, None, ni[0], ni[1],
                                                 ctx.pw.scale is not None and ni[2],
-                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape)
+                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)
         return dx, dw, dscale, dbias, None
 
 
@@ -400,12 +443,12 @@ class WNContractionTPReLU(torch.autograd.Function):
         shape = _layer_shapes(xc, weight, spec)
         pw = packed_weights(weight, scale, spec)
         b = None if bias is None else bias.detach().reshape(-1).contiguous()
-        a_c = a_raw.detach().clamp(0, 1)
         rel_f = L.TCONV if spec.transposed else L.CONV
         out, preact, planes = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_TPRELU,
-                                     act_a=a_c, act_b=b_t.detach().contiguous(), want_preact=True,
+                                     act_a=a_raw.detach().contiguous(), act_b=b_t.detach().contiguous(),
+                                     want_preact=True,
                                      want_planes=True)
-        ctx.spec, ctx.pw = spec, pw
+        ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
         ctx.save_for_backward(xc, preact, a_raw, b_t)
@@ -432,14 +475,22 @@ class WNContractionTPReLU(torch.autograd.Function):
         dy = torch.empty_like(preact)
         dy_hi = torch.empty_like(preact, dtype=torch.bfloat16) if want_planes else None
         dy_lo = torch.empty_like(preact, dtype=torch.bfloat16) if (want_planes and lo) else None
-        da = torch.zeros(c, device=doc.device, dtype=torch.float32)
-        db = torch.zeros(c, device=doc.device, dtype=torch.float32)
+        ga, gb = _dense_grad(a_raw), _dense_grad(b_t)
+        direct = ga is not None and gb is not None and ctx.needs_input_grad[4]
+        if direct:      # the kernel adds atomically: straight into the (zero-filled) flat gradients
+            da, db = ga, gb
+        else:
+            da = torch.zeros(c, device=doc.device, dtype=torch.float32)
+            db = torch.zeros(c, device=doc.device, dtype=torch.float32)
         L.call("glis_tprelu_backward_planes", L.ptr(preact), L.ptr(a_raw.detach()), L.ptr(b_t.detach()), L.ptr(doc),
                L.ptr(dy), L.ptr16(dy_hi), L.ptr16(dy_lo), L.ptr(da), L.ptr(db), preact.numel(), c, 1, L.stream())
+        if direct:
+            _touch_hooks(a_raw, b_t)
+            da = db = None
         ni = ctx.needs_input_grad
         dx, dw, dscale, dbias = _layer_backward(spec, ctx.pw, xc, dy, (dy_hi, dy_lo) if want_planes else None,
                                                 ni[0], ni[1], ctx.pw.scale is not None and ni[2],
-                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape)
+                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)
         return dx, dw, dscale, dbias, da, db, None
 
 
@@ -521,6 +572,31 @@ def randn_(out, seed, offset=0):
 def uniform_(out, seed, offset=0):
     L.call("glis_uniform", L.ptr(out), out.numel(), seed, offset, L.stream())
     return out
+
+
+class BCEWithLogitsConst(torch.autograd.Function):
+    """mean BCE(sigmoid(logit), t) against a constant target t — nn.Sigmoid + nn.BCELoss of the
+    reference's D head (common/model.py:61, g_lis/main.py:311,555,564,578) as one kernel that also
+    leaves d(loss)/d(logit); backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, logit, target):
+        lg = logit.detach().reshape(-1).contiguous()
+        loss = torch.empty(1, device=lg.device, dtype=torch.float32)
+        dl = torch.empty_like(lg)
+        L.call("glis_bce_logits", L.ptr(lg), float(target), lg.numel(), 1.0, L.ptr(loss), L.ptr(dl), None, L.stream())
+        ctx.save_for_backward(dl)
+        ctx.shape = tuple(logit.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (dl,) = ctx.saved_tensors
+        return (dl * gloss).view(ctx.shape), None
+
+
+def bce_with_logits_const(logit, target):
+    return BCEWithLogitsConst.apply(logit, target)
 
 
 def bce_logits(logit, target, gscale=1.0, want_grad=True, want_prob=False):

@@ -36,16 +36,20 @@ class FlatParams(object):
             total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = total
         self.p = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.g = torch.zeros(total, device=dev, dtype=torch.float32)
+        # gradients and the raw-filter-gradient scratch share one allocation: one memset clears both
+        self.gs = torch.zeros(2 * total, device=dev, dtype=torch.float32)
+        self.g, self.scratch = self.gs[:total], self.gs[total:]
         self.v = torch.zeros(total, device=dev, dtype=torch.float32)
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.p[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.p[o:o + n].view(p.shape)
             p.grad = self.g[o:o + n].view(p.shape)
+            p._glis_direct_grad = True                      # kernels may add into .grad in place
+            p._glis_scratch = self.scratch[o:o + n].view(p.shape) if p.dim() >= 2 else None
 
     def zero_grad(self):
-        self.g.zero_()
+        self.gs.zero_()
 
     def rebind_grads(self):
         """Autograd may have replaced ``.grad`` (it does not for in-place accumulation, but a
@@ -56,6 +60,7 @@ class FlatParams(object):
                 if p.grad is not None:
                     want.add_(p.grad)
                 p.grad = want
+                p._glis_direct_grad = True
 
     def optimizer_state_dict(self, lr, alpha=0.9, eps=1e-6):
         """RMSprop state in ``torch.optim.RMSprop.state_dict()`` form — what the reference saves as
@@ -80,6 +85,29 @@ class FlatParams(object):
 
     def rmsprop_step(self, lr, alpha=0.9, eps=1e-6, gscale=1.0):
         ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale, params=self.params)
+
+
+def _split_head(dis):
+    """(layers up to the logits, True) when ``dis`` ends in Sigmoid + View(1) as build_discriminator
+    makes it (common/model.py:56-62), so that the loss can run on logits in one fused kernel."""
+    mods = list(dis.children()) if isinstance(dis, torch.nn.Sequential) else []
+    if len(mods) >= 3 and isinstance(mods[-2], torch.nn.Sigmoid) and type(mods[-1]).__name__ == "View":
+        return mods[:-2]
+    return None
+
+
+def dis_bce(dis, x, targets):
+    """[mean BCE(dis(x)[chunk_i], targets[i])] for equal batch chunks of ``x`` — nn.Sigmoid +
+    nn.BCELoss (g_lis/main.py:311,555,564,578) fused into one kernel per chunk when D has the standard head."""
+    from common.model import run_layers
+    n = x.shape[0] // len(targets)
+    body = _split_head(dis)
+    if body is None:
+        p = dis(x)
+        return [F.binary_cross_entropy(p[i * n:(i + 1) * n], torch.full_like(p[i * n:(i + 1) * n], t))
+                for i, t in enumerate(targets)]
+    logits = run_layers(body, x).reshape(x.shape[0], -1)
+    return [ops.bce_with_logits_const(logits[i * n:(i + 1) * n], t) for i, t in enumerate(targets)]
 
 
 class GLISTrainer(object):
@@ -118,8 +146,6 @@ class GLISTrainer(object):
     def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
         gen, dis = self.gen, self.dis
         B = real.shape[0]
-        ones = torch.ones(B, 1, device=real.device)
-        zeros = torch.zeros(B, 1, device=real.device)
 
         # ---- D step: real and generated batches go through D as ONE batch of 2B images.  The two
         # BCE means are taken over their own halves, so the gradients are exactly the sum of the
@@ -129,9 +155,7 @@ class GLISTrainer(object):
         with torch.no_grad():
             fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
         both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
-        p_both = dis(both)
-        loss_d_real = F.binary_cross_entropy(p_both[:B], ones)
-        loss_d_fake = F.binary_cross_entropy(p_both[B:], zeros)
+        loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
         self._sync_begin("dis")
         (loss_d_real + loss_d_fake).backward()
         self.dis_flat.rebind_grads()
@@ -142,7 +166,7 @@ class GLISTrainer(object):
         self._set_dis_requires_grad(False)
         self.gen_flat.zero_grad()
         fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
-        loss_g = F.binary_cross_entropy(dis(fake), ones)
+        (loss_g,) = dis_bce(dis, fake, [1.0])
         total = loss_g
         loss_r = []
         if self.lambda_r > 0:
@@ -280,8 +304,6 @@ class RIterTrainer(object):
     def step(self, first_code, reals, train_flags=None):
         gen, rev, dis = self.gen, self.rev, self.dis
         B = first_code.shape[0]
-        ones = torch.ones(B, 1, device=first_code.device)
-        zeros = torch.zeros(B, 1, device=first_code.device)
         hops = 1 + self.r_iterations
         if train_flags is None:
             train_flags = [True] * hops
@@ -300,7 +322,7 @@ class RIterTrainer(object):
             self.gen_flat.zero_grad()
             self._requires_grad(self.dis_flat, False)
             generated = gen(code.detach())
-            loss_g = F.binary_cross_entropy(dis(generated), ones)
+            (loss_g,) = dis_bce(dis, generated, [1.0])
             loss_g.backward()
             self.gen_flat.rebind_grads()
             self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps)
@@ -309,7 +331,7 @@ class RIterTrainer(object):
             if last_code is not None:
                 self.rev_flat.zero_grad()
                 self._requires_grad(self.gen_flat, False)
-                loss_g2 = F.binary_cross_entropy(dis(gen(code)), ones)
+                (loss_g2,) = dis_bce(dis, gen(code), [1.0])
                 loss_r = F.mse_loss(code, first_code.detach())
                 lar = self.lambda_r ** r_idx
                 (lar * loss_r + (1 - lar) * loss_g2).backward()
@@ -321,9 +343,7 @@ class RIterTrainer(object):
             self.dis_flat.zero_grad()
             self._requires_grad(self.dis_flat, True)
             both = torch.cat([reals.pop(0).contiguous(memory_format=torch.channels_last), generated.detach()], dim=0)
-            p_both = dis(both)
-            loss_d_real = F.binary_cross_entropy(p_both[:B], ones)
-            loss_d_fake = F.binary_cross_entropy(p_both[B:], zeros)
+            loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
             (loss_d_real + loss_d_fake).backward()
             self.dis_flat.rebind_grads()
             self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps)

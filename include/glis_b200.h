@@ -42,7 +42,7 @@ extern "C" {
 
 /* epilogue activation */
 #define GLIS_ACT_NONE 0
-#define GLIS_ACT_TPRELU 1  /* (t>0 ? t : a*t) + b, t = y-b, a pre-clamped to [0,1] */
+#define GLIS_ACT_TPRELU 1  /* (t>0 ? t : a*t) + b, t = y-b, a = clamp(act_a, 0, 1) */
 #define GLIS_ACT_SIGMOID 2
 
 /* arithmetic of the contraction */
@@ -64,7 +64,7 @@ typedef struct glis_geom {
 typedef struct glis_epilogue {
   const float* bias;   /* per out-channel, or NULL */
   int32_t act;         /* GLIS_ACT_* */
-  const float* act_a;  /* TPReLU slope, already clamped to [0,1] (per out-channel) */
+  const float* act_a;  /* TPReLU slope, raw parameter (clamped to [0,1] by the kernel), per out-channel */
   const float* act_b;  /* TPReLU translation (per out-channel) */
   float* preact;       /* if non-NULL, y (before act) is also stored here (NHWC) */
   void* out_hi;        /* fp32 kernels only: if non-NULL, bf16 hi plane of the activated output */
