@@ -432,7 +432,7 @@ int tc_conv_supported(const glis_geom_t* g) {
   }
   int Wq = g->Wo;
   if (g->relation == GLIS_TCONV) Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
-  if (Wq > 128) return 0;                                 // one tile row must fit the MMA N
+  if (Wq > 256) return 0;                                 // one tile row must fit the MMA N
   if (g->relation == GLIS_TCONV && g->Wo % g->stride_w != 0) return 0;  // all phases equally wide
   if (g->KH * g->KW * (g->Ci / TC_BK) < 1) return 0;
   return 1;
@@ -453,21 +453,42 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     Hq = (g->Ho + g->stride_h - 1) / g->stride_h;
     Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
   }
-  // ---- pixel tile: full rows; whole images when they are small
-  const int NMAX = 128;
+  // ---- pixel tile: full rows (tn = 1, th rows) or whole images (th = Hq, tn images), <= 256 columns.
+  // The main loop is bound by shared-memory traffic — per k-step the MMAs read 128 weight rows plus
+  // N pixel rows — and by how evenly the tiles fill the SMs, so pick the shape that minimises
+  //   waves(tiles / #SMs) x (N + 128).
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  static int nmax_cfg = 0;
+  if (!nmax_cfg) {
+    const char* e = getenv("GLIS_TC_NMAX");   // tuning knob: upper bound on columns per tile (16..256)
+    nmax_cfg = e ? atoi(e) : 256;
+    if (nmax_cfg < 16 || nmax_cfg > 256) nmax_cfg = 256;
+  }
+  const int NMAX = nmax_cfg;
+  const int co_tiles = (g->Co + TC_BM - 1) / TC_BM;
   P.tw = Wq;
-  if (Wq * Hq <= NMAX) {
-    P.th = Hq;
-    P.tn = NMAX / (Wq * Hq);
-    if (P.tn > g->N) P.tn = g->N;
-  } else {
-    P.tn = 1;
-    int best_th = 1; long best_cost = -1;
-    for (int th = 1; th <= NMAX / Wq && th <= Hq; ++th) {
-      const long cost = (long)((Hq + th - 1) / th) * (round_up(Wq * th, 16) + 24);  // +24: per-tile fixed cost
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
-    }
+  {
+    long best_cost = -1;
+    int best_th = 1, best_tn = 1;
+    auto consider = [&](int th, int tn) {
+      const int n = round_up(Wq * th * tn, 16);
+      if (n > NMAX || n > 256) return;
+      const long tiles = (long)((Hq + th - 1) / th) * ((g->N + tn - 1) / tn) * co_tiles * nphase;
+      const long waves = (tiles + num_sms - 1) / num_sms;
+      const long cost = waves * (n + 128) * 1024 + n;   // tie-break: smaller tiles
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; best_tn = tn; }
+    };
+    for (int th = 1; th <= Hq && Wq * th <= 256; ++th) consider(th, 1);
+    for (int tn = 2; tn <= g->N && Wq * Hq * tn <= 256; ++tn) consider(Hq, tn);
+    GLIS_REQUIRE(best_cost >= 0, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: no pixel tile fits");
     P.th = best_th;
+    P.tn = best_tn;
   }
   P.n_mma = round_up(P.tw * P.th * P.tn, 16);
   P.tmem_cols = 64;  // two accumulators of tmem_cols / 2 columns each
@@ -538,13 +559,6 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
   }
   const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
   tc_conv_kernel<<<grid, TC_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);

@@ -10,6 +10,12 @@ import torch
 from glis_b200 import _lib as L, ops
 
 SHAPES = [  # name, relation, N, Hi, Wi, Ci, Ho, Wo, Co
+    ("D1 conv 2B", L.CONV, 128, 40, 40, 64, 20, 20, 128),
+    ("D2 conv 2B", L.CONV, 128, 20, 20, 128, 10, 10, 256),
+    ("D3 conv 2B", L.CONV, 128, 10, 10, 256, 5, 5, 512),
+    ("dD3 tconv 2B", L.TCONV, 128, 5, 5, 512, 10, 10, 256),
+    ("dD2 tconv 2B", L.TCONV, 128, 10, 10, 256, 20, 20, 128),
+    ("dD1 tconv 2B", L.TCONV, 128, 20, 20, 128, 40, 40, 64),
     ("D1 conv 64->128 40->20", L.CONV, 64, 40, 40, 64, 20, 20, 128),
     ("D2 conv 128->256 20->10", L.CONV, 64, 20, 20, 128, 10, 10, 256),
     ("D3 conv 256->512 10->5", L.CONV, 64, 10, 10, 256, 5, 5, 512),
@@ -33,7 +39,7 @@ def main():
         out = torch.empty(n, ho, wo, co, device=dev)
         ep = L.Epilogue(None, 0, None, None, None)
         res = []
-        for dbg in ("0", "1", "2", "3", "4", "6"):
+        for dbg in ("0",):
             os.environ["GLIS_TC_DEBUG"] = dbg
             for prec in (L.PREC_BF16X3, L.PREC_BF16):
                 def run():
