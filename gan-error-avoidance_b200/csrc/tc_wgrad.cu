@@ -9,6 +9,8 @@
 // NHWC TMA box delivers), 8-pixel groups are 1024 B apart, 64-channel groups one tile apart.
 // The gather of B for the tap is again just a shifted box of the stride-parity view.
 // K is split across blockIdx.x; partial sums are added atomically into G (master layout).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -27,8 +29,10 @@ struct TcWgradParams {
   int tw, th, tn;       // pixel tile on the coarse grid (full rows)
   int rows;             // tw*th*tn  (valid smem rows per 64-channel group)
   int kp;               // rows rounded up to 16 (smem rows per group; tail rows are zero)
-  int nb;               // b-channels per CTA: 64 or 128
+  int nb;               // b-channels per tap per CTA: 64 or 128
   int n_btiles;         // ceil(Cb / nb)
+  int tpc;              // taps per CTA: their B tiles sit side by side as N-groups, so ONE MMA of
+                        // N = tpc*nb columns covers them all and reads the S tile once
   int passes, stages;
   int tiles_h, tiles_total, tiles_per_split;
   float* G;
@@ -41,7 +45,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const glis_geom_t& g = P.g;
   const int Ca = g.Co, Cb = g.Ci, T = g.KH * g.KW;
-  const int tap = blockIdx.z, kh = tap / g.KW, kw = tap - kh * g.KW;
+  const int tap0 = blockIdx.z * P.tpc;
   const int a_tile = blockIdx.y / P.n_btiles, b_tile = blockIdx.y - a_tile * P.n_btiles;
   const int a0 = a_tile * 128, b0 = b_tile * P.nb;
   const int t_beg = blockIdx.x * P.tiles_per_split;
@@ -50,7 +54,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t grp_bytes = (uint32_t)P.kp * 128;   // one 64-channel group of one plane
-  const int a_groups = 2, b_groups = P.nb / 64;
+  const int a_groups = 2, b_groups = P.tpc * (P.nb / 64);
+  const int n_cols = P.tpc * P.nb;
   const uint32_t plane_a = a_groups * grp_bytes, plane_b = b_groups * grp_bytes;
   const uint32_t stage_bytes = 2 * (plane_a + plane_b);   // [A_hi][A_lo][B_hi][B_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.stages * stage_bytes);
@@ -60,7 +65,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = P.nb <= 64 ? 64 : 128;
+  const uint32_t tmem_cols = n_cols <= 64 ? 64 : (n_cols <= 128 ? 128 : 256);
 
   // zero the tail rows (never written by TMA) of every group so they contribute nothing
   if (P.kp > P.rows) {
@@ -89,12 +94,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
   if (ksteps > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        // tap -> (parity, shift) of the fine-grid gather
-        const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
-        const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
-        const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
-        const int fy = (ey - pary) / g.stride_h, fx = (ex - parx) / g.stride_w;
         const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (uint32_t)(a_groups + b_groups) * (uint32_t)P.rows * 128u;
+        const int gpt = P.nb / 64;   // 64-channel groups per tap
         int s = 0; uint32_t parity = 0;
         for (int t = t_beg; t < t_end; ++t) {
           const int tile_h = t % P.tiles_h, tile_n = t / P.tiles_h;
@@ -109,15 +110,24 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
             uint8_t* sb = st + 2 * plane_a + pl * plane_b;
             for (int gi = 0; gi < a_groups; ++gi)
               tma_load_4d(sa + gi * grp_bytes, ms, &full_bar[s], a0 + gi * 64, 0, y0, n0);
-            for (int gi = 0; gi < b_groups; ++gi)
-              tma_load_5d(sb + gi * grp_bytes, mb, &full_bar[s], parx * Cb + b0 + gi * 64, fx, pary, y0 + fy, n0);
+            for (int tl = 0; tl < P.tpc; ++tl) {
+              // tap -> (parity, shift) of the fine-grid gather
+              const int tap = tap0 + tl, kh = tap / g.KW, kw = tap - kh * g.KW;
+              const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
+              const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
+              const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
+              const int fy = (ey - pary) / g.stride_h, fx = (ex - parx) / g.stride_w;
+              for (int gi = 0; gi < gpt; ++gi)
+                tma_load_5d(sb + (tl * gpt + gi) * grp_bytes, mb, &full_bar[s], parx * Cb + b0 + gi * 64, fx, pary,
+                            y0 + fy, n0);
+            }
           }
           if (++s == P.stages) { s = 0; parity ^= 1; }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(128, P.nb, 1, 1);  // both operands MN-major
+        const uint32_t idesc = umma_idesc_bf16(128, n_cols, 1, 1);  // both operands MN-major
         const uint64_t desc0 = umma_smem_desc(smem_u32(base), grp_bytes, 1024);  // stage 0, S_hi
         int s = 0; uint32_t parity = 0, accumulate = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -151,15 +161,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
       const int a = a0 + q * 32 + lane;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
-      for (int cb = 0; cb < P.nb; cb += 32) {
+      for (int cb = 0; cb < n_cols; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
         tmem_ld_wait();
+        const int tl = cb / P.nb, bb = b0 + (cb - tl * P.nb);   // a 32-column chunk never straddles a tap
         if (a < Ca) {
-          float* row = P.G + (size_t)a * Cb * T + tap;
+          float* row = P.G + (size_t)a * Cb * T + tap0 + tl;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int b = b0 + cb + j;
+            const int b = bb + j;
             if (b < Cb) atomicAdd(row + (size_t)b * T, __uint_as_float(v[j]));
           }
         }
@@ -207,19 +218,29 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
   P.kp = (P.rows + 15) / 16 * 16;
   P.nb = g->Ci > 64 ? 128 : 64;
   P.n_btiles = (g->Ci + P.nb - 1) / P.nb;
+  const int T_all = g->KH * g->KW;
+  static int tpc_cfg = -1;
+  if (tpc_cfg < 0) {
+    const char* e = getenv("GLIS_WG_COLS");   // tuning knob: accumulator columns per CTA (64..256)
+    tpc_cfg = e ? atoi(e) : 128;
+    if (tpc_cfg < 64 || tpc_cfg > 256) tpc_cfg = 128;
+  }
+  P.tpc = tpc_cfg / P.nb;                   // e.g. 2 taps of 64 channels, or 1 tap of 128
+  if (P.tpc < 1) P.tpc = 1;
+  while (P.tpc > 1 && T_all % P.tpc != 0) P.tpc /= 2;
   const int n_atiles = (g->Co + 127) / 128;
   P.passes = passes;
   P.tiles_h = (g->Ho + P.th - 1) / P.th;
   P.tiles_total = P.tiles_h * ((g->N + P.tn - 1) / P.tn);
   const int T = g->KH * g->KW;
-  const int ctas = n_atiles * P.n_btiles * T;
+  const int ctas = n_atiles * P.n_btiles * (T / P.tpc);
   int splits = (148 * 2 + ctas - 1) / ctas;
   const int max_splits = (P.tiles_total + 7) / 8;  // at least 8 K-tiles per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   P.tiles_per_split = (P.tiles_total + splits - 1) / splits;
   splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
-  const size_t stage_bytes = 2 * (size_t)(2 + P.nb / 64) * P.kp * 128;
+  const size_t stage_bytes = 2 * (size_t)(2 + P.tpc * (P.nb / 64)) * P.kp * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: tile does not fit shared memory");
@@ -254,7 +275,7 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_wgrad_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(splits, n_atiles * P.n_btiles, T);
+  dim3 grid(splits, n_atiles * P.n_btiles, T / P.tpc);
   tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(ms_hi, ms_lo, mb_hi, mb_lo, P);
   GLIS_CHECK_LAUNCH("glis_conv_wgrad_bf16");
   return GLIS_OK;
