@@ -119,7 +119,7 @@ int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int C
                          void* stream);
 
 /* 1 if glis_conv_forward_bf16 can tile this geometry (Ci % 64 == 0, no dilation, input
- * divisible by the stride for GLIS_CONV, output rows <= 128 pixels), else 0. */
+ * divisible by the stride for GLIS_CONV, output rows <= 256 pixels, Cout >= 32), else 0. */
 int glis_conv_tc_supported(const glis_geom_t* g);
 
 /* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
