@@ -104,7 +104,21 @@ class PackedWeights(object):
         return w, sc
 
     def need_fp32(self, io, oi):
-        io, oi = io and self.io is None, oi and self.oi is None
+        # a layer that needs one fp32 pack this step needs the other one in its backward: build both
+        # on the first request (one launch pair instead of two) once backward has been seen to want it
+        wanted = getattr(self.weight, "_glis_wanted", None)
+        if wanted is None:
+            wanted = set()
+            try:
+                self.weight._glis_wanted = wanted
+            except AttributeError:
+                pass
+        if io:
+            wanted.add("io")
+        if oi:
+            wanted.add("oi")
+        io = (io or "io" in wanted) and self.io is None
+        oi = (oi or "oi" in wanted) and self.oi is None
         if not (io or oi) and self.norm is not None:
             return
         w, sc = self._w()
@@ -122,7 +136,19 @@ class PackedWeights(object):
             self.oi = b
 
     def need_bf16(self, fwd, bwd, lo):
-        fwd, bwd = fwd and self.fwd is None, bwd and self.bwd is None
+        wanted = getattr(self.weight, "_glis_wanted", None)
+        if wanted is None:
+            wanted = set()
+            try:
+                self.weight._glis_wanted = wanted
+            except AttributeError:
+                pass
+        if fwd:
+            wanted.add("fwd")
+        if bwd:
+            wanted.add("bwd")
+        fwd = (fwd or "fwd" in wanted) and self.fwd is None
+        bwd = (bwd or "bwd" in wanted) and self.bwd is None
         if not (fwd or bwd):
             return
         w, sc = self._w()
