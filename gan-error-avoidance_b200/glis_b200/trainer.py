@@ -351,3 +351,58 @@ class RIterTrainer(object):
             last_images, last_code = generated, code
             out.append(rec)
         return out
+
+
+class HostFedStepper(object):
+    """Drives ``GraphedStep`` from HOST batches without ever idling the device.
+
+    ``submit(real, z_d, z_g)`` takes pinned host tensors and (1) enqueues their host-to-device copy
+    on a copy stream into one of two staging sets — it overlaps the previous iteration, which is
+    still running on the main stream; (2) enqueues the training iteration (device-to-device copy
+    into the graph's static inputs, graph replay) behind the copy; (3) enqueues an asynchronous
+    read-back of the iteration's losses into pinned memory; (4) waits for the PREVIOUS
+    iteration's losses — normally already there — and returns them as Python floats (``None`` on
+    the first call).  ``flush()`` returns the last iteration's losses.  Every iteration's inputs
+    cross PCIe and every iteration's losses are read on the host; only the waiting is pipelined.
+    """
+
+    def __init__(self, graphed):
+        self.g = graphed
+        dev = graphed.real.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [(torch.empty_like(graphed.real), torch.empty_like(graphed.z_d), torch.empty_like(graphed.z_g))
+                      for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]     # H2D of set i finished
+        self.consumed = [torch.cuda.Event() for _ in range(2)]   # set i has been read by its iteration
+        self.loss_ready = [torch.cuda.Event() for _ in range(2)]
+        self.h_loss = [torch.zeros(8).pin_memory() for _ in range(2)]
+        self.n_r = [0, 0]
+        self.count = 0
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.stage[0])
+
+    def _read(self, slot):
+        self.loss_ready[slot].synchronize()
+        v = self.h_loss[slot].tolist()
+        return {"d_real": v[0], "d_fake": v[1], "g": v[2], "r": v[3:3 + self.n_r[slot]]}
+
+    def submit(self, real, z_d, z_g, depth_d=None, depth_g=None):
+        slot = self.count & 1
+        main = torch.cuda.current_stream()
+        if self.count >= 2:
+            self.copy_stream.wait_event(self.consumed[slot])     # the iteration two back has read this set
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self.stage[slot], (real, z_d, z_g)):
+                dst.copy_(src, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+        main.wait_event(self.copied[slot])
+        out = self.g.step(self.stage[slot][0], self.stage[slot][1], self.stage[slot][2], depth_d, depth_g)
+        self.consumed[slot].record(main)
+        vals = [out["d_real"], out["d_fake"], out["g"]] + list(out["r"])[:5]
+        self.n_r[slot] = len(vals) - 3
+        self.h_loss[slot][:len(vals)].copy_(torch.stack([v.reshape(()) for v in vals]), non_blocking=True)
+        self.loss_ready[slot].record(main)
+        self.count += 1
+        return self._read(slot ^ 1) if self.count >= 2 else None
+
+    def flush(self):
+        return self._read((self.count - 1) & 1) if self.count else None
