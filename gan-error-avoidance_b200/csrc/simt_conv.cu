@@ -397,9 +397,11 @@ small_cin_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __
   }
   __syncthreads();
   const int64_t P = (int64_t)g.N * g.Ho * g.Wo;
+  __shared__ __align__(16) float s_tile[SI_NT / 32][32 * 20];
   const int64_t pix = (int64_t)blockIdx.x * SI_NT + threadIdx.x;
-  if (pix >= P) return;
-  const int ox = (int)(pix % g.Wo); const int64_t t = pix / g.Wo; const int oy = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+  const bool live = pix < P;   // dead lanes still help their warp store
+  const int64_t pc = live ? pix : P - 1;
+  const int ox = (int)(pc % g.Wo); const int64_t t = pc / g.Wo; const int oy = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
 
   float x[SI_MAXK];
 #pragma unroll
@@ -434,7 +436,6 @@ small_cin_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __
       }
     }
   }
-  const int64_t base = pix * g.Co;
   for (int c0 = 0; c0 < g.Co; c0 += 16) {       // 16 channels at a time keeps the accumulators in registers
     float acc[16];
 #pragma unroll
@@ -459,20 +460,46 @@ small_cin_fwd(const glis_geom_t g, const float* __restrict__ in, const float* __
       if (ep.act == GLIS_ACT_TPRELU) { const float tt = y[j] - s_b[c0 + j]; o[j] = (tt > 0.f ? tt : s_a[c0 + j] * tt) + s_b[c0 + j]; }
       else if (ep.act == GLIS_ACT_SIGMOID) o[j] = 1.f / (1.f + expf(-y[j]));
     }
+    // ---- coalesced stores: the warp's 32 pixels x 16 channels go through a padded shared tile so
+    // that 4 consecutive lanes write one pixel's 64 contiguous bytes (full 32-byte sectors)
+    float* tile = s_tile[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int64_t wbase = (pix - lane) * g.Co + c0;     // first pixel of this warp
+    const int64_t wpix_left = P - (pix - lane);          // valid pixels in this warp
+    if (ep.preact) {
+      __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (ep.preact) reinterpret_cast<float4*>(ep.preact + base + c0)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-      reinterpret_cast<float4*>(out + base + c0)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(tile + lane * 20)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = i * 32 + lane, p = idx >> 2, q = idx & 3;
+        if (p < wpix_left) reinterpret_cast<float4*>(ep.preact + wbase + (int64_t)p * g.Co)[q] = reinterpret_cast<const float4*>(tile + p * 20)[q];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(tile + lane * 20)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane, p = idx >> 2, q = idx & 3;
+      if (p < wpix_left) reinterpret_cast<float4*>(out + wbase + (int64_t)p * g.Co)[q] = reinterpret_cast<const float4*>(tile + p * 20)[q];
     }
     if (ep.out_hi) {
-      __align__(16) __nv_bfloat16 h[16], l[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sm100::split_bf16(o[j], h[j], l[j]);
-      uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + base + c0);
-      dh[0] = reinterpret_cast<uint4*>(h)[0]; dh[1] = reinterpret_cast<uint4*>(h)[1];
-      if (ep.out_lo) {
-        uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + base + c0);
-        dl[0] = reinterpret_cast<uint4*>(l)[0]; dl[1] = reinterpret_cast<uint4*>(l)[1];
+      for (int i = 0; i < 2; ++i) {
+        const int idx = i * 32 + lane, p = idx >> 1, h8 = idx & 1;   // 8 channels = 16 bytes of bf16 per lane
+        if (p < wpix_left) {
+          const float4 v0 = reinterpret_cast<const float4*>(tile + p * 20)[2 * h8], v1 = reinterpret_cast<const float4*>(tile + p * 20)[2 * h8 + 1];
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sm100::split_bf16(vv[j], hh[j], ll[j]);
+          const int64_t off = wbase + (int64_t)p * g.Co + h8 * 8;
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + off) = *reinterpret_cast<uint4*>(hh);
+          if (ep.out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + off) = *reinterpret_cast<uint4*>(ll);
+        }
       }
     }
   }
