@@ -54,6 +54,7 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
   }
   float* acc_a = staged ? sa : da;
   float* acc_b = staged ? sb : db;
+  const bool sums = da != nullptr;   // da and db come together (or not at all: frozen TPReLU parameters)
   const int64_t stride = (int64_t)gridDim.x * PW_NT;
   const int64_t rounds = (numel + stride - 1) / stride;
   for (int64_t r = 0; r < rounds; ++r) {
@@ -78,10 +79,12 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
         gb = g * (1.f - a);
       }
     }
-    channel_accumulate(acc_a, c, ga, active);
-    channel_accumulate(acc_b, c, gb, active);
+    if (sums) {
+      channel_accumulate(acc_a, c, ga, active);
+      channel_accumulate(acc_b, c, gb, active);
+    }
   }
-  if (staged) {
+  if (staged && sums) {
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += PW_NT) {
       if (sa[c] != 0.f) atomicAdd(da + c, sa[c]);
@@ -138,6 +141,7 @@ tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_
     }
   }
   __syncthreads();
+  if (da == nullptr) return;   // frozen TPReLU parameters: only dx is wanted
   for (int c = threadIdx.x; c < C; c += PW_NT) {   // one global atomic per channel per block
     if (s_a[c] != 0.f) atomicAdd(da + c, s_a[c]);
     if (s_b[c] != 0.f) atomicAdd(db + c, s_b[c]);
@@ -319,7 +323,7 @@ extern "C" int glis_tprelu_backward(const float* x, const float* a_raw, const fl
 extern "C" int glis_tprelu_backward_planes(const float* x, const float* a_raw, const float* b, const float* dout,
                                            float* dx, void* dx_hi, void* dx_lo, float* da, float* db, int64_t numel,
                                            int C, int inner, void* stream) {
-  GLIS_REQUIRE(x && a_raw && b && dout && da && db && (dx || dx_hi), GLIS_E_BADARG,
+  GLIS_REQUIRE(x && a_raw && b && dout && (dx || dx_hi) && ((da != nullptr) == (db != nullptr)), GLIS_E_BADARG,
                "glis_tprelu_backward_planes: NULL pointer");
   GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_backward_planes: bad sizes");
   if (numel == 0) return GLIS_OK;

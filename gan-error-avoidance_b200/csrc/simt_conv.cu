@@ -671,7 +671,13 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
   return GLIS_OK;
 }
 
+int simt_linear_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st);
+
 int simt_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
+  if (g->relation == GLIS_CONV && is_linear_geom(g)) {
+    const int rc = simt_linear_wgrad(g, small, big, G, st);
+    if (rc != GLIS_E_UNSUPPORTED) return rc;
+  }
   const int T = g->KH * g->KW;
   const int P = g->N * g->Ho * g->Wo;
   const int tiles = cdiv(g->Co, BM) * cdiv((int64_t)T * g->Ci, BN);

@@ -1,90 +1,153 @@
 // Batch-sized ("skinny") fp32 GEMMs of the G-LIS step: the LIS linears, G's initial linear and
-// its data gradient, the discriminator / reverser heads.  out[M, N] = X[M, K] * Wp[K, N] with
-// M = batch (64-128 rows).  The work is tiny and latency / weight-read bound: see the kernel
-// comment.  K longer than a 256-deep chunk is split across blockIdx.z (atomicAdd into a
-// zero-filled output; bias-only epilogues), which is also what gives the 12800-deep
-// contractions enough blocks.
+// its data gradient, the discriminator / reverser heads, and the weight gradients of all of them.
+//
+//   forward / data gradient :  out[M, N] = X[M, K] * Wp[K, N],   M = batch (64-128 rows)
+//   weight gradient         :  G[n][j]  += sum_m dy[m][n] * x[m][j]
+//
+// The work is tiny (a few MFLOP) and bound by latency and by reading the weights once, so the
+// kernels are organised to put MANY short blocks on the machine:
+//   * forward: a block owns a 64 x 32 output tile and ONE 64-deep K chunk; the K chunks of a tile
+//     form a thread-block cluster (up to 8 blocks along z) whose partial tiles meet through
+//     distributed shared memory — block r of the cluster finishes rows [r*64/cs, (r+1)*64/cs) and
+//     applies the epilogue (bias, TPReLU, pre-activation, bf16 planes).  Contractions deeper than
+//     one cluster (K > 512: the 12800-deep ones) add the cluster results atomically into a
+//     zero-filled output (bias-only epilogues).
+//   * weight gradient: a block owns 16 output features x 256 input features and walks the batch
+//     in 64-row chunks staged in shared memory; every output has one owner, no atomics.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace glis {
 
-constexpr int LN_TM = 64, LN_TN = 64, LN_KC = 256, LN_KQ = 4, LN_NT = LN_TN * LN_KQ;
-constexpr int LN_LD = LN_TM + 4;   // padded row of the k-major X tile (keeps float4 alignment)
+constexpr int LC_TM = 64, LC_KC = 64, LC_NT = 256;
+constexpr int LC_LD = LC_TM + 4;   // padded row of the k-major X tile (keeps float4 alignment)
+constexpr int LC_MAXCS = 8;
 
-// Block = 64 output columns x 4 K-slices (256 threads).  The 64 x 256 chunk of X is staged k-major
-// in shared memory (all loads in flight at once); a thread owns ONE output column and one quarter
-// of the chunk: per k it reads its weight W[k][n] straight from global memory (coalesced across
-// the 64 columns) and the 64 row values X[.][k] as 16 broadcast float4 from shared memory — 64 FMAs
-// per 17 loads.  The four K-slices then meet in shared memory and the block applies the epilogue.
-__global__ void __launch_bounds__(LN_NT)
-linear_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Wp, int M, int N, int K,
-                  const glis_epilogue_t ep, float* __restrict__ out, int ksplit) {
-  extern __shared__ __align__(16) float lsm[];   // Xs[LN_KC][LN_TM] then reused as partial sums [LN_KQ][LN_TM][LN_TN]
-  const int m0 = blockIdx.y * LN_TM, n0 = blockIdx.x * LN_TN;
-  const int k0 = blockIdx.z * LN_KC;
-  const int kc = min(LN_KC, K - k0);
+// CPT = output columns per thread (tile = 64 rows x 32*CPT columns): 1 for narrow outputs, where the
+// blocks are spread over K instead; 2 when N alone provides enough blocks (halves the re-reads of X).
+// `chunks` consecutive 64-deep K chunks per block, the next chunk's global loads in flight (in
+// registers) while the current one is multiplied out of shared memory.
+template <int CPT>
+__global__ void __launch_bounds__(LC_NT)
+linear_cluster_kernel(const float* __restrict__ X, const float* __restrict__ Wp, int M, int N, int K,
+                      const glis_epilogue_t ep, float* __restrict__ out, int kgroups, int chunks) {
+  constexpr int TN = 32 * CPT;
+  __shared__ __align__(16) float Xs[LC_KC * LC_LD];   // [k][row]
+  __shared__ __align__(16) float Ws[LC_KC * TN];      // [k][col]; afterwards this block's partial tile [row][col]
+  static_assert(LC_KC == LC_TM, "the partial tile reuses the weight tile");
+  float* part = Ws;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int m0 = blockIdx.y * LC_TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x;
+  const int c = tid & 31, rg = tid >> 5;   // column (and column + 32) of the tile, group of 8 rows (= warp)
 
-  // ---- stage X[m0:m0+64, k0:k0+kc] transposed (k-major): Xs[k][r]
-  // consecutive lanes take consecutive ROWS (conflict-free shared stores); each reads 16 bytes along k
-  const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (kc % 4 == 0);
-  for (int i = tid; i < LN_TM * (LN_KC / 4); i += LN_NT) {
-    const int r = i % LN_TM, g4 = i / LN_TM, k = 4 * g4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m0 + r < M && k < kc) {
-      const float* src = X + (size_t)(m0 + r) * K + k0 + k;
-      if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
-      else {
-        v.x = __ldg(src);
-        if (k + 1 < kc) v.y = __ldg(src + 1);
-        if (k + 2 < kc) v.z = __ldg(src + 2);
-        if (k + 3 < kc) v.w = __ldg(src + 3);
+  const bool wvec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wp) & 15) == 0);
+  const bool xvec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  constexpr int WV = LC_KC * (TN / 4) / LC_NT;        // float4 per thread
+  constexpr int XV = LC_TM * (LC_KC / 4) / LC_NT;
+  float4 wv[WV], xv[XV];
+
+  auto load_chunk = [&](int k0) {
+    const int kc = max(0, min(LC_KC, K - k0));
+#pragma unroll
+    for (int u = 0; u < WV; ++u) {
+      const int i = tid + u * LC_NT;
+      const int k = i / (TN / 4), nn = n0 + 4 * (i % (TN / 4));
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < kc && nn < N) {
+        const float* src = Wp + (size_t)(k0 + k) * N + nn;
+        if (wvec && nn + 3 < N) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          v.x = __ldg(src);
+          if (nn + 1 < N) v.y = __ldg(src + 1);
+          if (nn + 2 < N) v.z = __ldg(src + 2);
+          if (nn + 3 < N) v.w = __ldg(src + 3);
+        }
+      }
+      wv[u] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < XV; ++u) {   // consecutive lanes take consecutive ROWS, each reads 16 bytes along k
+      const int i = tid + u * LC_NT;
+      const int r = i % LC_TM, k = 4 * (i / LC_TM);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && k < kc) {
+        const float* src = X + (size_t)(m0 + r) * K + k0 + k;
+        if (xvec && k + 3 < kc) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          v.x = __ldg(src);
+          if (k + 1 < kc) v.y = __ldg(src + 1);
+          if (k + 2 < kc) v.z = __ldg(src + 2);
+          if (k + 3 < kc) v.w = __ldg(src + 3);
+        }
+      }
+      xv[u] = v;
+    }
+  };
+
+  float acc[CPT][8];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+
+  const int kbase = blockIdx.z * chunks * LC_KC;
+  load_chunk(kbase);
+  for (int ch = 0; ch < chunks; ++ch) {
+    if (ch > 0) __syncthreads();   // the previous chunk has been consumed
+#pragma unroll
+    for (int u = 0; u < XV; ++u) {   // transposed, conflict-free shared stores
+      const int i = tid + u * LC_NT;
+      const int r = i % LC_TM, k = 4 * (i / LC_TM);
+      Xs[(k + 0) * LC_LD + r] = xv[u].x; Xs[(k + 1) * LC_LD + r] = xv[u].y;
+      Xs[(k + 2) * LC_LD + r] = xv[u].z; Xs[(k + 3) * LC_LD + r] = xv[u].w;
+    }
+#pragma unroll
+    for (int u = 0; u < WV; ++u) reinterpret_cast<float4*>(Ws)[tid + u * LC_NT] = wv[u];
+    __syncthreads();
+    if (ch + 1 < chunks) load_chunk(kbase + (ch + 1) * LC_KC);   // in flight during the multiply
+#pragma unroll 16
+    for (int j = 0; j < LC_KC; ++j) {
+      const float4* xr = reinterpret_cast<const float4*>(Xs + j * LC_LD + rg * 8);   // warp-wide broadcast
+      const float4 x0 = xr[0], x1 = xr[1];
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        const float w = Ws[j * TN + c + 32 * q];
+        acc[q][0] = fmaf(x0.x, w, acc[q][0]); acc[q][1] = fmaf(x0.y, w, acc[q][1]);
+        acc[q][2] = fmaf(x0.z, w, acc[q][2]); acc[q][3] = fmaf(x0.w, w, acc[q][3]);
+        acc[q][4] = fmaf(x1.x, w, acc[q][4]); acc[q][5] = fmaf(x1.y, w, acc[q][5]);
+        acc[q][6] = fmaf(x1.z, w, acc[q][6]); acc[q][7] = fmaf(x1.w, w, acc[q][7]);
       }
     }
-    lsm[(k + 0) * LN_LD + r] = v.x; lsm[(k + 1) * LN_LD + r] = v.y;
-    lsm[(k + 2) * LN_LD + r] = v.z; lsm[(k + 3) * LN_LD + r] = v.w;
   }
-  __syncthreads();
+  __syncthreads();   // everyone is done with the weight tile
+#pragma unroll
+  for (int q = 0; q < CPT; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[(rg * 8 + i) * TN + c + 32 * q] = acc[q][i];
+  if (cs > 1) cluster.sync(); else __syncthreads();
 
-  const int c = tid & (LN_TN - 1), kq = tid / LN_TN;
-  const int n = n0 + c;
-  const int kper = LN_KC / LN_KQ;
-  float acc[LN_TM];
+  // ---- block `rank` finishes its share of the rows: sum the cluster's partial tiles
+  const int rows_per = LC_TM / cs;
+  const float* remote[LC_MAXCS];
 #pragma unroll
-  for (int r = 0; r < LN_TM; ++r) acc[r] = 0.f;
-  const int kb = kq * kper, ke = min(kc, kb + kper);
-  for (int k8 = kb; k8 < ke; k8 += 8) {
-    float w[8];   // eight weight loads in flight before the first FMA needs one
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = (n < N && k8 + j < ke) ? __ldg(Wp + (size_t)(k0 + k8 + j) * N + n) : 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4* xr = reinterpret_cast<const float4*>(lsm + (k8 + j) * LN_LD);
-#pragma unroll
-      for (int q = 0; q < LN_TM / 4; ++q) {
-        const float4 x = xr[q];
-        acc[4 * q + 0] = fmaf(x.x, w[j], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x.y, w[j], acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(x.z, w[j], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, w[j], acc[4 * q + 3]);
-      }
-    }
-  }
-  __syncthreads();   // everyone is done reading Xs: reuse it for the K-slice partial sums
-  float* part = lsm;  // [kq][r][c]
-#pragma unroll
-  for (int r = 0; r < LN_TM; ++r) part[(kq * LN_TM + r) * LN_TN + c] = acc[r];
-  __syncthreads();
-
-  for (int i = tid; i < LN_TM * LN_TN; i += LN_NT) {
-    const int r = i / LN_TN, cc = i - r * LN_TN;
+  for (int q = 0; q < LC_MAXCS; ++q) remote[q] = q < cs ? cluster.map_shared_rank(part, q) : part;
+  for (int i = tid; i < rows_per * TN; i += LC_NT) {
+    const int r = rank * rows_per + i / TN, cc = i % TN;
     const int m = m0 + r, nn = n0 + cc;
-    if (m >= M || nn >= N) continue;
     float y = 0.f;
 #pragma unroll
-    for (int q = 0; q < LN_KQ; ++q) y += part[(q * LN_TM + r) * LN_TN + cc];
+    for (int q = 0; q < LC_MAXCS; ++q) if (q < cs) y += remote[q][r * TN + cc];
+    if (m >= M || nn >= N) continue;
     const size_t idx = (size_t)m * N + nn;
-    if (ksplit > 1) {
-      if (ep.bias && blockIdx.z == 0) y += __ldg(ep.bias + nn);
+    if (kgroups > 1) {
+      if (ep.bias && blockIdx.z < (unsigned)cs) y += __ldg(ep.bias + nn);
       atomicAdd(out + idx, y);
       continue;
     }
@@ -106,6 +169,7 @@ linear_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Wp, int
       if (ep.out_lo) reinterpret_cast<__nv_bfloat16*>(ep.out_lo)[idx] = l;
     }
   }
+  if (cs > 1) cluster.sync();   // nobody leaves while a neighbour still reads its partial tile
 }
 
 // Does this launch reduce to a plain [M,K] x [K,N] product over the NHWC-flattened input?
@@ -122,22 +186,164 @@ int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpac
                         float* out, cudaStream_t st) {
   const int M = g->N, N = g->Co, K = g->KH * g->KW * g->Ci;
   if (M > 4096) return GLIS_E_UNSUPPORTED;
-  int ksplit = (K + LN_KC - 1) / LN_KC;
-  if (ksplit > 1 && (ep->act != GLIS_ACT_NONE || ep->preact || ep->out_hi)) return GLIS_E_UNSUPPORTED;
-  const size_t smem = sizeof(float) * (size_t)LN_KC * LN_LD;   // 68 KB; the partial sums (4*64*64 floats) fit in it too
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(linear_fwd_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  if (ksplit > 1) {
+  const int nk = (K + LC_KC - 1) / LC_KC;
+  const int gy = (M + LC_TM - 1) / LC_TM;
+  // wide tiles once N alone gives every SM a block; then spread over K until ~3 blocks per SM
+  const int cpt = ((N + 63) / 64) * gy >= 148 ? 2 : 1;
+  const int gx = (N + 32 * cpt - 1) / (32 * cpt);
+  const int want_z = (3 * 148 + gx * gy - 1) / (gx * gy);
+  int chunks = (nk + want_z - 1) / want_z;
+  if (chunks < 1) chunks = 1;
+  const int gz = (nk + chunks - 1) / chunks;
+  int cs = 1;
+  while (cs * 2 <= LC_MAXCS && cs * 2 <= gz) cs *= 2;
+  const int kgroups = (gz + cs - 1) / cs;
+  if (kgroups > 1 && (ep->act != GLIS_ACT_NONE || ep->preact || ep->out_hi)) return GLIS_E_UNSUPPORTED;
+  if (kgroups > 1) {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward(linear): memset failed: %s", cudaGetErrorString(e));
   }
-  dim3 grid((N + LN_TN - 1) / LN_TN, (M + LN_TM - 1) / LN_TM, ksplit);
-  linear_fwd_kernel<<<grid, LN_NT, smem, st>>>(in, wpack, M, N, K, *ep, out, ksplit);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, kgroups * cs);
+  cfg.blockDim = dim3(LC_NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cs;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cpt == 2
+      ? cudaLaunchKernelEx(&cfg, linear_cluster_kernel<2>, in, wpack, M, N, K, *ep, out, kgroups, chunks)
+      : cudaLaunchKernelEx(&cfg, linear_cluster_kernel<1>, in, wpack, M, N, K, *ep, out, kgroups, chunks);
+  GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward(fp32, linear): %s", cudaGetErrorString(e));
   GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, linear)");
+  return GLIS_OK;
+}
+
+// ---------------------------------------------------------------------------- weight gradient
+constexpr int LW_TJ = 256, LW_MC = 32, LW_NT = 256;
+
+// G[(a*Cb + b)*T + tap] += sum_m small[m][a] * big[m][j],  j = tap*Cb + b (the NHWC-flattened row of
+// `big`).  Block = 8*APT a x 256 j, thread = APT a x 8 consecutive j (APT = 4 when the layer is wide
+// enough to fill the machine with 32-row blocks, else 2); the batch is walked in 32-row chunks staged in
+// shared memory, the next chunk's loads in flight during the multiply.  One owner per output element:
+// no atomics.
+template <int APT>
+__global__ void __launch_bounds__(LW_NT)
+linear_wgrad_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ G,
+                    int M, int Ca, int Cb, int T) {
+  __shared__ __align__(16) float xs[LW_MC * LW_TJ];   // [m][j]
+  constexpr int LW_TN = 8 * APT;
+  __shared__ __align__(16) float ds[LW_MC * LW_TN];   // [m][a]
+  const int J = Cb * T;
+  const int j0 = blockIdx.x * LW_TJ, a0 = blockIdx.y * LW_TN;
+  const int tid = threadIdx.x;
+  const int tk = tid & 31, tn = tid >> 5;
+  const bool xvec = (J % 4 == 0) && ((reinterpret_cast<uintptr_t>(big) & 15) == 0);
+  const bool dvec = (Ca % 4 == 0) && ((reinterpret_cast<uintptr_t>(small) & 15) == 0);
+  constexpr int XV = LW_MC * (LW_TJ / 4) / LW_NT, DV = (LW_MC * (LW_TN / 4) + LW_NT - 1) / LW_NT;
+  float4 xv[XV], dv[DV];
+
+  auto load_chunk = [&](int mb) {
+#pragma unroll
+    for (int u = 0; u < XV; ++u) {
+      const int i = tid + u * LW_NT;
+      const int r = i / (LW_TJ / 4), j = j0 + 4 * (i % (LW_TJ / 4));
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mb + r < M && j < J) {
+        const float* src = big + (size_t)(mb + r) * J + j;
+        if (xvec && j + 3 < J) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          v.x = __ldg(src);
+          if (j + 1 < J) v.y = __ldg(src + 1);
+          if (j + 2 < J) v.z = __ldg(src + 2);
+          if (j + 3 < J) v.w = __ldg(src + 3);
+        }
+      }
+      xv[u] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < DV; ++u) {
+      const int i = tid + u * LW_NT;
+      const int r = i / (LW_TN / 4), a = a0 + 4 * (i % (LW_TN / 4));
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < LW_MC && mb + r < M && a < Ca) {
+        const float* src = small + (size_t)(mb + r) * Ca + a;
+        if (dvec && a + 3 < Ca) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          v.x = __ldg(src);
+          if (a + 1 < Ca) v.y = __ldg(src + 1);
+          if (a + 2 < Ca) v.z = __ldg(src + 2);
+          if (a + 3 < Ca) v.w = __ldg(src + 3);
+        }
+      }
+      dv[u] = v;
+    }
+  };
+
+  float acc[APT][8];
+#pragma unroll
+  for (int i = 0; i < APT; ++i)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
+
+  load_chunk(0);
+  for (int mb = 0; mb < M; mb += LW_MC) {
+    if (mb > 0) __syncthreads();
+#pragma unroll
+    for (int u = 0; u < XV; ++u) reinterpret_cast<float4*>(xs)[tid + u * LW_NT] = xv[u];
+#pragma unroll
+    for (int u = 0; u < DV; ++u)
+      if (tid + u * LW_NT < LW_MC * (LW_TN / 4)) reinterpret_cast<float4*>(ds)[tid + u * LW_NT] = dv[u];
+    __syncthreads();
+    if (mb + LW_MC < M) load_chunk(mb + LW_MC);
+#pragma unroll 4
+    for (int m = 0; m < LW_MC; ++m) {
+      const float* dr = ds + m * LW_TN + tn * APT;   // warp-wide broadcast
+      const float4* xr = reinterpret_cast<const float4*>(xs + m * LW_TJ + tk * 8);
+      const float4 x0 = xr[0], x1 = xr[1];
+      float dd[APT];
+      if (APT == 8) {
+        const float4 d0 = reinterpret_cast<const float4*>(dr)[0], d1 = reinterpret_cast<const float4*>(dr)[1];
+        dd[0] = d0.x; dd[1] = d0.y; dd[2 % APT] = d0.z; dd[3 % APT] = d0.w;
+        dd[4 % APT] = d1.x; dd[5 % APT] = d1.y; dd[6 % APT] = d1.z; dd[7 % APT] = d1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < APT; ++i) dd[i] = dr[i];
+      }
+      const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < APT; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(dd[i], xx[q], acc[i][q]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < APT; ++i) {
+    const int a = a0 + APT * tn + i;
+    if (a >= Ca) continue;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + 8 * tk + q;
+      if (j >= J) continue;
+      const int tap = j / Cb, b = j - tap * Cb;
+      float* dst = G + ((size_t)a * Cb + b) * T + tap;   // one owner per element
+      *dst += acc[i][q];
+    }
+  }
+}
+
+// Weight gradient of a linear-shaped layer (is_linear_geom, GLIS_CONV): adds into G.
+int simt_linear_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
+  const int M = g->N, Ca = g->Co, Cb = g->Ci, T = g->KH * g->KW;
+  if (M > 4096) return GLIS_E_UNSUPPORTED;
+  const int gx = (Cb * T + LW_TJ - 1) / LW_TJ;
+  if (gx * ((Ca + 31) / 32) >= 296)
+    linear_wgrad_kernel<4><<<dim3(gx, (Ca + 31) / 32), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T);
+  else
+    linear_wgrad_kernel<2><<<dim3(gx, (Ca + 15) / 16), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T);
+  GLIS_CHECK_LAUNCH("glis_conv_wgrad(fp32, linear)");
   return GLIS_OK;
 }
 

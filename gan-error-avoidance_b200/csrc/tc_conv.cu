@@ -31,6 +31,7 @@ constexpr int TC_BM = 128;       // channels per CTA (UMMA M)
 constexpr int TC_BK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_DEFAULT_CLUSTER = 1;
 
 struct TcConvParams {
   glis_geom_t g;
@@ -44,6 +45,9 @@ struct TcConvParams {
   int tiles_x;       // pixel tiles per (phase, channel tile) = tiles_h * ceil(N / tn)
   int tiles_co;      // ceil(Co / 128)
   int total_tiles;   // tiles_x * tiles_co * phases
+  int cluster;       // CTAs per cluster (1, 2, 4): the pixel tiles of a cluster share ONE weight tile, each
+                     // CTA fetches 128/cluster of its rows and multicasts them (tiles_x is padded to a multiple)
+  int n_groups;      // total_tiles / cluster
   const float* bias; int act; const float* act_a; const float* act_b;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int ep_mode;       // compile-time specialised epilogue (0 = generic)
@@ -119,7 +123,8 @@ __device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int n
 struct TcTile {
   TcPhase ph;
   int qy0, n0, co0, ntaps, ksteps;
-  bool empty;
+  bool empty;   // nothing to contract (uniform over the tiles of a cluster)
+  bool ghost;   // padding tile: takes part in loads and MMAs (zero pixels), stores nothing
 };
 
 __device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int id) {
@@ -134,7 +139,8 @@ __device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int id) {
   t.co0 = y * TC_BM;
   t.ntaps = t.ph.nth * t.ph.ntw;
   t.ksteps = t.ntaps * P.kblocks;
-  t.empty = (t.qy0 >= t.ph.Hq) || t.ph.Wq <= 0 || t.ksteps == 0;
+  t.empty = t.ph.Hq <= 0 || t.ph.Wq <= 0 || t.ksteps == 0;
+  t.ghost = t.qy0 >= t.ph.Hq || t.n0 >= P.g.N;
   return t;
 }
 
@@ -164,16 +170,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
     if (P.passes == 3) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
-    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)P.cluster); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
   tc_fence_before_sync();
   __syncthreads();
+  if (P.cluster > 1) cluster_sync_all();   // every CTA's barriers exist before a neighbour signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)P.tmem_cols / 2;
+  const int cs = P.cluster;
+  const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1087] = global_timer_ns();
 
   if (warp == 0) {
@@ -183,12 +194,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + ((P.debug & 4) ? 0u : box_rows * 128u));
       int s = 0; uint32_t parity = 0;
       int tr_n = 0;
-      for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+      const uint32_t w_rows = (uint32_t)(TC_BM / cs), w_slice = w_rows * 128u;   // this CTA's share of the weight tile
+      for (int grp = cluster_id; grp < P.n_groups; grp += n_clusters) {
+        const int id = grp * cs + crank;
         const TcTile tl = tc_tile(P, id);
         if (tl.empty) continue;
-        // Every CTA walks the taps from a different starting point: otherwise all 148 SMs pull the
+        // Every cluster walks the taps from a different starting point: otherwise all 148 SMs pull the
         // same weight tile from the same L2 slices in lock step (accumulation order is free).
-        const int rot = (int)((blockIdx.x * 5u + (uint32_t)id * 3u) % (uint32_t)tl.ntaps);
+        const int rot = (int)(((uint32_t)cluster_id * 5u + (uint32_t)grp * 3u) % (uint32_t)tl.ntaps);
         for (int t0 = 0; t0 < tl.ntaps; ++t0) {
           const int t = (t0 + rot) % tl.ntaps;
           const int jh = t / tl.ph.ntw, jw = t - jh * tl.ph.ntw;
@@ -213,14 +226,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             if (P.trace && blockIdx.x == 0 && tr_n < 512) P.trace[tr_n++] = global_timer_ns();
             uint8_t* st = base + (size_t)s * stage_bytes;
             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0, tap);
+            if (cs == 1) tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0, tap);
+            else tma_load_3d_mc(st + crank * w_slice, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0 + crank * (int)w_rows, tap, cmask);
             if (P.debug & 4) { /* expect_tx below was reduced accordingly */ }
             else if (g.relation == GLIS_CONV)
               tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
             else
               tma_load_4d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], kb * TC_BK, c1, c3, tl.n0);
             if (P.passes == 3) {
-              tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0, tap);
+              if (cs == 1) tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0, tap);
+              else tma_load_3d_mc(st + a_bytes + crank * w_slice, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0 + crank * (int)w_rows, tap, cmask);
               if (P.debug & 4) {}
               else if (g.relation == GLIS_CONV)
                 tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
@@ -240,7 +255,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       int s = 0; uint32_t parity = 0;
       uint32_t acc = 0, acc_phase = 0;  // bit a of acc_phase = parity of tmem_empty_bar[a] to wait for
       int tr_n = 512;
-      for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+      for (int grp = cluster_id; grp < P.n_groups; grp += n_clusters) {
+        const int id = grp * cs + crank;
         const TcTile tl = tc_tile(P, id);
         if (tl.empty) continue;
         mbar_wait(&tmem_empty_bar[acc], ((acc_phase >> acc) & 1u) ^ 1u);  // epilogue drained this accumulator
@@ -273,7 +289,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
               }
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          // frees the stage once these MMAs have read it — in EVERY CTA of the cluster, whose producers
+          // multicast weight rows into this CTA's stage as well
+          if (cs == 1) umma_commit(&empty_bar[s]); else umma_commit_mc(&empty_bar[s], cmask);
           if (++s == P.stages) { s = 0; parity ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
@@ -294,11 +312,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     const long long step_n = (long long)g.Ho * g.Wo * g.Co - (long long)P.th * row_pitch;
     uint32_t acc = 0, full_phase = 0;
     int tr_e = 1024;
-    for (int id = blockIdx.x; id < P.total_tiles; id += gridDim.x) {
+    for (int grp = cluster_id; grp < P.n_groups; grp += n_clusters) {
+      const int id = grp * cs + crank;
       const TcTile tl = tc_tile(P, id);
       if (tl.empty) continue;
       const int co = tl.co0 + q * 32 + lane;
-      const bool ch_ok = co < g.Co && !(P.debug & 1);
+      const bool ch_ok = co < g.Co && !(P.debug & 1) && !tl.ghost;
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias) bias = __ldg(P.bias + co);
@@ -362,6 +381,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (P.cluster > 1) cluster_sync_all();   // nobody leaves while a neighbour may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
@@ -472,6 +492,12 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   }
   const int NMAX = nmax_cfg;
   const int co_tiles = (g->Co + TC_BM - 1) / TC_BM;
+  int cs = 1;
+  {
+    const char* e = getenv("GLIS_TC_CLUSTER");   // CTAs sharing one multicast weight tile: 1, 2 or 4
+    cs = e ? atoi(e) : TC_DEFAULT_CLUSTER;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+  }
   P.tw = Wq;
   {
     long best_cost = -1;
@@ -479,9 +505,11 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     auto consider = [&](int th, int tn) {
       const int n = round_up(Wq * th * tn, 16);
       if (n > NMAX || n > 256) return;
-      const long tiles = (long)((Hq + th - 1) / th) * ((g->N + tn - 1) / tn) * co_tiles * nphase;
-      const long waves = (tiles + num_sms - 1) / num_sms;
-      const long cost = waves * (n + 128) * 1024 + n;   // tie-break: smaller tiles
+      const long tiles_x = ((long)((Hq + th - 1) / th) * ((g->N + tn - 1) / tn) + cs - 1) / cs * cs;
+      const long tiles = tiles_x * co_tiles * nphase;
+      const long slots = num_sms / cs * cs;
+      const long waves = (tiles + slots - 1) / slots;
+      const long cost = waves * (n + 128 / cs) * 1024 + n;   // tie-break: smaller tiles
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; best_tn = tn; }
     };
     for (int th = 1; th <= Hq && Wq * th <= 256; ++th) consider(th, 1);
@@ -497,9 +525,11 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.passes = passes;
   P.tiles_h = (Hq + P.th - 1) / P.th;
   const int tiles_n = (g->N + P.tn - 1) / P.tn;
-  P.tiles_x = P.tiles_h * tiles_n;
+  P.tiles_x = (P.tiles_h * tiles_n + cs - 1) / cs * cs;   // padded: the tiles of a cluster share (phase, channel tile)
   P.tiles_co = (g->Co + TC_BM - 1) / TC_BM;
   P.total_tiles = P.tiles_x * P.tiles_co * nphase;
+  P.cluster = cs;
+  P.n_groups = P.total_tiles / cs;
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -526,7 +556,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   {
     const uint64_t dims[3] = {(uint64_t)g->Ci, (uint64_t)g->Co, (uint64_t)T};
     const uint64_t strides[2] = {(uint64_t)g->Ci * 2, (uint64_t)g->Ci * g->Co * 2};
-    const uint32_t box[3] = {TC_BK, TC_BM, 1};
+    const uint32_t box[3] = {TC_BK, (uint32_t)(TC_BM / cs), 1};   // one CTA's share of the (multicast) weight tile
     int rc = make_bf16_map(&mw_hi, w_hi, 3, dims, strides, box);
     if (rc) return rc;
     rc = make_bf16_map(&mw_lo, passes == 3 ? w_lo : w_hi, 3, dims, strides, box);
@@ -560,8 +590,28 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
-  tc_conv_kernel<<<grid, TC_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent: as many clusters as the device can hold at once (one CTA per SM), at most one per group
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (!max_clusters[cs]) {
+    int nc = 0;
+    cfg.gridDim = dim3(num_sms / cs * cs);
+    if (cs == 1 || cudaOccupancyMaxActiveClusters(&nc, tc_conv_kernel, &cfg) != cudaSuccess || nc <= 0) nc = num_sms / cs;
+    (void)cudaGetLastError();
+    max_clusters[cs] = nc;
+  }
+  const int n_clusters = P.n_groups < max_clusters[cs] ? P.n_groups : max_clusters[cs];
+  cfg.gridDim = dim3(n_clusters * cs);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_kernel, mw_hi, mw_lo, mx_hi, mx_lo, P);
+  GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16: launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16");
   return GLIS_OK;
 }

@@ -23,6 +23,7 @@ int make_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dim
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 4;
+constexpr int WG_MAX_TPC = 4;      // taps per CTA (N-groups of one accumulator)
 
 struct TcWgradParams {
   glis_geom_t g;
@@ -36,6 +37,7 @@ struct TcWgradParams {
   int passes, stages;
   int tiles_h, tiles_total, tiles_per_split;
   float* G;
+  int debug;         // GLIS_WG_DEBUG bits (profiling experiments only): 1 = no stores, 2 = no MMA, 4 = no B loads, 8 = no S loads
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -94,32 +96,46 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
   if (ksteps > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (uint32_t)(a_groups + b_groups) * (uint32_t)P.rows * 128u;
+        const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) *
+                                  (uint32_t)(((P.debug & 8) ? 0 : a_groups) + ((P.debug & 4) ? 0 : b_groups)) *
+                                  (uint32_t)P.rows * 128u;
         const int gpt = P.nb / 64;   // 64-channel groups per tap
+        // tap -> (parity, shift) of the fine-grid gather, decoded ONCE: the integer divisions must not
+        // sit in the per-stage issue loop of this single thread
+        int bc0[WG_MAX_TPC], bfx[WG_MAX_TPC], bpy[WG_MAX_TPC], bfy[WG_MAX_TPC];
+#pragma unroll
+        for (int tl = 0; tl < WG_MAX_TPC; ++tl) {
+          const int tap = tap0 + (tl < P.tpc ? tl : 0), kh = tap / g.KW, kw = tap - kh * g.KW;
+          const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
+          const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
+          const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
+          bc0[tl] = parx * Cb + b0; bpy[tl] = pary;
+          bfy[tl] = (ey - pary) / g.stride_h; bfx[tl] = (ex - parx) / g.stride_w;
+        }
+        const int ntl = (P.debug & 4) ? 0 : P.tpc, nag = (P.debug & 8) ? 0 : a_groups;
+        const int npl = P.passes == 3 ? 2 : 1;
         int s = 0; uint32_t parity = 0;
+        int tile_h = t_beg % P.tiles_h, tile_n = t_beg / P.tiles_h;
         for (int t = t_beg; t < t_end; ++t) {
-          const int tile_h = t % P.tiles_h, tile_n = t / P.tiles_h;
           const int y0 = tile_h * P.th, n0 = tile_n * P.tn;
+          if (++tile_h == P.tiles_h) { tile_h = 0; ++tile_n; }
           mbar_wait(&empty_bar[s], parity ^ 1);
           uint8_t* st = base + (size_t)s * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          for (int pl = 0; pl < (P.passes == 3 ? 2 : 1); ++pl) {
+          for (int pl = 0; pl < npl; ++pl) {
             const CUtensorMap* ms = pl ? &map_s_lo : &map_s_hi;
             const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
             uint8_t* sa = st + pl * plane_a;
             uint8_t* sb = st + 2 * plane_a + pl * plane_b;
-            for (int gi = 0; gi < a_groups; ++gi)
+            for (int gi = 0; gi < nag; ++gi)
               tma_load_4d(sa + gi * grp_bytes, ms, &full_bar[s], a0 + gi * 64, 0, y0, n0);
-            for (int tl = 0; tl < P.tpc; ++tl) {
-              // tap -> (parity, shift) of the fine-grid gather
-              const int tap = tap0 + tl, kh = tap / g.KW, kw = tap - kh * g.KW;
-              const int ey = kh * g.dil_h - g.pad_h, ex = kw * g.dil_w - g.pad_w;
-              const int pary = ((ey % g.stride_h) + g.stride_h) % g.stride_h;
-              const int parx = ((ex % g.stride_w) + g.stride_w) % g.stride_w;
-              const int fy = (ey - pary) / g.stride_h, fx = (ex - parx) / g.stride_w;
-              for (int gi = 0; gi < gpt; ++gi)
-                tma_load_5d(sb + (tl * gpt + gi) * grp_bytes, mb, &full_bar[s], parx * Cb + b0 + gi * 64, fx, pary,
-                            y0 + fy, n0);
+#pragma unroll
+            for (int tl = 0; tl < WG_MAX_TPC; ++tl) {
+              if (tl < ntl) {
+                for (int gi = 0; gi < gpt; ++gi)
+                  tma_load_5d(sb + (tl * gpt + gi) * grp_bytes, mb, &full_bar[s], bc0[tl] + gi * 64, bfx[tl], bpy[tl],
+                              y0 + bfy[tl], n0);
+              }
             }
           }
           if (++s == P.stages) { s = 0; parity ^= 1; }
@@ -138,7 +154,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
           const uint64_t dbh0 = dah0 + ((2 * plane_a) >> 4);
           const uint64_t dbl0 = dbh0 + (plane_b >> 4);
           const int nk16 = P.kp / 16;
-          if (P.passes == 3) {
+          if (P.debug & 2) {
+          } else if (P.passes == 3) {
             for (int k16 = 0; k16 < nk16; ++k16) {  // 16 pixel rows of 128 B = 2048 B = 128 descriptor units
               umma_bf16(tmem_base, dah0 + 128 * k16, dbl0 + 128 * k16, idesc, accumulate);
               umma_bf16(tmem_base, dal0 + 128 * k16, dbh0 + 128 * k16, idesc, 1);
@@ -161,17 +178,53 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
       const int a = a0 + q * 32 + lane;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
-      for (int cb = 0; cb < n_cols; cb += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-        tmem_ld_wait();
-        const int tl = cb / P.nb, bb = b0 + (cb - tl * P.nb);   // a 32-column chunk never straddles a tap
-        if (a < Ca) {
-          float* row = P.G + (size_t)a * Cb * T + tap0 + tl;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool st_ok = a < Ca && !(P.debug & 1);
+      float* row = P.G + (size_t)a * Cb * T + tap0;
+      if (P.tpc == 4) {
+        // columns = [tap][b]: gather the 4 taps of 16 b-channels, then ONE 16-byte reduction per (a, b)
+        // (taps are the contiguous axis of the master layout; tap0 is a multiple of 4)
+        for (int bb = 0; bb < P.nb; bb += 16) {
+          uint32_t v[4][16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int b = bb + j;
-            if (b < Cb) atomicAdd(row + (size_t)b * T, __uint_as_float(v[j]));
+          for (int tl = 0; tl < 4; ++tl) tmem_ld_32x16(tbase + (uint32_t)(tl * P.nb + bb), v[tl]);
+          tmem_ld_wait();
+          if (st_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int b = b0 + bb + j;
+              if (b < Cb)
+                red_add_v4(row + (size_t)b * T, __uint_as_float(v[0][j]), __uint_as_float(v[1][j]),
+                           __uint_as_float(v[2][j]), __uint_as_float(v[3][j]));
+            }
+          }
+        }
+      } else if (P.tpc == 2) {
+        for (int bb = 0; bb < P.nb; bb += 32) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(tbase + (uint32_t)bb, v0);
+          tmem_ld_32x32(tbase + (uint32_t)(P.nb + bb), v1);
+          tmem_ld_wait();
+          if (st_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int b = b0 + bb + j;
+              if (b < Cb) red_add_v2(row + (size_t)b * T, __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+            }
+          }
+        }
+      } else {
+        for (int cb = 0; cb < n_cols; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)cb, v);
+          tmem_ld_wait();
+          const int tl = cb / P.nb, bb = b0 + (cb - tl * P.nb);   // a 32-column chunk never straddles a tap
+          if (st_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int b = bb + j;
+              if (b < Cb) atomicAdd(row + (size_t)b * T + tl, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -219,14 +272,16 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
   P.nb = g->Ci > 64 ? 128 : 64;
   P.n_btiles = (g->Ci + P.nb - 1) / P.nb;
   const int T_all = g->KH * g->KW;
-  static int tpc_cfg = -1;
-  if (tpc_cfg < 0) {
+  int tpc_cfg;
+  {
     const char* e = getenv("GLIS_WG_COLS");   // tuning knob: accumulator columns per CTA (64..256)
-    tpc_cfg = e ? atoi(e) : 128;
-    if (tpc_cfg < 64 || tpc_cfg > 256) tpc_cfg = 128;
+    tpc_cfg = e ? atoi(e) : 256;
+    if (tpc_cfg < 64 || tpc_cfg > 256) tpc_cfg = 256;
   }
   P.tpc = tpc_cfg / P.nb;                   // e.g. 2 taps of 64 channels, or 1 tap of 128
   if (P.tpc < 1) P.tpc = 1;
+  if (P.tpc == 3) P.tpc = 2;
+  if (P.tpc > WG_MAX_TPC) P.tpc = WG_MAX_TPC;
   while (P.tpc > 1 && T_all % P.tpc != 0) P.tpc /= 2;
   const int n_atiles = (g->Co + 127) / 128;
   P.passes = passes;
@@ -246,6 +301,10 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: tile does not fit shared memory");
   P.stages = stages;
   P.G = G;
+  {
+    const char* dbg = getenv("GLIS_WG_DEBUG");
+    P.debug = dbg ? atoi(dbg) : 0;
+  }
 
   CUtensorMap ms_hi, ms_lo, mb_hi, mb_lo;
   {

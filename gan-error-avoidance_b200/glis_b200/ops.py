@@ -210,6 +210,8 @@ def attach_planes(t, planes):
 
 def planes_of(t, lo=True):
     """Planes of ``t``: the attached ones if still valid, else a fresh split."""
+    if isinstance(t, PlanesOnly):
+        return t._glis_planes_only
     tag = getattr(t, "_glis_planes", None)
     if tag is not None and tag[2] == t.data_ptr() and tag[3] == t._version and (tag[1] is not None or not lo):
         return tag[0], tag[1]
@@ -259,7 +261,8 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
     in_shape = tuple(x.shape)
     prec = spec.precision
     lo = prec == L.PREC_BF16X3
-    g, out = _launch_geom(spec, relation, in_shape, out_shape, x)
+    like = x._glis_planes_only[0] if isinstance(x, PlanesOnly) else x
+    g, out = _launch_geom(spec, relation, in_shape, out_shape, like)
     preact = torch.empty_like(out) if want_preact else None
     use_tc = _use_tc(spec, relation, in_shape, out_shape)
     planes = None
@@ -276,6 +279,8 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
                    L.ptr16(wp[1]), C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
                    L.ptr16(planes[1]) if planes else None, prec, L.stream())
     else:
+        if isinstance(x, PlanesOnly):
+            raise RuntimeError("glis_b200: planes-only gradient reached an fp32 kernel (internal planning error)")
         pw.need_fp32(forward_pack, not forward_pack)
         wp = pw.io if forward_pack else pw.oi
         ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact),
@@ -341,15 +346,43 @@ def _touch_hooks(*params):
             hook(p)
 
 
+class PlanesOnly(object):
+    """Stand-in for a gradient that exists ONLY as bf16 hi/lo planes (every consumer of the layer's
+    output gradient runs on tensor cores, so the fp32 copy is never written)."""
+
+    def __init__(self, shape, planes):
+        self.shape, self._glis_planes_only = tuple(shape), planes
+
+    def dim(self):
+        return len(self.shape)
+
+
+def _backward_plan(spec, pw, x_shape, dy_shape, need_dx, need_dw):
+    """(dgrad on tensor cores?, wgrad on tensor cores?) for a layer with input ``x_shape`` (NCHW-shaped)."""
+    if spec.precision == L.PREC_FP32 or len(x_shape) != 4:
+        return False, False
+    n, cin, h, w = x_shape
+    _, cout, ho, wo = dy_shape
+    tc_dx = tc_dw = True
+    if need_dx:
+        rel = L.CONV if spec.transposed else L.TCONV
+        tc_dx = _use_tc(spec, rel, tuple(dy_shape), tuple(x_shape))
+    if need_dw:
+        g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin) if spec.transposed else \
+            spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
+        tc_dw = bool(L.load().glis_wgrad_tc_supported(C.byref(g)))
+    return tc_dx, tc_dw
+
+
 def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape,
                     pw_bias=None):
     """dgrad + wgrad + weight-norm projection + bias gradient of one WN layer.
-    ``dyc``: fp32 gradient w.r.t. the layer's affine output (NHWC-dense)."""
+    ``dyc``: fp32 gradient w.r.t. the layer's affine output (NHWC-dense), or ``PlanesOnly``."""
     weight, scale = pw.weight, pw.scale
     cout, cin, t = pw.cout, pw.cin, pw.t
     prec = spec.precision
     lo = prec == L.PREC_BF16X3
-    if dy_planes is not None:
+    if dy_planes is not None and not isinstance(dyc, PlanesOnly):
         attach_planes(dyc, dy_planes)
     if xc.dim() == 4:
         n, _, h, w = xc.shape
@@ -498,12 +531,21 @@ class WNContractionTPReLU(torch.autograd.Function):
         doc = _nhwc(dout)
         lo = spec.precision == L.PREC_BF16X3
         want_planes = spec.precision != L.PREC_FP32 and doc.dim() == 4
-        dy = torch.empty_like(preact)
+        ni = ctx.needs_input_grad
+        need_dw = ni[1] or (ctx.pw.scale is not None and ni[2])
+        need_db = ctx.bias_shape is not None and ni[3]
+        tc_dx, tc_dw = _backward_plan(spec, ctx.pw, tuple(xc.shape), tuple(preact.shape), ni[0], need_dw)
+        # every consumer of dy on tensor cores (and no bias gradient): the fp32 copy is never read
+        planes_only = want_planes and tc_dx and tc_dw and not need_db and (ni[0] or need_dw)
+        dy = None if planes_only else torch.empty_like(preact)
         dy_hi = torch.empty_like(preact, dtype=torch.bfloat16) if want_planes else None
         dy_lo = torch.empty_like(preact, dtype=torch.bfloat16) if (want_planes and lo) else None
         ga, gb = _dense_grad(a_raw), _dense_grad(b_t)
-        direct = ga is not None and gb is not None and ctx.needs_input_grad[4]
-        if direct:      # the kernel adds atomically: straight into the (zero-filled) flat gradients
+        want_ab = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        direct = ga is not None and gb is not None and ctx.needs_input_grad[4] and ctx.needs_input_grad[5]
+        if not want_ab:   # frozen TPReLU parameters (D during the G update): no sums, no buffers
+            da = db = None
+        elif direct:      # the kernel adds atomically: straight into the (zero-filled) flat gradients
             da, db = ga, gb
         else:
             da = torch.zeros(c, device=doc.device, dtype=torch.float32)
@@ -513,7 +555,8 @@ class WNContractionTPReLU(torch.autograd.Function):
         if direct:
             _touch_hooks(a_raw, b_t)
             da = db = None
-        ni = ctx.needs_input_grad
+        if planes_only:
+            dy = PlanesOnly(preact.shape, (dy_hi, dy_lo))
         dx, dw, dscale, dbias = _layer_backward(spec, ctx.pw, xc, dy, (dy_hi, dy_lo) if want_planes else None,
                                                 ni[0], ni[1], ctx.pw.scale is not None and ni[2],
                                                 ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)

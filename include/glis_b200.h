@@ -156,7 +156,8 @@ int glis_tprelu_backward(const float* x, const float* a_raw, const float* b, con
                          float* dx, float* da, float* db, int64_t numel, int C, int inner,
                          void* stream);
 /* As glis_tprelu_backward, writing dx as fp32 (dx may be NULL) and/or as bf16 hi/lo planes
- * (dx_hi may be NULL; dx_lo may be NULL) so the tensor-core dgrad / wgrad can consume it directly. */
+ * (dx_hi may be NULL; dx_lo may be NULL) so the tensor-core dgrad / wgrad can consume it directly.
+ * da and db may BOTH be NULL (frozen TPReLU parameters, e.g. D during the G update): no sums. */
 int glis_tprelu_backward_planes(const float* x, const float* a_raw, const float* b, const float* dout,
                                 float* dx, void* dx_hi, void* dx_lo, float* da, float* db, int64_t numel,
                                 int C, int inner, void* stream);

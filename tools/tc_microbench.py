@@ -39,9 +39,12 @@ def main():
         out = torch.empty(n, ho, wo, co, device=dev)
         ep = L.Epilogue(None, 0, None, None, None)
         res = []
-        for dbg in ("0",):
+        ref = None
+        for cl in (sys.argv[1:] or ["1", "2", "4"]):
+            dbg = "0"
             os.environ["GLIS_TC_DEBUG"] = dbg
-            for prec in (L.PREC_BF16X3, L.PREC_BF16):
+            os.environ["GLIS_TC_CLUSTER"] = cl
+            for prec in (L.PREC_BF16X3,):
                 def run():
                     L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xh), L.ptr16(xl), L.ptr16(wh), L.ptr16(wl),
                            C.byref(ep), L.ptr(out), None, None, prec, L.stream())
@@ -59,10 +62,17 @@ def main():
                 graph.replay()
                 e1.record()
                 torch.cuda.synchronize()
-                res.append("dbg%s/%s %6.1fus" % (dbg, "x3" if prec == L.PREC_BF16X3 else "x1", e0.elapsed_time(e1) * 50))
+                out.zero_()
+                run()
+                torch.cuda.synchronize()
+                if ref is None:
+                    ref = out.clone()
+                err = ((out - ref).abs().max() / ref.abs().max()).item()
+                res.append("cl%s %6.1fus (dev %.1e)" % (cl, e0.elapsed_time(e1) * 50, err))
         flop = 2.0 * n * (ho * wo if rel == L.CONV else hi * wi) * co * ci * (16 if rel == L.CONV else 16)
         print("%-28s %5.2f GFLOP | %s" % (name, flop / 1e9, "  ".join(res)))
     os.environ["GLIS_TC_DEBUG"] = "0"
+    os.environ.pop("GLIS_TC_CLUSTER", None)
 
 
 if __name__ == "__main__":
