@@ -443,7 +443,9 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // Reasons the tensor-core path does not apply (the caller then uses the fp32 kernel).
 int tc_conv_supported(const glis_geom_t* g) {
-  if (g->Ci % TC_BK != 0) return 0;                       // K blocks of 64 channels
+  // K blocks of 64 channels; a ragged last block is TMA zero fill on the weight side (whatever the
+  // pixel box reads beyond Ci is multiplied by zero), at most half of a block wasted
+  if (g->Ci % 8 != 0 || (g->Ci % TC_BK != 0 && g->Ci < 32)) return 0;
   if (g->Co < 32) return 0;                               // 3- and 1-channel outputs: < 25 % of the 128 MMA rows
   if (g->dil_h != 1 || g->dil_w != 1) return 0;
   if (g->relation == GLIS_CONV) {
@@ -454,7 +456,6 @@ int tc_conv_supported(const glis_geom_t* g) {
   if (g->relation == GLIS_TCONV) Wq = (g->Wo + g->stride_w - 1) / g->stride_w;
   if (Wq > 256) return 0;                                 // one tile row must fit the MMA N
   if (g->relation == GLIS_TCONV && g->Wo % g->stride_w != 0) return 0;  // all phases equally wide
-  if (g->KH * g->KW * (g->Ci / TC_BK) < 1) return 0;
   return 1;
 }
 
@@ -521,7 +522,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.n_mma = round_up(P.tw * P.th * P.tn, 16);
   P.tmem_cols = 64;  // two accumulators of tmem_cols / 2 columns each
   while (P.tmem_cols < 2 * P.n_mma) P.tmem_cols *= 2;
-  P.kblocks = g->Ci / TC_BK;
+  P.kblocks = (g->Ci + TC_BK - 1) / TC_BK;
   P.passes = passes;
   P.tiles_h = (Hq + P.th - 1) / P.th;
   const int tiles_n = (g->N + P.tn - 1) / P.tn;

@@ -237,7 +237,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 
 int tc_wgrad_supported(const glis_geom_t* g) {
   if (g->relation != GLIS_CONV) return 0;
-  if (g->Co % 8 != 0 || g->Ci % 8 != 0 || g->Ci < 64 || g->Co < 64) return 0;
+  if (g->Co % 8 != 0 || g->Ci % 8 != 0 || g->Ci < 32 || g->Co < 64) return 0;   // ragged 64-channel groups: TMA zero fill
   if (g->Hi % g->stride_h != 0 || g->Wi % g->stride_w != 0) return 0;
   if (g->Wo > 64) return 0;  // one coarse row per K tile at least
   return 1;

@@ -51,6 +51,9 @@ SIGNATURES = {
     "glis_rmsprop": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "glis_randn": [_vp, _i64, _u64, _u64, _vp],
     "glis_uniform": [_vp, _i64, _u64, _u64, _vp],
+    "glis_unfold4x4s2_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "glis_fold4x4s2": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "glis_wn_pack_matrix_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
 }
 
 _lib = None

@@ -97,6 +97,7 @@ class PackedWeights(object):
         self.norm = None
         self.io = self.oi = None            # fp32 [T][Cin][Cout], [T][Cout][Cin]
         self.fwd = self.bwd = None          # bf16 (hi, lo): [T][Cout][Cin], [T][Cin][Cout]
+        self.mat = self.mat_t = None        # bf16 (hi, lo): E [A][J] and E^T [J][A] (image-side layers)
 
     def _w(self):
         w = self.weight.detach().contiguous()
@@ -168,6 +169,25 @@ class PackedWeights(object):
             self.fwd = (fh, fl)
         if bwd:
             self.bwd = (bh, bl)
+
+
+def _need_matrix(pw, lo):
+    """E / E^T packs of an image-side layer (csrc/image_side.cu): one norm + one pack launch."""
+    if pw.mat is not None:
+        return
+    w, sc = pw._w()
+    dev = w.device
+    had_norm = pw.norm is not None
+    if not had_norm:
+        pw.need_fp32(False, False)          # the norm alone
+    a = w.shape[0]
+    j = w.numel() // a
+    mk = lambda shape, want: torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
+    eh, el = mk((a, j), True), mk((a, j), lo)
+    th, tl = mk((j, a), True), mk((j, a), lo)
+    L.call("glis_wn_pack_matrix_bf16", L.ptr(w), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, a, j, pw.t,
+           L.ptr16(eh), L.ptr16(el), L.ptr16(th), L.ptr16(tl), L.stream())
+    pw.mat, pw.mat_t = (eh, el), (th, tl)
 
 
 def packed_weights(weight, scale, spec):
@@ -250,6 +270,94 @@ def _use_tc(spec, relation, in_shape, out_shape):
     return tc_supported(spec.geom(relation, n, hi, wi, ci, ho, wo, co))
 
 
+_SPEC_1X1 = None
+
+
+def _spec_1x1():
+    global _SPEC_1X1
+    if _SPEC_1X1 is None:
+        _SPEC_1X1 = ContractionSpec(False, (1, 1), (1, 1), (0, 0), (1, 1))
+    return _SPEC_1X1
+
+
+def _is_4x4s2p1(spec):
+    return (spec.kernel_size == (4, 4) and spec.stride == (2, 2) and spec.padding == (1, 1)
+            and spec.dilation == (1, 1) and tuple(spec.output_padding) == (0, 0))
+
+
+def image_side_mode(spec, relation, in_shape, out_shape):
+    """"unfold" / "fold" when this launch is an image-side 4x4-s2-p1 contraction that runs as a 1x1
+    product on the tensor cores (csrc/image_side.cu), else None."""
+    if spec.precision == L.PREC_FP32 or len(in_shape) != 4 or not _is_4x4s2p1(spec):
+        return None
+    n, ci, hi, wi = in_shape
+    _, co, ho, wo = out_shape
+    if relation == L.CONV and ci <= 4 and co % 8 == 0 and co >= 32 and hi == 2 * ho and wi == 2 * wo and wo <= 256:
+        return "unfold"
+    if relation == L.TCONV and co <= 4 and ci % 8 == 0 and ci >= 32 and ho == 2 * hi and wo == 2 * wi and wi <= 256:
+        return "fold"
+    return None
+
+
+def unfolded_planes(x, lo=True):
+    """bf16 hi/lo planes [N, H/2, W/2, 16*C] of the 4x4-s2-p1 patches of ``x`` (fp32 NHWC-dense, C <= 4);
+    cached on the tensor so that a layer's forward / data gradient and its weight gradient share them."""
+    tag = getattr(x, "_glis_unfolded", None)
+    if tag is not None and tag[2] == x.data_ptr() and tag[3] == x._version and (tag[1] is not None or not lo):
+        return tag[0], tag[1]
+    n, c, h, w = x.shape
+    hi = torch.empty((n, h // 2, w // 2, 16 * c), device=x.device, dtype=torch.bfloat16)
+    lo_t = torch.empty_like(hi) if lo else None
+    L.call("glis_unfold4x4s2_bf16", L.ptr(x), n, h, w, c, L.ptr16(hi), L.ptr16(lo_t), L.stream())
+    try:
+        x._glis_unfolded = (hi, lo_t, x.data_ptr(), x._version)
+    except AttributeError:
+        pass
+    return hi, lo_t
+
+
+def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
+                       want_preact, want_planes):
+    """The two image-side launches as 1x1 tensor-core products (see image_side_mode)."""
+    prec = spec.precision
+    lo = prec == L.PREC_BF16X3
+    _need_matrix(pw, lo)
+    n, ci, hi, wi = x.shape
+    _, co, ho, wo = out_shape
+    s1 = _spec_1x1()
+    if mode == "unfold":
+        # out[pix][co] = sum_j unfold(x)[pix][j] * M[co][j]:  M = E (conv forward) or E (transposed dgrad)
+        xp = unfolded_planes(x, lo)
+        j = 16 * ci
+        g = s1.geom(L.CONV, n, ho, wo, j, ho, wo, co)
+        out = _empty_nhwc(n, co, ho, wo, x)
+        preact = torch.empty_like(out) if want_preact else None
+        planes = None
+        if want_planes:
+            planes = (torch.empty_like(out, dtype=torch.bfloat16),
+                      torch.empty_like(out, dtype=torch.bfloat16) if lo else None)
+        wp = pw.mat
+        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None)
+        with L.timed("image_side unfold M=%d N=%d K=%d tc" % (n * ho * wo, co, j)):
+            L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]), L.ptr16(wp[1]),
+                   C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
+                   L.ptr16(planes[1]) if planes else None, prec, L.stream())
+        return out, preact, planes
+    # fold: cols[pix][j] = sum_ci x[pix][ci] * E^T[j][ci];  out = fold(cols) + bias
+    xp = planes_of(x, lo)
+    j = 16 * co
+    g = s1.geom(L.CONV, n, hi, wi, ci, hi, wi, j)
+    cols = torch.empty((n, hi, wi, j), device=xp[0].device, dtype=torch.float32)
+    wp = pw.mat_t
+    ep = L.Epilogue(None, L.ACT_NONE, None, None, None, None, None)
+    with L.timed("image_side fold M=%d N=%d K=%d tc" % (n * hi * wi, j, ci)):
+        L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]), L.ptr16(wp[1]),
+               C.byref(ep), L.ptr(cols), None, None, prec, L.stream())
+    out = _empty_nhwc(n, co, ho, wo, xp[0])
+    L.call("glis_fold4x4s2", L.ptr(cols), n, hi, wi, co, L.ptr(bias), act, L.ptr(out), L.stream())
+    return out, None, None
+
+
 def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_NONE, act_a=None, act_b=None,
            want_preact=False, want_planes=False):
     """One gather-GEMM launch (tensor cores when the geometry tiles, FFMA otherwise).
@@ -261,6 +369,14 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
     in_shape = tuple(x.shape)
     prec = spec.precision
     lo = prec == L.PREC_BF16X3
+    mode = image_side_mode(spec, relation, in_shape, tuple(out_shape))
+    if mode == "fold" and (act not in (L.ACT_NONE, L.ACT_SIGMOID) or want_preact or want_planes):
+        mode = None
+    if mode == "unfold" and isinstance(x, PlanesOnly):
+        mode = None
+    if mode is not None:
+        return _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
+                                  want_preact, want_planes)
     like = x._glis_planes_only[0] if isinstance(x, PlanesOnly) else x
     g, out = _launch_geom(spec, relation, in_shape, out_shape, like)
     preact = torch.empty_like(out) if want_preact else None
@@ -366,12 +482,31 @@ def _backward_plan(spec, pw, x_shape, dy_shape, need_dx, need_dw):
     tc_dx = tc_dw = True
     if need_dx:
         rel = L.CONV if spec.transposed else L.TCONV
-        tc_dx = _use_tc(spec, rel, tuple(dy_shape), tuple(x_shape))
+        # (a "fold" data gradient reads dy as planes; an "unfold" one needs the fp32 dy)
+        tc_dx = (_use_tc(spec, rel, tuple(dy_shape), tuple(x_shape))
+                 or image_side_mode(spec, rel, tuple(dy_shape), tuple(x_shape)) == "fold")
     if need_dw:
-        g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin) if spec.transposed else \
-            spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
-        tc_dw = bool(L.load().glis_wgrad_tc_supported(C.byref(g)))
+        if _image_side_wgrad(spec, x_shape, dy_shape) is not None:
+            tc_dw = not spec.transposed     # conv: small = dy as planes; transposed: unfold(dy) needs fp32 dy
+        else:
+            g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin) if spec.transposed else \
+                spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
+            tc_dw = bool(L.load().glis_wgrad_tc_supported(C.byref(g)))
     return tc_dx, tc_dw
+
+
+def _image_side_wgrad(spec, x_shape, dy_shape):
+    """(n, hs, ws, ca, c_img) when the layer's weight gradient runs as the 1x1 product
+    G[a][j] = sum_pix small[pix][a] * unfold(big)[pix][j] on tcgen05 (csrc/image_side.cu), else None."""
+    if spec.precision == L.PREC_FP32 or len(x_shape) != 4 or not _is_4x4s2p1(spec):
+        return None
+    n, cin, h, w = x_shape
+    _, cout, ho, wo = dy_shape
+    if spec.transposed:       # small = x (coarse, Cin channels), big = dy (fine, Cout <= 4)
+        ok = cout <= 4 and cin % 8 == 0 and cin >= 64 and ho == 2 * h and wo == 2 * w and w <= 64
+        return (n, h, w, cin, cout) if ok else None
+    ok = cin <= 4 and cout % 8 == 0 and cout >= 64 and h == 2 * ho and w == 2 * wo and wo <= 64
+    return (n, ho, wo, cout, cin) if ok else None
 
 
 def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape,
@@ -406,7 +541,15 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
             g = spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
             small, big = dyc, xc
         tag = "conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)
-        if prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
+        isw = _image_side_wgrad(spec, tuple(xc.shape), tuple(dyc.shape)) if xc.dim() == 4 else None
+        if isw is not None:
+            n_, hs, ws, ca, c_img = isw
+            g1 = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
+            sp, bp = planes_of(small, lo), unfolded_planes(big, lo)
+            with L.timed(tag + " tc (image side)"):
+                L.call("glis_conv_wgrad_bf16", C.byref(g1), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
+                       L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
+        elif prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
             sp, bp = planes_of(small, lo), planes_of(big, lo)
             with L.timed(tag + " tc"):
                 L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
@@ -469,6 +612,7 @@ class WNContraction(torch.autograd.Function):
         ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
+        ctx.x_unfolded = getattr(xc, "_glis_unfolded", None)
         ctx.save_for_backward(xc)
         return out
 
@@ -477,6 +621,8 @@ class WNContraction(torch.autograd.Function):
         (xc,) = ctx.saved_tensors
         if ctx.x_planes is not None:
             xc._glis_planes = ctx.x_planes
+        if ctx.x_unfolded is not None:
+            xc._glis_unfolded = ctx.x_unfolded
         dyc = _nhwc(dy)
         ni = ctx.needs_input_grad
         dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dyc, None, ni[0], ni[1],
@@ -510,6 +656,7 @@ class WNContractionTPReLU(torch.autograd.Function):
         ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
+        ctx.x_unfolded = getattr(xc, "_glis_unfolded", None)
         ctx.save_for_backward(xc, preact, a_raw, b_t)
         ctx.set_materialize_grads(False)   # no zero tensors for the (non-differentiable) plane outputs
         if planes is None:
@@ -524,6 +671,8 @@ class WNContractionTPReLU(torch.autograd.Function):
         xc, preact, a_raw, b_t = ctx.saved_tensors
         if ctx.x_planes is not None:
             xc._glis_planes = ctx.x_planes
+        if ctx.x_unfolded is not None:
+            xc._glis_unfolded = ctx.x_unfolded
         spec = ctx.spec
         c = a_raw.numel()
         if dout is None:

@@ -118,7 +118,7 @@ int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int C
                          float c, float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo,
                          void* stream);
 
-/* 1 if glis_conv_forward_bf16 can tile this geometry (Ci % 64 == 0, no dilation, input
+/* 1 if glis_conv_forward_bf16 can tile this geometry (Ci % 8 == 0 and >= 32 or a multiple of 64, no dilation, input
  * divisible by the stride for GLIS_CONV, output rows <= 256 pixels, Cout >= 32), else 0. */
 int glis_conv_tc_supported(const glis_geom_t* g);
 
@@ -138,13 +138,29 @@ int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x
 int glis_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G,
                     int precision, void* stream);
 
-/* 1 if glis_conv_wgrad_bf16 can tile this geometry (channels multiples of 8 and >= 64, fine
+/* 1 if glis_conv_wgrad_bf16 can tile this geometry (channels multiples of 8, Co >= 64, Ci >= 32, fine
  * grid divisible by the stride, coarse rows <= 64 pixels). */
 int glis_wgrad_tc_supported(const glis_geom_t* g);
 
 /* glis_conv_wgrad on tcgen05 (both operands MN-major straight from the NHWC planes); adds into G. */
 int glis_conv_wgrad_bf16(const glis_geom_t* g, const void* small_hi, const void* small_lo,
                          const void* big_hi, const void* big_lo, float* G, int precision, void* stream);
+
+/* ---- image-side layers (C <= 4 colour channels on one side; 4x4 kernel, stride 2, pad 1) ------------
+ * Unfolding the image side into J = 16*C columns per coarse pixel, j = c*16 + kh*4 + kw, turns
+ * D / R level 0 (common/model.py:31-36), G level 0 (:249-251) and their gradients into 1x1
+ * contractions for glis_conv_forward_bf16 / glis_conv_wgrad_bf16 (see csrc/image_side.cu). */
+
+/* x fp32 [N,H,W,C] -> bf16 hi/lo planes [N,H/2,W/2,16*C] (lo may be NULL); zero padding applied. */
+int glis_unfold4x4s2_bf16(const float* x, int N, int H, int W, int C, void* hi, void* lo, void* stream);
+/* cols fp32 [N,Hi,Wi,16*C] -> out fp32 [N,2Hi,2Wi,C] = fold(cols) + bias[c], act in {NONE, SIGMOID}. */
+int glis_fold4x4s2(const float* cols, int N, int Hi, int Wi, int C, const float* bias, int act, float* out,
+                   void* stream);
+/* Effective weights as the matrix E[a][j] in master memory order (conv: a = Cout, j = ci*T + tap,
+ * out_axis 0; transposed: a = Cin, j = co*T + tap, out_axis 1), scaled by scale/norm of the true
+ * output channel: E (A x J) and E^T (J x A) as K-major bf16 hi/lo packs (each optional). */
+int glis_wn_pack_matrix_bf16(const float* w, const float* scale, const float* norm, int out_axis, int A, int J,
+                             int T, void* e_hi, void* e_lo, void* et_hi, void* et_lo, void* stream);
 
 /* ---- pointwise / reductions -------------------------------------------------------
  * TPReLU forward (common/modules/TPReLU.py:16-18) on a tensor whose channel of element i is
