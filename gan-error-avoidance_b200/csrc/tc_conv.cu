@@ -15,8 +15,8 @@
 // fp32 fidelity comes from a bf16 hi/lo split of both operands: three MMAs per k-step
 // (hi*hi + hi*lo + lo*hi), ~2^-16 relative (GLIS_PREC_BF16X3); one MMA in GLIS_PREC_BF16.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (TMEM -> registers -> bias / TPReLU / sigmoid -> global, plus the
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..17 = epilogue (TMEM -> registers -> bias / TPReLU / sigmoid -> global, plus the
 // optional bf16 hi/lo planes the next tensor-core layer consumes).
 #include <stdlib.h>
 
@@ -29,7 +29,8 @@ using namespace sm100;
 
 constexpr int TC_BM = 128;       // channels per CTA (UMMA M)
 constexpr int TC_BK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_EPI_WARPS = 16; // 4 per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA warp, MMA warp, epilogue warps
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_DEFAULT_CLUSTER = 1;
 
@@ -78,44 +79,32 @@ __device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
   return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
-// Walks the (iw, ih) position of consecutive tile columns without branches.
-struct ColWalk {
-  long long off;           // output element offset of the current column (this lane's channel)
-  int iw, ih;
-  long long step_w, step_h, step_n;
-  int tw, th;
-  __device__ __forceinline__ void next() {
-    const bool wrap_w = (iw + 1 == tw);
-    const bool wrap_h = wrap_w && (ih + 1 == th);
-    off += step_w + (wrap_w ? step_h : 0ll) + (wrap_h ? step_n : 0ll);
-    iw = wrap_w ? 0 : iw + 1;
-    ih = wrap_h ? 0 : (wrap_w ? ih + 1 : ih);
-  }
-};
-
 // Epilogue of one 32-column accumulator chunk for this lane's channel, specialised at compile
-// time so that the per-column code is a handful of predicated instructions.
+// time so that the per-column code is a handful of predicated instructions.  `rel` = element
+// offsets of the chunk's columns relative to the tile origin (shared memory, built once per CTA:
+// every tile of a launch has the same shape), `base` = the tile origin + this lane's channel.
 template <int ACT, bool PREACT, bool F32, bool PLANES>
-__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int nvalid, ColWalk w, float bias, float ta,
+__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int nvalid, long long base,
+                                                  const uint32_t* __restrict__ rel, float bias, float ta,
                                                   float tb, float* __restrict__ preact, float* __restrict__ out_f32,
                                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j < nvalid) {
+      const long long off = base + rel[j];
       const float y = __uint_as_float(v[j]) + bias;
-      if (PREACT) preact[w.off] = y;
+      if (PREACT) preact[off] = y;
       float o = y;
       if (ACT == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
       if (ACT == GLIS_ACT_SIGMOID) o = 1.f / (1.f + __expf(-y));
-      if (F32) out_f32[w.off] = o;
+      if (F32) out_f32[off] = o;
       if (PLANES) {
         __nv_bfloat16 hi, lo;
         split_bf16(o, hi, lo);
-        out_hi[w.off] = hi;
-        if (out_lo) out_lo[w.off] = lo;
+        out_hi[off] = hi;
+        if (out_lo) out_lo[off] = lo;
       }
     }
-    w.next();
   }
 }
 
@@ -164,6 +153,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
+  uint32_t* rel = tmem_slot + 4;   // [256] column -> element offset from the tile origin
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -171,10 +161,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
     if (P.passes == 3) { tma_prefetch_desc(&map_w_lo); tma_prefetch_desc(&map_x_lo); }
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)P.cluster); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  {
+    const int sh = g.relation == GLIS_TCONV ? g.stride_h : 1, sw = g.relation == GLIS_TCONV ? g.stride_w : 1;
+    const int per_img = P.tw * P.th;
+    for (int c = threadIdx.x; c < 256; c += TC_THREADS) {
+      const int in_ = c / per_img, r = c - in_ * per_img, ih = r / P.tw, iw = r - ih * P.tw;
+      rel[c] = (uint32_t)((((long long)in_ * g.Ho + (long long)ih * sh) * g.Wo + (long long)iw * sw) * g.Co);
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (P.cluster > 1) cluster_sync_all();   // every CTA's barriers exist before a neighbour signals them
@@ -300,16 +298,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // Two warps per TMEM lane quarter; they take alternate 32-column chunks of the tile.
+    // ===================== epilogue (warps 2..17) =====================
+    // Four warps per TMEM lane quarter; they take every fourth 32-column chunk of the tile.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // 0 or 1
+    const int part = (warp - 2) >> 2;       // 0..3
     const int cols = P.tw * P.th * P.tn;
-    const int sh = g.relation == GLIS_TCONV ? g.stride_h : 1, sw = g.relation == GLIS_TCONV ? g.stride_w : 1;
-    const long long step_w = (long long)sw * g.Co;
-    const long long row_pitch = (long long)sh * g.Wo * g.Co;
-    const long long step_h = row_pitch - (long long)P.tw * step_w;
-    const long long step_n = (long long)g.Ho * g.Wo * g.Co - (long long)P.th * row_pitch;
+    const int sh = g.relation == GLIS_TCONV ? g.stride_h : 1;
     uint32_t acc = 0, full_phase = 0;
     int tr_e = 1024;
     for (int grp = cluster_id; grp < P.n_groups; grp += n_clusters) {
@@ -325,48 +319,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       }
       const int oy0 = g.relation == GLIS_TCONV ? tl.qy0 * sh + tl.ph.ry : tl.qy0;
       const int ox0 = g.relation == GLIS_TCONV ? tl.ph.rx : 0;
+      const long long base = (((long long)tl.n0 * g.Ho + oy0) * g.Wo + ox0) * g.Co + co;
       const int valid_cols = P.tn == 1 ? min(P.th, tl.ph.Hq - tl.qy0) * P.tw : min(P.tn, g.N - tl.n0) * P.th * P.tw;
       mbar_wait(&tmem_full_bar[acc], (full_phase >> acc) & 1u);
       tc_fence_after_sync();
       if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) P.trace[tr_e++] = global_timer_ns();
       const uint32_t tmem_d = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      for (int cb = half * 32; cb < cols; cb += 64) {
-        // position of column cb inside the pixel tile and its output offset
-        const int in_ = cb / (P.tw * P.th);
-        const int r = cb - in_ * (P.tw * P.th);
-        ColWalk w;
-        w.ih = r / P.tw; w.iw = r - w.ih * P.tw;
-        w.tw = P.tw; w.th = P.th; w.step_w = step_w; w.step_h = step_h; w.step_n = step_n;
-        w.off = (((long long)(tl.n0 + in_) * g.Ho + oy0 + (long long)w.ih * sh) * g.Wo + ox0 + (long long)w.iw * sw) * g.Co + co;
+      // a quarter whose 32 channels are all out of range (Cout <= 64 or 96) has nothing to store
+      const bool quarter_ok = tl.co0 + q * 32 < g.Co && !(P.debug & 1) && !tl.ghost;
+      for (int cb = part * 32; cb < cols && quarter_ok; cb += 128) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_d + (uint32_t)cb, v);
         tmem_ld_wait();
         // valid columns form a prefix of the tile: ragged rows (tn == 1) or ragged images (th == Hq) come last
         const int nvalid = ch_ok ? valid_cols - cb : 0;
+        const uint32_t* rc = rel + cb;
         switch (P.ep_mode) {
-          case 1: tc_epilogue_chunk<GLIS_ACT_NONE, false, true, false>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
-          case 2: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
-          case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
-          case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
-          case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, w, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 1: tc_epilogue_chunk<GLIS_ACT_NONE, false, true, false>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 2: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           default: {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nvalid) {
+                const long long off = base + rc[j];
                 const float y = __uint_as_float(v[j]) + bias;
-                if (P.preact) P.preact[w.off] = y;
+                if (P.preact) P.preact[off] = y;
                 float o = y;
                 if (P.act == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
                 else if (P.act == GLIS_ACT_SIGMOID) { o = 1.f / (1.f + __expf(-y)); }
-                if (P.out_f32) P.out_f32[w.off] = o;
+                if (P.out_f32) P.out_f32[off] = o;
                 if (P.out_hi) {
                   __nv_bfloat16 hi, lo;
                   split_bf16(o, hi, lo);
-                  P.out_hi[w.off] = hi;
-                  if (P.out_lo) P.out_lo[w.off] = lo;
+                  P.out_hi[off] = hi;
+                  if (P.out_lo) P.out_lo[off] = lo;
                 }
               }
-              w.next();
             }
           }
         }
@@ -532,7 +523,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.cluster = cs;
   P.n_groups = P.total_tiles / cs;
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
-  int stages = (int)((220 * 1024) / stage_bytes);
+  int stages = (int)((219 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: tile does not fit shared memory");
   P.stages = stages;
@@ -583,7 +574,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     if (rc) return rc;
   }
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*column offsets*/;
   GLIS_REQUIRE(P.tmem_cols <= 512, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: accumulators exceed TMEM");
   static bool attr_set = false;
   if (!attr_set) {
