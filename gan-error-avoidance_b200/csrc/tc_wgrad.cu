@@ -289,10 +289,34 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
   P.tiles_total = P.tiles_h * ((g->N + P.tn - 1) / P.tn);
   const int T = g->KH * g->KW;
   const int ctas = n_atiles * P.n_btiles * (T / P.tpc);
-  int splits = (148 * 2 + ctas - 1) / ctas;
-  const int max_splits = (P.tiles_total + 7) / 8;  // at least 8 K-tiles per CTA
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // Split K so that the CTAs fill whole waves of the machine (one CTA per SM: the stages take most of
+  // the shared memory): cost = waves x (K tiles per CTA + the fixed prologue / reduction epilogue,
+  // worth about EPI tiles); fewer splits also mean fewer reductions into G.
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  int epi = 10;
+  {
+    const char* e = getenv("GLIS_WG_EPI");
+    if (e) epi = atoi(e);
+  }
+  int max_splits = (P.tiles_total + 3) / 4;  // at least 4 K-tiles per CTA
+  if (max_splits < 1) max_splits = 1;
+  if (max_splits > 4 * num_sms) max_splits = 4 * num_sms;
+  int splits = 1;
+  long best_cost = -1;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int tps = (P.tiles_total + sp - 1) / sp;
+    const int sp_eff = (P.tiles_total + tps - 1) / tps;
+    if (sp_eff != sp) continue;
+    const long waves = ((long)ctas * sp + num_sms - 1) / num_sms;
+    const long cost = waves * (tps + epi);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+  }
   P.tiles_per_split = (P.tiles_total + splits - 1) / splits;
   splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
   const size_t stage_bytes = 2 * (size_t)(2 + P.tpc * (P.nb / 64)) * P.kp * 128;

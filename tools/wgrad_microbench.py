@@ -17,6 +17,10 @@ SHAPES = [  # name, N, Hi, Wi, Cb (fine), Ho, Wo, Ca (coarse)
     ("G2 wgrad 256->128 10->20", 64, 20, 20, 128, 10, 10, 256),
     ("G1 wgrad 128->64 20->40", 64, 40, 40, 64, 20, 20, 128),
 ]
+SHAPES_1X1 = [  # image-side weight gradients as 1x1 products: name, N, H, W, Cb, Ca
+    ("D0 wgrad 2B (unfolded)", 128, 40, 40, 48, 64),
+    ("G0 wgrad (unfolded)", 64, 40, 40, 48, 64),
+]
 
 
 def timeit(fn, reps=20):
@@ -45,16 +49,41 @@ def main():
         G = torch.zeros(ca, cb, 4, 4, device=dev)
         res = []
         for v in variants:
-            dbg, cols = v.split(":")
+            parts = v.split(":")
+            dbg, cols = parts[0], parts[1]
             os.environ["GLIS_WG_DEBUG"] = dbg
             os.environ["GLIS_WG_COLS"] = cols
+            if len(parts) > 2:
+                os.environ["GLIS_WG_EPI"] = parts[2]
+            else:
+                os.environ.pop("GLIS_WG_EPI", None)
             t = timeit(lambda: L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]),
                                       L.ptr16(bp[0]), L.ptr16(bp[1]), L.ptr(G), L.PREC_BF16X3, L.stream()))
-            res.append("d%s/c%s %6.1f" % (dbg, cols, t))
+            res.append("%s %6.1f" % (v, t))
         flop = 2.0 * n * ho * wo * ca * cb * 16
         print("%-30s %5.2f GF | %s" % (name, flop / 1e9, "  ".join(res)), flush=True)
+    spec1 = ops.ContractionSpec(False, (1, 1), (1, 1), (0, 0), (1, 1))
+    for name, n, h, w, cb, ca in SHAPES_1X1:
+        g = spec1.geom(L.CONV, n, h, w, cb, h, w, ca)
+        sp = ops.split_bf16(torch.randn(n, h, w, ca, device=dev))
+        bp = ops.split_bf16(torch.randn(n, h, w, cb, device=dev))
+        G = torch.zeros(ca, cb, device=dev)
+        res = []
+        for v in variants:
+            parts = v.split(":")
+            os.environ["GLIS_WG_DEBUG"] = parts[0]
+            os.environ["GLIS_WG_COLS"] = parts[1]
+            if len(parts) > 2:
+                os.environ["GLIS_WG_EPI"] = parts[2]
+            else:
+                os.environ.pop("GLIS_WG_EPI", None)
+            t = timeit(lambda: L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]),
+                                      L.ptr16(bp[0]), L.ptr16(bp[1]), L.ptr(G), L.PREC_BF16X3, L.stream()))
+            res.append("%s %6.1f" % (v, t))
+        print("%-30s          | %s" % (name, "  ".join(res)), flush=True)
     os.environ["GLIS_WG_DEBUG"] = "0"
     os.environ.pop("GLIS_WG_COLS", None)
+    os.environ.pop("GLIS_WG_EPI", None)
 
 
 if __name__ == "__main__":
