@@ -172,6 +172,25 @@ channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t
   }
 }
 
+// Channel sums of an NHWC tensor with C <= 4 (the image-side bias gradient): a thread owns whole
+// pixels, keeps C partial sums in registers, warps reduce, one atomic per warp and channel.
+__global__ void __launch_bounds__(PW_NT)
+channel_sum_small_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int C) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = (int64_t)blockIdx.x * PW_NT + threadIdx.x; r < rows; r += (int64_t)gridDim.x * PW_NT) {
+    const float* p = x + r * C;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c < C) acc[c] += __ldg(p + c);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < C) {
+      const float s = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(out + c, s);
+    }
+  }
+}
+
 // One block: B is the batch (tens to thousands of logits).
 __global__ void __launch_bounds__(PW_NT)
 bce_logits_kernel(const float* __restrict__ logit, float target, int B, float gscale, float* __restrict__ loss,
@@ -357,6 +376,12 @@ extern "C" int glis_channel_sum(const float* x, float* out, int64_t numel, int C
     }
   }
   if (numel == 0) return GLIS_OK;
+  if (inner == 1 && C <= 4 && numel % C == 0) {
+    const int64_t rows = numel / C;
+    channel_sum_small_kernel<<<pw_blocks(rows, 8), PW_NT, 0, st>>>(x, out, rows, C);
+    GLIS_CHECK_LAUNCH("glis_channel_sum(small C)");
+    return GLIS_OK;
+  }
   channel_sum_kernel<<<pw_blocks(numel, 8), PW_NT, 0, st>>>(x, out, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_channel_sum");
   return GLIS_OK;

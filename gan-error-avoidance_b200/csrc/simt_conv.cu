@@ -598,12 +598,13 @@ int validate_geom(const glis_geom_t* g, const char* who) {
 }
 
 bool is_linear_geom(const glis_geom_t* g);
+bool is_head_dgrad_geom(const glis_geom_t* g);
 int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                         float* out, cudaStream_t st);
 
 int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                       float* out, cudaStream_t st) {
-  if (is_linear_geom(g)) {
+  if (is_linear_geom(g) || is_head_dgrad_geom(g)) {
     const int rc = simt_linear_forward(g, in, wpack, ep, out, st);
     if (rc != GLIS_E_UNSUPPORTED) return rc;
   }

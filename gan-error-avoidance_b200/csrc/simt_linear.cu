@@ -181,10 +181,18 @@ bool is_linear_geom(const glis_geom_t* g) {
   return g->KH == 1 && g->KW == 1 && g->Hi == 1 && g->Wi == 1 && g->stride_h == 1 && g->stride_w == 1;
 }
 
+// The data gradient of a one-channel "valid" head (D's final conv): out[n][tap][co] = in[n] * Wp[tap][0][co],
+// a rank-1 product — the K = 1 case of the linear kernel with Wp read as one row of KH*KW*Co columns.
+bool is_head_dgrad_geom(const glis_geom_t* g) {
+  return g->relation == GLIS_TCONV && g->Ci == 1 && g->Hi == 1 && g->Wi == 1 && g->pad_h == 0 && g->pad_w == 0 &&
+         g->dil_h == 1 && g->dil_w == 1 && g->Ho == g->KH && g->Wo == g->KW;
+}
+
 // Returns GLIS_E_UNSUPPORTED when the generic kernel should run instead.
 int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                         float* out, cudaStream_t st) {
-  const int M = g->N, N = g->Co, K = g->KH * g->KW * g->Ci;
+  int M = g->N, N = g->Co, K = g->KH * g->KW * g->Ci;
+  if (is_head_dgrad_geom(g)) { N = g->KH * g->KW * g->Co; K = 1; }
   if (M > 4096) return GLIS_E_UNSUPPORTED;
   const int nk = (K + LC_KC - 1) / LC_KC;
   const int gy = (M + LC_TM - 1) / LC_TM;

@@ -48,7 +48,9 @@ struct TcConvParams {
   int total_tiles;   // tiles_x * tiles_co * phases
   int cluster;       // CTAs per cluster (1, 2, 4): the pixel tiles of a cluster share ONE weight tile, each
                      // CTA fetches 128/cluster of its rows and multicasts them (tiles_x is padded to a multiple)
-  int n_groups;      // total_tiles / cluster
+  int n_groups;      // total_tiles / cluster (x ksplit)
+  int ksplit;        // K (the 64-channel blocks of every tap) split across `ksplit` work items per tile; their
+                     // partial sums are added into a zero-filled fp32 output (plain-output launches only)
   const float* bias; int act; const float* act_a; const float* act_b;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int ep_mode;       // compile-time specialised epilogue (0 = generic)
@@ -112,12 +114,17 @@ __device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int n
 struct TcTile {
   TcPhase ph;
   int qy0, n0, co0, ntaps, ksteps;
+  int kb_beg, kb_end, split;   // this work item's share of the 64-channel blocks
   bool empty;   // nothing to contract (uniform over the tiles of a cluster)
   bool ghost;   // padding tile: takes part in loads and MMAs (zero pixels), stores nothing
 };
 
-__device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int id) {
+__device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int item) {
   TcTile t;
+  const int id = item / P.ksplit;
+  t.split = item - id * P.ksplit;
+  t.kb_beg = (int)((long long)P.kblocks * t.split / P.ksplit);
+  t.kb_end = (int)((long long)P.kblocks * (t.split + 1) / P.ksplit);
   const int per_phase = P.tiles_x * P.tiles_co;
   const int z = id / per_phase, rem = id - z * per_phase;
   const int y = rem / P.tiles_x, x = rem - y * P.tiles_x;
@@ -127,7 +134,7 @@ __device__ __forceinline__ TcTile tc_tile(const TcConvParams& P, int id) {
   t.n0 = tile_n * P.tn;
   t.co0 = y * TC_BM;
   t.ntaps = t.ph.nth * t.ph.ntw;
-  t.ksteps = t.ntaps * P.kblocks;
+  t.ksteps = t.ntaps * (t.kb_end - t.kb_beg);
   t.empty = t.ph.Hq <= 0 || t.ph.Wq <= 0 || t.ksteps == 0;
   t.ghost = t.qy0 >= t.ph.Hq || t.n0 >= P.g.N;
   return t;
@@ -219,7 +226,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             c3 = tl.qy0 + (tl.ph.ry + g.pad_h - kh) / g.stride_h;
           }
           const int tap = kh * g.KW + kw;
-          for (int kb = 0; kb < P.kblocks; ++kb) {
+          for (int kb = tl.kb_beg; kb < tl.kb_end; ++kb) {
             mbar_wait(&empty_bar[s], parity ^ 1);
             if (P.trace && blockIdx.x == 0 && tr_n < 512) P.trace[tr_n++] = global_timer_ns();
             uint8_t* st = base + (size_t)s * stage_bytes;
@@ -314,7 +321,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       const bool ch_ok = co < g.Co && !(P.debug & 1) && !tl.ghost;
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
-        if (P.bias) bias = __ldg(P.bias + co);
+        if (P.bias && tl.split == 0) bias = __ldg(P.bias + co);
         if (P.act == GLIS_ACT_TPRELU) { ta = fminf(fmaxf(__ldg(P.act_a + co), 0.f), 1.f); tb = __ldg(P.act_b + co); }
       }
       const int oy0 = g.relation == GLIS_TCONV ? tl.qy0 * sh + tl.ph.ry : tl.qy0;
@@ -340,6 +347,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 6: {   // split K: add this item's partial sums (one 128-byte reduction per warp and column)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) atomicAdd(P.out_f32 + base + rc[j], __uint_as_float(v[j]) + bias);
+            break;
+          }
           default: {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -491,18 +504,36 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   }
   P.tw = Wq;
+  const int kblocks = (g->Ci + TC_BK - 1) / TC_BK;
+  const bool plain_out = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
+  int ksplit_max = 8;
   {
+    const char* e = getenv("GLIS_TC_KSPLIT");   // tuning knob: upper bound on the K split (1 = off)
+    if (e) ksplit_max = atoi(e);
+    if (ksplit_max < 1) ksplit_max = 1;
+  }
+  int best_ks = 1;
+  {
+    // cost ~ waves x (k-steps per item + fixed prologue / epilogue, ~4 k-steps) x shared-memory bytes per
+    // k-step (n + 128 rows); splitting K pays one extra pass of reductions over the output and a memset
     long best_cost = -1;
     int best_th = 1, best_tn = 1;
+    const int ntaps_max = g->relation == GLIS_CONV ? g->KH * g->KW
+                          : ((g->KH + g->stride_h - 1) / g->stride_h) * ((g->KW + g->stride_w - 1) / g->stride_w);
     auto consider = [&](int th, int tn) {
       const int n = round_up(Wq * th * tn, 16);
       if (n > NMAX || n > 256) return;
       const long tiles_x = ((long)((Hq + th - 1) / th) * ((g->N + tn - 1) / tn) + cs - 1) / cs * cs;
       const long tiles = tiles_x * co_tiles * nphase;
       const long slots = num_sms / cs * cs;
-      const long waves = (tiles + slots - 1) / slots;
-      const long cost = waves * (n + 128 / cs) * 1024 + n;   // tie-break: smaller tiles
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; best_tn = tn; }
+      for (int ks = 1; ks <= ksplit_max && ks <= kblocks; ks *= 2) {
+        if (ks > 1 && (!plain_out || cs > 1 || kblocks % ks != 0)) break;
+        const long waves = (tiles * ks + slots - 1) / slots;
+        const long steps = (long)ntaps_max * (kblocks / ks) + 4;
+        long cost = waves * steps * (n + 128 / cs) + (ks > 1 ? waves * 2 * n + 1024 : 0);
+        cost = cost * 1024 + n;   // tie-break: smaller tiles
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; best_tn = tn; best_ks = ks; }
+      }
     };
     for (int th = 1; th <= Hq && Wq * th <= 256; ++th) consider(th, 1);
     for (int tn = 2; tn <= g->N && Wq * Hq * tn <= 256; ++tn) consider(Hq, tn);
@@ -521,7 +552,8 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.tiles_co = (g->Co + TC_BM - 1) / TC_BM;
   P.total_tiles = P.tiles_x * P.tiles_co * nphase;
   P.cluster = cs;
-  P.n_groups = P.total_tiles / cs;
+  P.ksplit = best_ks;
+  P.n_groups = P.total_tiles / cs * best_ks;
   const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
   int stages = (int)((219 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -535,6 +567,11 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   else if (ep->act == GLIS_ACT_NONE && !ep->preact && !out_f32 && out_hi) P.ep_mode = 3;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && !out_hi) P.ep_mode = 4;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && out_hi) P.ep_mode = 5;
+  if (best_ks > 1) {
+    P.ep_mode = 6;
+    cudaError_t me = cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)g->N * g->Ho * g->Wo * g->Co, st);
+    GLIS_REQUIRE(me == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16: memset failed: %s", cudaGetErrorString(me));
+  }
   {
     const char* dbg = getenv("GLIS_TC_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;

@@ -213,6 +213,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
             }
           }
         }
+      } else if (T == 1 && (Cb & 3) == 0) {
+        // 1x1: consecutive columns are consecutive addresses of a master row (16-byte aligned: Cb % 4 == 0)
+        for (int cb = 0; cb < n_cols; cb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)cb, v);
+          tmem_ld_wait();
+          if (st_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int b = b0 + cb + j;
+              if (b < Cb)
+                red_add_v4(row + b, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                           __uint_as_float(v[j + 3]));
+            }
+          }
+        }
       } else {
         for (int cb = 0; cb < n_cols; cb += 32) {
           uint32_t v[32];

@@ -43,7 +43,12 @@ def main():
         for cl in (sys.argv[1:] or ["1", "2", "4"]):
             dbg = "0"
             os.environ["GLIS_TC_DEBUG"] = dbg
-            os.environ["GLIS_TC_CLUSTER"] = cl
+            if cl.startswith("k"):      # "k1", "k8": upper bound on the K split, no cluster
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ["GLIS_TC_KSPLIT"] = cl[1:]
+            else:
+                os.environ["GLIS_TC_CLUSTER"] = cl
+                os.environ["GLIS_TC_KSPLIT"] = "1"
             for prec in (L.PREC_BF16X3,):
                 def run():
                     L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xh), L.ptr16(xl), L.ptr16(wh), L.ptr16(wl),
@@ -73,6 +78,7 @@ def main():
         print("%-28s %5.2f GFLOP | %s" % (name, flop / 1e9, "  ".join(res)))
     os.environ["GLIS_TC_DEBUG"] = "0"
     os.environ.pop("GLIS_TC_CLUSTER", None)
+    os.environ.pop("GLIS_TC_KSPLIT", None)
 
 
 if __name__ == "__main__":
