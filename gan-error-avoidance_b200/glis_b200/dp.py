@@ -135,8 +135,14 @@ class OverlappedGradSync(object):
     def _send(self, st, b):
         off, n = st["buckets"][b]
         ready = torch.cuda.Event()
-        ready.record()                      # gradients of this bucket are complete on the main stream
+        ready.record()                      # gradients of this bucket are complete on the current stream ...
         self.side.wait_event(ready)
+        from . import ops                   # ... and on the other one of (main, weight-gradient side stream)
+        for other in (ops.Overlap.main_stream(), ops.Overlap.side_stream()):
+            if other is not None and other != torch.cuda.current_stream():
+                ev = torch.cuda.Event()
+                ev.record(other)
+                self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
             dist.all_reduce(st["flat"].g[off:off + n], op=dist.ReduceOp.SUM, group=self.group)
         st["sent"][b] = True

@@ -7,6 +7,7 @@ boundary as fp32 CUDA tensors; 4-D tensors are handled in NHWC memory order
 ``(N, C, H, W)`` shape — what the reference API promises — untouched.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -462,6 +463,66 @@ def _touch_hooks(*params):
             hook(p)
 
 
+class Overlap(object):
+    """Weight-gradient work (wgrad kernel + weight-norm projection) on a SIDE stream.
+
+    Nothing reads a parameter gradient before the optimizer, while the data-gradient chain is the
+    critical path of backward and is made of many short kernels that leave most SMs idle: between
+    ``Overlap.begin()`` and ``Overlap.join()`` (the trainer brackets its backward passes with them)
+    every layer forks its weight gradient onto one side stream behind an event, so it fills the
+    machine under the data-gradient / TPReLU-backward kernels.  Stream-ordered only, hence
+    capturable into the step's CUDA graph (fork/join inside the capture).  Tensors the side stream
+    reads are kept alive until the join."""
+
+    enabled = os.environ.get("GLIS_OVERLAP_WGRAD", "1") != "0"
+    _on = False
+    _side = None
+    _main = None
+    _dirty = False
+    _keep = []
+
+    @classmethod
+    def active(cls):
+        return cls._on
+
+    @classmethod
+    def side_stream(cls):
+        return cls._side if cls._on else None
+
+    @classmethod
+    def main_stream(cls):
+        return cls._main if cls._on else None
+
+    @classmethod
+    def begin(cls):
+        if not cls.enabled or not torch.cuda.is_available():
+            return
+        if cls._side is None:
+            cls._side = torch.cuda.Stream()
+        cls._main = torch.cuda.current_stream()
+        cls._on, cls._dirty = True, False
+
+    @classmethod
+    def run(cls, fn, keep=()):
+        ready = torch.cuda.Event()
+        ready.record(cls._main)               # everything the side work reads has been enqueued
+        cls._side.wait_event(ready)
+        with torch.cuda.stream(cls._side):
+            fn()
+        cls._keep.append(keep)
+        cls._dirty = True
+
+    @classmethod
+    def join(cls):
+        """The main stream waits for the side stream; call before anything reads a parameter gradient."""
+        if not cls._on:
+            return
+        if cls._dirty:
+            cls._main.wait_stream(cls._side)
+        cls._keep = []
+        cls._on, cls._dirty = False, False
+
+
 class PlanesOnly(object):
     """Stand-in for a gradient that exists ONLY as bf16 hi/lo planes (every consumer of the layer's
     output gradient runs on tensor cores, so the fp32 copy is never written)."""
@@ -525,12 +586,6 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
     else:
         n, h, w, ho, wo = xc.shape[0], 1, 1, 1, 1
 
-    dx = None
-    if need_dx:
-        # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
-        rel = L.CONV if spec.transposed else L.TCONV
-        dx, _, _ = launch(spec, rel, dyc, tuple(xc.shape), pw, forward_pack=False)
-
     dw = dscale = dbias = None
     if need_dw or need_dscale:
         graw = _take_scratch(weight)
@@ -542,42 +597,65 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
             small, big = dyc, xc
         tag = "conv_wgrad M=%d N=%d K=%d" % (g.Co, g.Ci * t, n * g.Ho * g.Wo)
         isw = _image_side_wgrad(spec, tuple(xc.shape), tuple(dyc.shape)) if xc.dim() == 4 else None
+        use_tc_w = isw is None and prec != L.PREC_FP32 and xc.dim() == 4 and \
+            bool(L.load().glis_wgrad_tc_supported(C.byref(g)))
+        # operands of the weight gradient are produced on the main stream (planes may need a split /
+        # unfold kernel) — before the fork, so that the data-gradient launch shares them
+        sp = bp = None
         if isw is not None:
-            n_, hs, ws, ca, c_img = isw
-            g1 = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
             sp, bp = planes_of(small, lo), unfolded_planes(big, lo)
-            with L.timed(tag + " tc (image side)"):
-                L.call("glis_conv_wgrad_bf16", C.byref(g1), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
-                       L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
-        elif prec != L.PREC_FP32 and xc.dim() == 4 and L.load().glis_wgrad_tc_supported(C.byref(g)):
+        elif use_tc_w:
             sp, bp = planes_of(small, lo), planes_of(big, lo)
-            with L.timed(tag + " tc"):
-                L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
-                       L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
-        else:
-            with L.timed(tag + " fp32"):
-                L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
-                       L.stream())
-        # Parameters owned by a FlatParams buffer carry a dense `.grad`: add into it in place and
-        # hand autograd nothing to accumulate (one kernel less per parameter); otherwise return it.
         direct_w = _dense_grad(weight)
         direct_s = _dense_grad(scale) if scale is not None else None
-        if direct_w is not None and (scale is None or direct_s is not None):
+        pw.need_fp32(False, False)  # the norm
+        wc = weight.detach().contiguous()
+        sc = None if scale is None else scale.detach().contiguous()
+        # Parameters owned by a FlatParams buffer carry a dense `.grad`: add into it in place and
+        # hand autograd nothing to accumulate (one kernel less per parameter); otherwise return it.
+        in_place = direct_w is not None and (scale is None or direct_s is not None)
+        fork = Overlap.active() and in_place     # results nobody reads before the optimizer: side stream
+        if in_place:
             dw_buf, ds_buf, acc = direct_w, direct_s, 1
         else:
             dw_buf = torch.empty_like(graw)
             ds_buf = torch.empty(cout, device=dw_buf.device, dtype=torch.float32) if scale is not None else None
             acc = 0
-        pw.need_fp32(False, False)  # the norm
-        wc = weight.detach().contiguous()
-        sc = None if scale is None else scale.detach().contiguous()
-        L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, cout, cin, t,
-               spec.norm_factor, L.ptr(dw_buf), L.ptr(ds_buf), acc, L.stream())
-        if acc:
-            _touch_hooks(weight, scale)
+
+        def weight_gradient():
+            if isw is not None:
+                n_, hs, ws, ca, c_img = isw
+                g1 = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
+                with L.timed(tag + " tc (image side)"):
+                    L.call("glis_conv_wgrad_bf16", C.byref(g1), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
+                           L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
+            elif use_tc_w:
+                with L.timed(tag + " tc"):
+                    L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
+                           L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
+            else:
+                with L.timed(tag + " fp32"):
+                    L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
+                           L.stream())
+            L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, cout, cin, t,
+                   spec.norm_factor, L.ptr(dw_buf), L.ptr(ds_buf), acc, L.stream())
+            if acc:
+                _touch_hooks(weight, scale)
+
+        if fork:
+            Overlap.run(weight_gradient, keep=(small, big, sp, bp, wc, sc, graw))
         else:
+            weight_gradient()
+        if not acc:
             dw = dw_buf
             dscale = None if ds_buf is None else ds_buf.view_as(scale)
+
+    dx = None
+    if need_dx:
+        # conv layer: dx gathers dy through the transposed relation; transposed layer: the direct one
+        rel = L.CONV if spec.transposed else L.TCONV
+        dx, _, _ = launch(spec, rel, dyc, tuple(xc.shape), pw, forward_pack=False)
+
     if need_dbias:
         direct_b = _dense_grad(pw_bias) if pw_bias is not None else None
         if direct_b is not None:

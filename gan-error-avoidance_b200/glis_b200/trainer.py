@@ -157,7 +157,9 @@ class GLISTrainer(object):
         both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
         loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
         self._sync_begin("dis")
+        ops.Overlap.begin()
         (loss_d_real + loss_d_fake).backward()
+        ops.Overlap.join()
         self.dis_flat.rebind_grads()
         gs = self._sync_done("dis", self.dis_flat)
         self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
@@ -175,7 +177,9 @@ class GLISTrainer(object):
                 loss_r.append(l.detach())
                 total = total + l
         self._sync_begin("gen")
+        ops.Overlap.begin()
         total.backward()
+        ops.Overlap.join()
         self.gen_flat.rebind_grads()
         gs = self._sync_done("gen", self.gen_flat)
         self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
