@@ -87,8 +87,10 @@ def bump_param_epoch():
 
 class PackedWeights(object):
     """Everything derived from one WN layer's (weight, scale) by ``glis_wn_prepare*``: the
-    per-channel norm and the fp32 / split-bf16 GEMM-order packs.  Built lazily per kind and
-    cached on the weight Parameter until the parameters change (once per optimizer step)."""
+    per-channel norm and the fp32 / split-bf16 GEMM-order packs.  One persistent object (and one
+    set of buffers) per weight Parameter: a kind is (re)built in place when it is asked for and
+    not ``fresh`` — lazily at first use, or ahead of time by ``refresh_packs`` right after the
+    optimizer step.  ``packed_weights`` clears ``fresh`` whenever the parameters changed."""
 
     def __init__(self, weight, scale, spec):
         self.weight, self.scale, self.spec = weight, scale, spec
@@ -99,15 +101,17 @@ class PackedWeights(object):
         self.io = self.oi = None            # fp32 [T][Cin][Cout], [T][Cout][Cin]
         self.fwd = self.bwd = None          # bf16 (hi, lo): [T][Cout][Cin], [T][Cin][Cout]
         self.mat = self.mat_t = None        # bf16 (hi, lo): E [A][J] and E^T [J][A] (image-side layers)
+        self.fresh = set()                  # kinds valid for the current parameter values
+
+    def invalidate(self):
+        self.fresh.clear()
 
     def _w(self):
         w = self.weight.detach().contiguous()
         sc = None if self.scale is None else self.scale.detach().contiguous()
         return w, sc
 
-    def need_fp32(self, io, oi):
-        # a layer that needs one fp32 pack this step needs the other one in its backward: build both
-        # on the first request (one launch pair instead of two) once backward has been seen to want it
+    def wanted(self):
         wanted = getattr(self.weight, "_glis_wanted", None)
         if wanted is None:
             wanted = set()
@@ -115,42 +119,45 @@ class PackedWeights(object):
                 self.weight._glis_wanted = wanted
             except AttributeError:
                 pass
+        return wanted
+
+    def need_fp32(self, io, oi):
+        # a layer that needs one fp32 pack this step needs the other one in its backward: build both
+        # on the first request (one launch pair instead of two) once backward has been seen to want it
+        wanted = self.wanted()
         if io:
             wanted.add("io")
         if oi:
             wanted.add("oi")
-        io = (io or "io" in wanted) and self.io is None
-        oi = (oi or "oi" in wanted) and self.oi is None
-        if not (io or oi) and self.norm is not None:
+        io = (io or "io" in wanted) and "io" not in self.fresh
+        oi = (oi or "oi" in wanted) and "oi" not in self.fresh
+        if not (io or oi) and "norm" in self.fresh:
             return
         w, sc = self._w()
         dev = w.device
         if self.norm is None:
             self.norm = torch.empty(self.cout, device=dev, dtype=torch.float32)
-        a = torch.empty(self.t, self.cin, self.cout, device=dev, dtype=torch.float32) if io else None
-        b = torch.empty(self.t, self.cout, self.cin, device=dev, dtype=torch.float32) if oi else None
+        if io and self.io is None:
+            self.io = torch.empty(self.t, self.cin, self.cout, device=dev, dtype=torch.float32)
+        if oi and self.oi is None:
+            self.oi = torch.empty(self.t, self.cout, self.cin, device=dev, dtype=torch.float32)
         L.call("glis_wn_prepare", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
-               self.spec.norm_factor, L.ptr(self.norm), L.ptr(a), L.ptr(b), L.stream(),
-               kernels=2 if (io or oi) else 1)
+               self.spec.norm_factor, L.ptr(self.norm), L.ptr(self.io if io else None),
+               L.ptr(self.oi if oi else None), L.stream(), kernels=2 if (io or oi) else 1)
+        self.fresh.add("norm")
         if io:
-            self.io = a
+            self.fresh.add("io")
         if oi:
-            self.oi = b
+            self.fresh.add("oi")
 
     def need_bf16(self, fwd, bwd, lo):
-        wanted = getattr(self.weight, "_glis_wanted", None)
-        if wanted is None:
-            wanted = set()
-            try:
-                self.weight._glis_wanted = wanted
-            except AttributeError:
-                pass
+        wanted = self.wanted()
         if fwd:
             wanted.add("fwd")
         if bwd:
             wanted.add("bwd")
-        fwd = (fwd or "fwd" in wanted) and self.fwd is None
-        bwd = (bwd or "bwd" in wanted) and self.bwd is None
+        fwd = (fwd or "fwd" in wanted) and "fwd" not in self.fresh
+        bwd = (bwd or "bwd" in wanted) and "bwd" not in self.fresh
         if not (fwd or bwd):
             return
         w, sc = self._w()
@@ -158,51 +165,139 @@ class PackedWeights(object):
         if self.norm is None:
             self.norm = torch.empty(self.cout, device=dev, dtype=torch.float32)
 
-        def plane(shape, want):
-            return torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
+        def planes(old, shape):
+            hi = old[0] if old is not None else torch.empty(shape, device=dev, dtype=torch.bfloat16)
+            lo_t = old[1] if old is not None else None
+            if lo and lo_t is None:
+                lo_t = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+            return hi, lo_t
 
-        fh, fl = plane((self.t, self.cout, self.cin), fwd), plane((self.t, self.cout, self.cin), fwd and lo)
-        bh, bl = plane((self.t, self.cin, self.cout), bwd), plane((self.t, self.cin, self.cout), bwd and lo)
-        L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
-               self.spec.norm_factor, L.ptr(self.norm), L.ptr16(fh), L.ptr16(fl), L.ptr16(bh), L.ptr16(bl),
-               L.stream(), kernels=2)
         if fwd:
-            self.fwd = (fh, fl)
+            self.fwd = planes(self.fwd, (self.t, self.cout, self.cin))
         if bwd:
-            self.bwd = (bh, bl)
+            self.bwd = planes(self.bwd, (self.t, self.cin, self.cout))
+        fh, fl = self.fwd if fwd else (None, None)
+        bh, bl = self.bwd if bwd else (None, None)
+        L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
+               self.spec.norm_factor, L.ptr(self.norm), L.ptr16(fh), L.ptr16(fl if lo else None), L.ptr16(bh),
+               L.ptr16(bl if lo else None), L.stream(), kernels=2)
+        self.fresh.add("norm")
+        if fwd:
+            self.fresh.add("fwd")
+        if bwd:
+            self.fresh.add("bwd")
+
+    def refresh(self):
+        """Rebuild, in place, every kind this layer has ever been asked for."""
+        wanted = self.wanted()
+        lo = self.spec.precision == L.PREC_BF16X3
+        if "fwd" in wanted or "bwd" in wanted:
+            self.need_bf16(False, False, lo)
+        if "io" in wanted or "oi" in wanted or "norm" not in self.fresh:
+            self.need_fp32(False, False)
+        if "mat" in wanted:
+            _need_matrix(self, lo)
 
 
 def _need_matrix(pw, lo):
     """E / E^T packs of an image-side layer (csrc/image_side.cu): one norm + one pack launch."""
-    if pw.mat is not None:
+    pw.wanted().add("mat")
+    if "mat" in pw.fresh:
         return
     w, sc = pw._w()
     dev = w.device
-    had_norm = pw.norm is not None
-    if not had_norm:
+    if "norm" not in pw.fresh:
         pw.need_fp32(False, False)          # the norm alone
     a = w.shape[0]
     j = w.numel() // a
-    mk = lambda shape, want: torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
-    eh, el = mk((a, j), True), mk((a, j), lo)
-    th, tl = mk((j, a), True), mk((j, a), lo)
+    if pw.mat is None:
+        mk = lambda shape, want: torch.empty(shape, device=dev, dtype=torch.bfloat16) if want else None
+        pw.mat, pw.mat_t = (mk((a, j), True), mk((a, j), lo)), (mk((j, a), True), mk((j, a), lo))
+    elif lo and pw.mat[1] is None:
+        pw.mat = (pw.mat[0], torch.empty_like(pw.mat[0]))
+        pw.mat_t = (pw.mat_t[0], torch.empty_like(pw.mat_t[0]))
+    (eh, el), (th, tl) = pw.mat, pw.mat_t
     L.call("glis_wn_pack_matrix_bf16", L.ptr(w), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, a, j, pw.t,
-           L.ptr16(eh), L.ptr16(el), L.ptr16(th), L.ptr16(tl), L.stream())
-    pw.mat, pw.mat_t = (eh, el), (th, tl)
+           L.ptr16(eh), L.ptr16(el if lo else None), L.ptr16(th), L.ptr16(tl if lo else None), L.stream())
+    pw.fresh.add("mat")
+
+
+def _pack_key(weight, scale, spec):
+    return (PARAM_EPOCH[0], getattr(weight, "_glis_epoch", 0), weight.data_ptr(), weight._version,
+            None if scale is None else scale._version, spec.precision, spec.transposed, spec.stride)
 
 
 def packed_weights(weight, scale, spec):
-    key = (PARAM_EPOCH[0], getattr(weight, "_glis_epoch", 0), weight.data_ptr(), weight._version,
-           None if scale is None else scale._version, spec.precision, spec.transposed, spec.stride)
+    holder = getattr(weight, "_glis_pack_wait", None)
+    if holder is not None and holder[0] is not None:
+        # packs of this network are being refreshed on the side stream (refresh_packs): first use waits
+        torch.cuda.current_stream().wait_event(holder[0])
+        holder[0] = None
+    key = _pack_key(weight, scale, spec)
     cached = getattr(weight, "_glis_packed", None)
     if cached is not None and cached[0] == key:
         return cached[1]
-    pw = PackedWeights(weight, scale, spec)
+    if cached is not None and cached[0][2] == key[2] and cached[0][5:] == key[5:] and cached[1].scale is scale:
+        pw = cached[1]          # same storage and layer structure, new parameter values: rebuild in place
+        pw.invalidate()
+    else:
+        pw = PackedWeights(weight, scale, spec)
     try:
         weight._glis_packed = (key, pw)
     except AttributeError:
         pass
     return pw
+
+
+def refresh_packs(flat, side=True):
+    """Rebuild the weight packs of every layer of ``flat`` (a trainer.FlatParams) for its CURRENT
+    parameter values — called right after the optimizer step.  With ``side`` the rebuild runs on the
+    side stream and the first later use of any of these packs waits for it, so it overlaps whatever
+    the main stream does next (the discriminator's packs rebuild under the generator's forward)."""
+    todo = []
+    for p in flat.params:
+        cached = getattr(p, "_glis_packed", None)
+        if cached is None:
+            continue
+        pw = cached[1]
+        key = _pack_key(p, pw.scale, pw.spec)
+        if cached[0] != key:
+            if cached[0][5] != key[5]:
+                continue        # precision switched since: rebuilt lazily as a new object
+            pw.invalidate()
+            p._glis_packed = (key, pw)
+        todo.append(pw)
+    if not todo:
+        return
+    use_side = side and Overlap.enabled and torch.cuda.is_available()
+    if not use_side:
+        for pw in todo:
+            pw.refresh()
+        return
+    holder = getattr(flat, "_pack_wait", None)
+    if holder is None:
+        holder = flat._pack_wait = [None]
+        for p in flat.params:
+            p._glis_pack_wait = holder
+    s = Overlap.stream()
+    main = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(main)
+    s.wait_event(ready)
+    with torch.cuda.stream(s):
+        for pw in todo:
+            pw.refresh()
+        done = torch.cuda.Event()
+        done.record(s)
+    holder[0] = done
+
+
+def join_pack_refresh(flat):
+    """Make the current stream wait for a pending side-stream refresh of ``flat``'s packs."""
+    holder = getattr(flat, "_pack_wait", None)
+    if holder is not None and holder[0] is not None:
+        torch.cuda.current_stream().wait_event(holder[0])
+        holder[0] = None
 
 
 def wn_prepare(weight, scale, spec, want_io=True, want_oi=True):
@@ -494,11 +589,16 @@ class Overlap(object):
         return cls._main if cls._on else None
 
     @classmethod
+    def stream(cls):
+        if cls._side is None:
+            cls._side = torch.cuda.Stream()
+        return cls._side
+
+    @classmethod
     def begin(cls):
         if not cls.enabled or not torch.cuda.is_available():
             return
-        if cls._side is None:
-            cls._side = torch.cuda.Stream()
+        cls.stream()
         cls._main = torch.cuda.current_stream()
         cls._on, cls._dirty = True, False
 

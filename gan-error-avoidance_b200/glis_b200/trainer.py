@@ -163,6 +163,8 @@ class GLISTrainer(object):
         self.dis_flat.rebind_grads()
         gs = self._sync_done("dis", self.dis_flat)
         self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+        # D's weight packs for its new parameters: rebuilt on the side stream under G's forward
+        ops.refresh_packs(self.dis_flat, side=True)
 
         # ---- G step
         self._set_dis_requires_grad(False)
@@ -183,6 +185,7 @@ class GLISTrainer(object):
         self.gen_flat.rebind_grads()
         gs = self._sync_done("gen", self.gen_flat)
         self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+        ops.refresh_packs(self.gen_flat, side=False)   # ready for the next iteration's first kernel
         self._set_dis_requires_grad(True)
 
         return {"d_real": loss_d_real.detach(), "d_fake": loss_d_fake.detach(), "g": loss_g.detach(),
@@ -228,9 +231,13 @@ class GraphedStep(object):
             f.p.copy_(p); f.g.copy_(g); f.v.copy_(v)
         if rng_state is not None:
             tr.gen.rng.setstate(rng_state)
-        # Every weight pack the step uses must be (re)built INSIDE the graph: a pack cached from the
-        # warm-up would be read at its capture-time address and go stale after the first replay.
+        # Weight packs live in persistent buffers and are rebuilt INSIDE the graph right after each
+        # optimizer step; the iteration therefore starts from packs that match the parameters: build
+        # them here for the restored parameters (eagerly, outside the capture).
         ops.bump_param_epoch()
+        ops.refresh_packs(tr.gen_flat, side=False)
+        ops.refresh_packs(tr.dis_flat, side=False)
+        torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, pool=self.pool):
             out = tr.step(self.real, self.z_d, self.z_g, depth_d, depth_g)
