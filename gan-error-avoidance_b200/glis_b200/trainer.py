@@ -110,6 +110,30 @@ def dis_bce(dis, x, targets):
     return [ops.bce_with_logits_const(logits[i * n:(i + 1) * n], t) for i, t in enumerate(targets)]
 
 
+def dis_logits(dis, x):
+    """Logits (N,) of a standard discriminator (common/model.py:56-62) — everything up to the Sigmoid —
+    or None when ``dis`` does not end in Sigmoid + View(1)."""
+    from common.model import run_layers
+    body = _split_head(dis)
+    if body is None:
+        return None
+    return run_layers(body, x).reshape(-1)
+
+
+def bce_on_logits(logits, targets):
+    """([mean BCE of chunk i against targets[i]], d(sum of those means)/d(logits)): one fused kernel
+    per chunk (sigmoid + BCE + gradient, g_lis/main.py:311,555,564,578); nothing for autograd to trace —
+    the caller starts backward from the logits with the returned gradient."""
+    lg = logits.detach()
+    n = lg.numel() // len(targets)
+    dl = torch.empty_like(lg)
+    losses = torch.empty(len(targets), device=lg.device, dtype=torch.float32)
+    for i, t in enumerate(targets):
+        ops.L.call("glis_bce_logits", ops.L.ptr(lg[i * n:(i + 1) * n]), float(t), n, 1.0, ops.L.ptr(losses[i:i + 1]),
+                   ops.L.ptr(dl[i * n:(i + 1) * n]), None, ops.L.stream())
+    return [losses[i] for i in range(len(targets))], dl
+
+
 class GLISTrainer(object):
     """One object per (G-LIS, D) pair; ``step`` = one reference training iteration."""
 
@@ -155,10 +179,15 @@ class GLISTrainer(object):
         with torch.no_grad():
             fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
         both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
-        loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
+        logits = dis_logits(dis, both)
         self._sync_begin("dis")
         ops.Overlap.begin()
-        (loss_d_real + loss_d_fake).backward()
+        if logits is not None:     # losses and d(loss)/d(logits) from one kernel per half; backward starts at the logits
+            (loss_d_real, loss_d_fake), dl = bce_on_logits(logits, [1.0, 0.0])
+            logits.backward(dl)
+        else:
+            loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
+            (loss_d_real + loss_d_fake).backward()
         ops.Overlap.join()
         self.dis_flat.rebind_grads()
         gs = self._sync_done("dis", self.dis_flat)
@@ -170,17 +199,32 @@ class GLISTrainer(object):
         self._set_dis_requires_grad(False)
         self.gen_flat.zero_grad()
         fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
-        (loss_g,) = dis_bce(dis, fake, [1.0])
-        total = loss_g
+        logits = dis_logits(dis, fake)
         loss_r = []
-        if self.lambda_r > 0:
-            for i, u in enumerate(lis_g):
-                l = F.mse_loss(u, z_g) * (self.lambda_r ** (i + 1))
-                loss_r.append(l.detach())
-                total = total + l
         self._sync_begin("gen")
         ops.Overlap.begin()
-        total.backward()
+        if logits is not None:
+            # roots of backward: the logits and every LIS output, each with its kernel-computed gradient
+            (loss_g,), dl = bce_on_logits(logits, [1.0])
+            roots, grads = [logits], [dl]
+            if self.lambda_r > 0:
+                zc = z_g.detach().contiguous()
+                for i, u in enumerate(lis_g):
+                    du = torch.empty_like(u, memory_format=torch.contiguous_format)
+                    l = ops.mse_scaled(u, zc, self.lambda_r ** (i + 1), du)
+                    loss_r.append(l.reshape(()))
+                    roots.append(u)
+                    grads.append(du)
+            torch.autograd.backward(roots, grads)
+        else:
+            (loss_g,) = dis_bce(dis, fake, [1.0])
+            total = loss_g
+            if self.lambda_r > 0:
+                for i, u in enumerate(lis_g):
+                    l = F.mse_loss(u, z_g) * (self.lambda_r ** (i + 1))
+                    loss_r.append(l.detach())
+                    total = total + l
+            total.backward()
         ops.Overlap.join()
         self.gen_flat.rebind_grads()
         gs = self._sync_done("gen", self.gen_flat)
