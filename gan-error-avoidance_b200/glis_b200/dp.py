@@ -112,7 +112,7 @@ class OverlappedGradSync(object):
             for i in members:
                 owner[i] = b
         st = {"flat": flat, "buckets": buckets, "owner": owner, "need": [len(m) for _, _, m in plan],
-              "left": [0] * len(buckets), "sent": [False] * len(buckets), "armed": False}
+              "left": [0] * len(buckets), "sent": [False] * len(buckets), "armed": False, "seen": set()}
         self.sets[tag] = st
         for idx, p in enumerate(flat.params):
             hook = self._make_hook(st, idx)
@@ -126,6 +126,13 @@ class OverlappedGradSync(object):
         def hook(_param):
             if not st["armed"] or self.world <= 1:
                 return
+            # A parameter reports ONCE per backward pass.  It may be announced twice — by the operator
+            # that added its gradient in place (ops._touch_hooks) and again by autograd, which runs the
+            # post-accumulate hooks of every parameter input of a Function even when the Function
+            # returned None for it — and either call comes after the gradient work was enqueued.
+            if idx in st["seen"]:
+                return
+            st["seen"].add(idx)
             b = st["owner"][idx]
             st["left"][b] -= 1
             if st["left"][b] == 0 and not st["sent"][b]:
@@ -153,6 +160,7 @@ class OverlappedGradSync(object):
         st = self.sets[tag]
         st["left"] = list(st["need"])
         st["sent"] = [False] * len(st["buckets"])
+        st["seen"] = set()
         st["armed"] = True
 
     def finish(self, tag):
