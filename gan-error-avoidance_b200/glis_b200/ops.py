@@ -102,6 +102,7 @@ class PackedWeights(object):
         self.fwd = self.bwd = None          # bf16 (hi, lo): [T][Cout][Cin], [T][Cin][Cout]
         self.mat = self.mat_t = None        # bf16 (hi, lo): E [A][J] and E^T [J][A] (image-side layers)
         self.fresh = set()                  # kinds valid for the current parameter values
+        self.pending = None                 # (event, kinds) of a rebuild in flight on the side stream
 
     def invalidate(self):
         self.fresh.clear()
@@ -121,6 +122,12 @@ class PackedWeights(object):
                 pass
         return wanted
 
+    def _wait(self, kinds):
+        """Kinds being rebuilt on the side stream (refresh_packs): the first use waits for that stream."""
+        if self.pending is not None and (self.pending[1] & set(kinds)):
+            torch.cuda.current_stream().wait_event(self.pending[0])
+            self.pending = None
+
     def need_fp32(self, io, oi):
         # a layer that needs one fp32 pack this step needs the other one in its backward: build both
         # on the first request (one launch pair instead of two) once backward has been seen to want it
@@ -129,10 +136,14 @@ class PackedWeights(object):
             wanted.add("io")
         if oi:
             wanted.add("oi")
+        self._wait(("norm",) + (("io",) if io else ()) + (("oi",) if oi else ()))
         io = (io or "io" in wanted) and "io" not in self.fresh
         oi = (oi or "oi" in wanted) and "oi" not in self.fresh
         if not (io or oi) and "norm" in self.fresh:
             return
+        self._build_fp32(io, oi)
+
+    def _build_fp32(self, io, oi):
         w, sc = self._w()
         dev = w.device
         if self.norm is None:
@@ -156,10 +167,14 @@ class PackedWeights(object):
             wanted.add("fwd")
         if bwd:
             wanted.add("bwd")
+        self._wait((("fwd",) if fwd else ()) + (("bwd",) if bwd else ()))
         fwd = (fwd or "fwd" in wanted) and "fwd" not in self.fresh
         bwd = (bwd or "bwd" in wanted) and "bwd" not in self.fresh
         if not (fwd or bwd):
             return
+        self._build_bf16(fwd, bwd, lo)
+
+    def _build_bf16(self, fwd, bwd, lo):
         w, sc = self._w()
         dev = w.device
         if self.norm is None:
@@ -187,21 +202,31 @@ class PackedWeights(object):
         if bwd:
             self.fresh.add("bwd")
 
-    def refresh(self):
-        """Rebuild, in place, every kind this layer has ever been asked for."""
+    FORWARD_KINDS, BACKWARD_KINDS = ("fwd", "io", "mat", "norm"), ("bwd", "oi")
+
+    def refresh(self, part="all"):
+        """Rebuild, in place, the kinds this layer has ever been asked for and that are stale:
+        ``part`` = "forward" (what forward launches read), "backward" (what data-gradient launches
+        read) or "all"."""
         wanted = self.wanted()
         lo = self.spec.precision == L.PREC_BF16X3
-        if "fwd" in wanted or "bwd" in wanted:
-            self.need_bf16(False, False, lo)
-        if "io" in wanted or "oi" in wanted or "norm" not in self.fresh:
-            self.need_fp32(False, False)
-        if "mat" in wanted:
+        f, b = part in ("all", "forward"), part in ("all", "backward")
+        fwd = f and "fwd" in wanted and "fwd" not in self.fresh
+        bwd = b and "bwd" in wanted and "bwd" not in self.fresh
+        if fwd or bwd:
+            self._build_bf16(fwd, bwd, lo)
+        io = f and "io" in wanted and "io" not in self.fresh
+        oi = b and "oi" in wanted and "oi" not in self.fresh
+        if io or oi or (f and "norm" not in self.fresh):
+            self._build_fp32(io, oi)
+        if f and "mat" in wanted:
             _need_matrix(self, lo)
 
 
 def _need_matrix(pw, lo):
     """E / E^T packs of an image-side layer (csrc/image_side.cu): one norm + one pack launch."""
     pw.wanted().add("mat")
+    pw._wait(("mat", "norm"))
     if "mat" in pw.fresh:
         return
     w, sc = pw._w()
@@ -228,11 +253,6 @@ def _pack_key(weight, scale, spec):
 
 
 def packed_weights(weight, scale, spec):
-    holder = getattr(weight, "_glis_pack_wait", None)
-    if holder is not None and holder[0] is not None:
-        # packs of this network are being refreshed on the side stream (refresh_packs): first use waits
-        torch.cuda.current_stream().wait_event(holder[0])
-        holder[0] = None
     key = _pack_key(weight, scale, spec)
     cached = getattr(weight, "_glis_packed", None)
     if cached is not None and cached[0] == key:
@@ -249,11 +269,12 @@ def packed_weights(weight, scale, spec):
     return pw
 
 
-def refresh_packs(flat, side=True):
-    """Rebuild the weight packs of every layer of ``flat`` (a trainer.FlatParams) for its CURRENT
-    parameter values — called right after the optimizer step.  With ``side`` the rebuild runs on the
-    side stream and the first later use of any of these packs waits for it, so it overlaps whatever
-    the main stream does next (the discriminator's packs rebuild under the generator's forward)."""
+def refresh_packs(flat, part="all", side=True):
+    """Rebuild the stale weight packs of every layer of ``flat`` (a trainer.FlatParams) for its CURRENT
+    parameter values.  ``part``: "forward" / "backward" / "all" kinds (PackedWeights.refresh).  With
+    ``side`` the rebuild runs on the side stream and the first later use of one of those kinds waits
+    for it, so it overlaps whatever the main stream does next: the discriminator's packs rebuild
+    under the generator's forward, the generator's data-gradient packs under the whole D update."""
     todo = []
     for p in flat.params:
         cached = getattr(p, "_glis_packed", None)
@@ -272,32 +293,26 @@ def refresh_packs(flat, side=True):
     use_side = side and Overlap.enabled and torch.cuda.is_available()
     if not use_side:
         for pw in todo:
-            pw.refresh()
+            pw._wait(PackedWeights.FORWARD_KINDS + PackedWeights.BACKWARD_KINDS)
+            pw.refresh(part)
         return
-    holder = getattr(flat, "_pack_wait", None)
-    if holder is None:
-        holder = flat._pack_wait = [None]
-        for p in flat.params:
-            p._glis_pack_wait = holder
+    kinds = set(PackedWeights.FORWARD_KINDS if part in ("all", "forward") else ()) | \
+        set(PackedWeights.BACKWARD_KINDS if part in ("all", "backward") else ()) | {"norm"}
     s = Overlap.stream()
     main = torch.cuda.current_stream()
     ready = torch.cuda.Event()
     ready.record(main)
     s.wait_event(ready)
+    launches = L.launch_count
     with torch.cuda.stream(s):
         for pw in todo:
-            pw.refresh()
+            pw.refresh(part)
+        if L.launch_count == launches:
+            return              # everything was fresh: nothing enqueued, nothing to wait for
         done = torch.cuda.Event()
         done.record(s)
-    holder[0] = done
-
-
-def join_pack_refresh(flat):
-    """Make the current stream wait for a pending side-stream refresh of ``flat``'s packs."""
-    holder = getattr(flat, "_pack_wait", None)
-    if holder is not None and holder[0] is not None:
-        torch.cuda.current_stream().wait_event(holder[0])
-        holder[0] = None
+    for pw in todo:
+        pw.pending = (done, kinds)
 
 
 def wn_prepare(weight, scale, spec, want_io=True, want_oi=True):

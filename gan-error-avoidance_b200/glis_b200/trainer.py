@@ -171,6 +171,9 @@ class GLISTrainer(object):
         gen, dis = self.gen, self.dis
         B = real.shape[0]
 
+        # G's data-gradient packs are not needed before the G update's backward: rebuilt on the side stream
+        ops.refresh_packs(self.gen_flat, part="backward", side=True)
+
         # ---- D step: real and generated batches go through D as ONE batch of 2B images.  The two
         # BCE means are taken over their own halves, so the gradients are exactly the sum of the
         # reference's two backward passes (g_lis/main.py:555-565) at half the kernel launches.
@@ -193,7 +196,7 @@ class GLISTrainer(object):
         gs = self._sync_done("dis", self.dis_flat)
         self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
         # D's weight packs for its new parameters: rebuilt on the side stream under G's forward
-        ops.refresh_packs(self.dis_flat, side=True)
+        ops.refresh_packs(self.dis_flat, part="all", side=True)
 
         # ---- G step
         self._set_dis_requires_grad(False)
@@ -229,7 +232,7 @@ class GLISTrainer(object):
         self.gen_flat.rebind_grads()
         gs = self._sync_done("gen", self.gen_flat)
         self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
-        ops.refresh_packs(self.gen_flat, side=False)   # ready for the next iteration's first kernel
+        ops.refresh_packs(self.gen_flat, part="forward", side=False)   # ready for the next iteration's first kernel
         self._set_dis_requires_grad(True)
 
         return {"d_real": loss_d_real.detach(), "d_fake": loss_d_fake.detach(), "g": loss_g.detach(),
@@ -279,8 +282,9 @@ class GraphedStep(object):
         # optimizer step; the iteration therefore starts from packs that match the parameters: build
         # them here for the restored parameters (eagerly, outside the capture).
         ops.bump_param_epoch()
-        ops.refresh_packs(tr.gen_flat, side=False)
-        ops.refresh_packs(tr.dis_flat, side=False)
+        # (the iteration itself rebuilds G's data-gradient packs at its start: leave them stale)
+        ops.refresh_packs(tr.gen_flat, part="forward", side=False)
+        ops.refresh_packs(tr.dis_flat, part="all", side=False)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, pool=self.pool):
