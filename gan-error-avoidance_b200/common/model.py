@@ -31,7 +31,16 @@ def run_layers(layers, x):
         nxt = layers[i + 1] if i + 1 < len(layers) else None
         fusable = (isinstance(m, (_WeightNormalizedConvNd, WeightNormalizedLinear)) and isinstance(nxt, TPReLU)
                    and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() in (2, 4))
-        if fusable:
+        after = layers[i + 2] if i + 2 < len(layers) else None
+        # linear -> View(C, h, w) -> TPReLU(C): the generators' head, one kernel writing the map in NHWC
+        head = (isinstance(m, WeightNormalizedLinear) and isinstance(nxt, View) and isinstance(after, TPReLU)
+                and m.bias is None and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() == 2
+                and len(nxt.target_size) == 3 and after.weight.numel() == nxt.target_size[0]
+                and m.out_features == nxt.target_size[0] * nxt.target_size[1] * nxt.target_size[2])
+        if head:
+            x = ops.wn_linear_view_tprelu(x, m.weight, m.scale, after.weight, after.bias, nxt.target_size)
+            i += 3
+        elif fusable:
             spec = m._spec() if isinstance(m, _WeightNormalizedConvNd) else m._spec
             x = ops.wn_contraction_tprelu(x, m.weight, m.scale, m.bias, nxt.weight, nxt.bias, spec)
             i += 2

@@ -41,7 +41,7 @@ extern "C" int glis_conv_forward(const glis_geom_t* g, const float* in, const fl
   int rc = validate_geom(g, "glis_conv_forward");
   if (rc != GLIS_OK) return rc;
   GLIS_REQUIRE(in && wpack && out, GLIS_E_BADARG, "glis_conv_forward: NULL tensor pointer");
-  glis_epilogue_t none = {nullptr, GLIS_ACT_NONE, nullptr, nullptr, nullptr, nullptr, nullptr};
+  glis_epilogue_t none = {nullptr, GLIS_ACT_NONE, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   if (!ep) ep = &none;
   GLIS_REQUIRE(ep->act == GLIS_ACT_NONE || ep->act == GLIS_ACT_SIGMOID ||
                    (ep->act == GLIS_ACT_TPRELU && ep->act_a && ep->act_b),
@@ -85,7 +85,7 @@ extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, co
   GLIS_REQUIRE(precision == GLIS_PREC_BF16X3 || precision == GLIS_PREC_BF16, GLIS_E_BADARG,
                "glis_conv_forward_bf16: precision must be GLIS_PREC_BF16X3 or GLIS_PREC_BF16");
   GLIS_REQUIRE(out_f32 || out_hi, GLIS_E_BADARG, "glis_conv_forward_bf16: no output tensor");
-  glis_epilogue_t none = {nullptr, GLIS_ACT_NONE, nullptr, nullptr, nullptr, nullptr, nullptr};
+  glis_epilogue_t none = {nullptr, GLIS_ACT_NONE, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   if (!ep) ep = &none;
   GLIS_REQUIRE(ep->act == GLIS_ACT_NONE || ep->act == GLIS_ACT_SIGMOID ||
                    (ep->act == GLIS_ACT_TPRELU && ep->act_a && ep->act_b),

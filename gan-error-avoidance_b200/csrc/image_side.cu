@@ -36,7 +36,8 @@ unfold4x4s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, __nv
   for (int64_t i = (int64_t)blockIdx.x * IS_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * IS_NT) {
     const int kh = (int)(i & 3);
     const int64_t pix = i >> 2;
-    const int ox = (int)(pix % Wo); const int64_t t = pix / Wo; const int oy = (int)(t % Ho); const int n = (int)(t / Ho);
+    const int p32 = (int)pix;   // < 2^31 pixels (checked by the host): 32-bit divisions
+    const int ox = p32 % Wo; const int t = p32 / Wo; const int oy = t % Ho; const int n = t / Ho;
     const int iy = 2 * oy - 1 + kh;
     const bool row_ok = iy >= 0 && iy < H;
     const float* row = x + ((int64_t)n * H + (row_ok ? iy : 0)) * W * C;
@@ -63,7 +64,8 @@ fold4x4s2_kernel(const float* __restrict__ cols, int N, int Hi, int Wi, int C, c
   const int Ho = 2 * Hi, Wo = 2 * Wi, J = 16 * C;
   const int64_t total = (int64_t)N * Ho * Wo;
   for (int64_t pix = (int64_t)blockIdx.x * IS_NT + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * IS_NT) {
-    const int ox = (int)(pix % Wo); const int64_t t = pix / Wo; const int oy = (int)(t % Ho); const int n = (int)(t / Ho);
+    const int p32 = (int)pix;   // < 2^31 pixels (checked by the host): 32-bit divisions
+    const int ox = p32 % Wo; const int t = p32 / Wo; const int oy = t % Ho; const int n = t / Ho;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int kh0 = (oy + 1) & 1, kw0 = (ox + 1) & 1;
 #pragma unroll
@@ -118,6 +120,7 @@ extern "C" int glis_unfold4x4s2_bf16(const float* x, int N, int H, int W, int C,
   GLIS_REQUIRE(x && hi, GLIS_E_BADARG, "glis_unfold4x4s2_bf16: NULL pointer");
   GLIS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0, GLIS_E_BADARG,
                "glis_unfold4x4s2_bf16: bad shape (N=%d H=%d W=%d C=%d)", N, H, W, C);
+  GLIS_REQUIRE((int64_t)N * H * W < ((int64_t)1 << 31), GLIS_E_UNSUPPORTED, "glis_unfold4x4s2_bf16: more than 2^31 pixels");
   unfold4x4s2_kernel<<<is_blocks((int64_t)N * (H / 2) * (W / 2) * 4), IS_NT, 0, (cudaStream_t)stream>>>(
       x, N, H, W, C, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   GLIS_CHECK_LAUNCH("glis_unfold4x4s2_bf16");
@@ -128,6 +131,7 @@ extern "C" int glis_fold4x4s2(const float* cols, int N, int Hi, int Wi, int C, c
                               void* stream) {
   GLIS_REQUIRE(cols && out, GLIS_E_BADARG, "glis_fold4x4s2: NULL pointer");
   GLIS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && C > 0 && C <= 4, GLIS_E_BADARG, "glis_fold4x4s2: bad shape");
+  GLIS_REQUIRE((int64_t)N * Hi * Wi * 4 < ((int64_t)1 << 31), GLIS_E_UNSUPPORTED, "glis_fold4x4s2: more than 2^31 pixels");
   GLIS_REQUIRE(act == GLIS_ACT_NONE || act == GLIS_ACT_SIGMOID, GLIS_E_UNSUPPORTED, "glis_fold4x4s2: activation %d", act);
   fold4x4s2_kernel<<<is_blocks((int64_t)N * Hi * Wi * 4), IS_NT, 0, (cudaStream_t)stream>>>(cols, N, Hi, Wi, C, bias, act,
                                                                                          out);

@@ -608,6 +608,8 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
     const int rc = simt_linear_forward(g, in, wpack, ep, out, st);
     if (rc != GLIS_E_UNSUPPORTED) return rc;
   }
+  GLIS_REQUIRE(ep->act_channels <= 0, GLIS_E_UNSUPPORTED,
+               "glis_conv_forward: act_channels is only implemented by the linear and tensor-core kernels");
   if (g->relation == GLIS_CONV && g->Ci <= 4 && g->KH * g->KW * g->Ci <= SI_MAXK && g->Co <= SI_MAXCO &&
       g->Co % 16 == 0 && (int64_t)g->N * g->Ho * g->Wo >= 4096 &&
       ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ep->preact) |

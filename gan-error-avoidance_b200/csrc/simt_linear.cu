@@ -155,7 +155,8 @@ linear_cluster_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
     if (ep.preact) ep.preact[idx] = y;
     float o = y;
     if (ep.act == GLIS_ACT_TPRELU) {
-      const float b = __ldg(ep.act_b + nn), a = fminf(fmaxf(__ldg(ep.act_a + nn), 0.f), 1.f);
+      const int ca = ep.act_channels > 0 ? nn % ep.act_channels : nn;
+      const float b = __ldg(ep.act_b + ca), a = fminf(fmaxf(__ldg(ep.act_a + ca), 0.f), 1.f);
       const float t = y - b;
       o = (t > 0.f ? t : a * t) + b;
     } else if (ep.act == GLIS_ACT_SIGMOID) {
@@ -240,7 +241,7 @@ constexpr int LW_TJ = 256, LW_MC = 32, LW_NT = 256;
 template <int APT>
 __global__ void __launch_bounds__(LW_NT)
 linear_wgrad_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ G,
-                    int M, int Ca, int Cb, int T) {
+                    int M, int Ca, int Cb, int T, int perm_c, int perm_p) {
   __shared__ __align__(16) float xs[LW_MC * LW_TJ];   // [m][j]
   constexpr int LW_TN = 8 * APT;
   __shared__ __align__(16) float ds[LW_MC * LW_TN];   // [m][a]
@@ -331,28 +332,42 @@ linear_wgrad_kernel(const float* __restrict__ small, const float* __restrict__ b
   for (int i = 0; i < APT; ++i) {
     const int a = a0 + APT * tn + i;
     if (a >= Ca) continue;
+    const int arow = perm_c ? (a % perm_c) * perm_p + a / perm_c : a;   // master row of this (permuted) feature
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int j = j0 + 8 * tk + q;
       if (j >= J) continue;
       const int tap = j / Cb, b = j - tap * Cb;
-      float* dst = G + ((size_t)a * Cb + b) * T + tap;   // one owner per element
+      float* dst = G + ((size_t)arow * Cb + b) * T + tap;   // one owner per element
       *dst += acc[i][q];
     }
   }
 }
 
 // Weight gradient of a linear-shaped layer (is_linear_geom, GLIS_CONV): adds into G.
-int simt_linear_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
-  const int M = g->N, Ca = g->Co, Cb = g->Ci, T = g->KH * g->KW;
+static int launch_linear_wgrad(const float* small, const float* big, float* G, int M, int Ca, int Cb, int T,
+                               int perm_c, int perm_p, cudaStream_t st) {
   if (M > 4096) return GLIS_E_UNSUPPORTED;
   const int gx = (Cb * T + LW_TJ - 1) / LW_TJ;
   if (gx * ((Ca + 31) / 32) >= 296)
-    linear_wgrad_kernel<4><<<dim3(gx, (Ca + 31) / 32), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T);
+    linear_wgrad_kernel<4><<<dim3(gx, (Ca + 31) / 32), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T, perm_c, perm_p);
   else
-    linear_wgrad_kernel<2><<<dim3(gx, (Ca + 15) / 16), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T);
+    linear_wgrad_kernel<2><<<dim3(gx, (Ca + 15) / 16), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T, perm_c, perm_p);
   GLIS_CHECK_LAUNCH("glis_conv_wgrad(fp32, linear)");
   return GLIS_OK;
 }
 
+int simt_linear_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
+  return launch_linear_wgrad(small, big, G, g->N, g->Co, g->Ci, g->KH * g->KW, 0, 0, st);
+}
+
 }  // namespace glis
+
+extern "C" int glis_linear_wgrad(const float* dy, const float* x, float* G, int M, int Ca, int Cb, int perm_c, int perm_p,
+                                 void* stream) {
+  using namespace glis;
+  GLIS_REQUIRE(dy && x && G && M > 0 && Ca > 0 && Cb > 0, GLIS_E_BADARG, "glis_linear_wgrad: bad arguments");
+  GLIS_REQUIRE((perm_c == 0 && perm_p == 0) || (perm_c > 0 && perm_p > 0 && (int64_t)perm_c * perm_p == Ca), GLIS_E_BADARG,
+               "glis_linear_wgrad: bad row permutation (C=%d P=%d for %d rows)", perm_c, perm_p, Ca);
+  return launch_linear_wgrad(dy, x, G, M, Ca, Cb, 1, perm_c, perm_p, (cudaStream_t)stream);
+}

@@ -51,7 +51,7 @@ struct TcConvParams {
   int n_groups;      // total_tiles / cluster (x ksplit)
   int ksplit;        // K (the 64-channel blocks of every tap) split across `ksplit` work items per tile; their
                      // partial sums are added into a zero-filled fp32 output (plain-output launches only)
-  const float* bias; int act; const float* act_a; const float* act_b;
+  const float* bias; int act; const float* act_a; const float* act_b; int act_channels;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int ep_mode;       // compile-time specialised epilogue (0 = generic)
   unsigned long long* trace;  // optional timeline buffer (GLIS_TC_TRACE): CTA 0 logs globaltimer per event
@@ -322,7 +322,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias && tl.split == 0) bias = __ldg(P.bias + co);
-        if (P.act == GLIS_ACT_TPRELU) { ta = fminf(fmaxf(__ldg(P.act_a + co), 0.f), 1.f); tb = __ldg(P.act_b + co); }
+        if (P.act == GLIS_ACT_TPRELU) {
+          const int ca = P.act_channels > 0 ? co % P.act_channels : co;
+          ta = fminf(fmaxf(__ldg(P.act_a + ca), 0.f), 1.f); tb = __ldg(P.act_b + ca);
+        }
       }
       const int oy0 = g.relation == GLIS_TCONV ? tl.qy0 * sh + tl.ph.ry : tl.qy0;
       const int ox0 = g.relation == GLIS_TCONV ? tl.ph.rx : 0;
@@ -560,6 +563,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: tile does not fit shared memory");
   P.stages = stages;
   P.bias = ep->bias; P.act = ep->act; P.act_a = ep->act_a; P.act_b = ep->act_b; P.preact = ep->preact;
+  P.act_channels = ep->act_channels;
   P.out_f32 = out_f32; P.out_hi = out_hi; P.out_lo = out_lo;
   P.ep_mode = 0;
   if (ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi) P.ep_mode = 1;

@@ -73,19 +73,30 @@ static void launch_wn_norm(const float* w, int out_axis, int Cout, int Cin, int 
 }
 
 // One thread per packed element; writes coalesced, reads gathered through L2.
+// Pack row o' -> master output channel (identity, or the NHWC feature order of glis_wn_prepare_perm).
+__device__ __forceinline__ int master_channel(int o, int perm_c, int perm_p) {
+  return perm_c ? (o % perm_c) * perm_p + o / perm_c : o;
+}
+
+// IDX = uint32_t whenever the tensor has fewer than 2^31 elements: the per-element index
+// decomposition is a chain of divisions, and 64-bit integer division costs ~10x the 32-bit one
+// (the kernel was bound by it, not by memory).
+template <typename IDX>
 __global__ void wn_pack_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T,
-                               float* __restrict__ pack_io, float* __restrict__ pack_oi) {
-  const int64_t total = (int64_t)T * Cin * Cout;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
+                               float* __restrict__ pack_io, float* __restrict__ pack_oi, int perm_c, int perm_p) {
+  const IDX total = (IDX)T * (IDX)Cin * (IDX)Cout;
+  for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (IDX)gridDim.x * blockDim.x) {
     if (pack_io) {  // [t][i][o]
-      const int o = (int)(e % Cout); const int64_t r = e / Cout; const int i = (int)(r % Cin); const int t = (int)(r / Cin);
+      const int o = master_channel((int)(e % (IDX)Cout), perm_c, perm_p);
+      const IDX r = e / (IDX)Cout; const int i = (int)(r % (IDX)Cin); const int t = (int)(r / (IDX)Cin);
       const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
       pack_io[e] = __ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a;
     }
     if (pack_oi) {  // [t][o][i]
-      const int i = (int)(e % Cin); const int64_t r = e / Cin; const int o = (int)(r % Cout); const int t = (int)(r / Cout);
+      const int i = (int)(e % (IDX)Cin); const IDX r = e / (IDX)Cin;
+      const int o = master_channel((int)(r % (IDX)Cout), perm_c, perm_p);
+      const int t = (int)(r / (IDX)Cout);
       const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
       pack_oi[e] = __ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a;
     }
@@ -94,15 +105,18 @@ __global__ void wn_pack_kernel(const float* __restrict__ w, const float* __restr
 
 // bf16 hi/lo packs for the tensor-core kernels (K-major operands):
 //   fwd [t][o][i] for the launch that reads Cin and writes Cout, bwd [t][i][o] for its data gradient.
+template <typename IDX>
 __global__ void wn_pack_bf16_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                     const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T,
                                     __nv_bfloat16* __restrict__ fwd_hi, __nv_bfloat16* __restrict__ fwd_lo,
-                                    __nv_bfloat16* __restrict__ bwd_hi, __nv_bfloat16* __restrict__ bwd_lo) {
-  const int64_t total = (int64_t)T * Cin * Cout;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
+                                    __nv_bfloat16* __restrict__ bwd_hi, __nv_bfloat16* __restrict__ bwd_lo,
+                                    int perm_c, int perm_p) {
+  const IDX total = (IDX)T * (IDX)Cin * (IDX)Cout;
+  for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (IDX)gridDim.x * blockDim.x) {
     if (fwd_hi) {  // [t][o][i]
-      const int i = (int)(e % Cin); const int64_t r = e / Cin; const int o = (int)(r % Cout); const int t = (int)(r / Cout);
+      const int i = (int)(e % (IDX)Cin); const IDX r = e / (IDX)Cin;
+      const int o = master_channel((int)(r % (IDX)Cout), perm_c, perm_p);
+      const int t = (int)(r / (IDX)Cout);
       const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
       __nv_bfloat16 h, l;
       sm100::split_bf16(__ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a, h, l);
@@ -110,7 +124,8 @@ __global__ void wn_pack_bf16_kernel(const float* __restrict__ w, const float* __
       if (fwd_lo) fwd_lo[e] = l;
     }
     if (bwd_hi) {  // [t][i][o]
-      const int o = (int)(e % Cout); const int64_t r = e / Cout; const int i = (int)(r % Cin); const int t = (int)(r / Cin);
+      const int o = master_channel((int)(e % (IDX)Cout), perm_c, perm_p);
+      const IDX r = e / (IDX)Cout; const int i = (int)(r % (IDX)Cin); const int t = (int)(r / (IDX)Cin);
       const float a = (scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o);
       __nv_bfloat16 h, l;
       sm100::split_bf16(__ldg(w + master_index(out_axis, Cout, Cin, T, o, i, t)) * a, h, l);
@@ -223,7 +238,22 @@ using namespace glis;
 
 extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
                                float c, float* norm, float* pack_io, float* pack_oi, void* stream) {
+  return glis_wn_prepare_perm(w, scale, out_axis, Cout, Cin, T, c, norm, pack_io, pack_oi, 0, 0, stream);
+}
+
+static int check_perm(int out_axis, int Cout, int T, int perm_c, int perm_p, const char* who) {
+  GLIS_REQUIRE((perm_c == 0 && perm_p == 0) ||
+                   (perm_c > 0 && perm_p > 0 && T == 1 && out_axis == 0 && (int64_t)perm_c * perm_p == Cout),
+               GLIS_E_BADARG, "%s: bad row permutation (C=%d P=%d for Cout=%d T=%d axis=%d)", who, perm_c, perm_p, Cout, T,
+               out_axis);
+  return GLIS_OK;
+}
+
+extern "C" int glis_wn_prepare_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                                    float c, float* norm, float* pack_io, float* pack_oi, int perm_c, int perm_p,
+                                    void* stream) {
   GLIS_REQUIRE(w && norm, GLIS_E_BADARG, "glis_wn_prepare: w/norm is NULL");
+  if (int rc = check_perm(out_axis, Cout, T, perm_c, perm_p, "glis_wn_prepare_perm")) return rc;
   GLIS_REQUIRE(Cout > 0 && Cin > 0 && T > 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
                "glis_wn_prepare: bad shape (Cout=%d Cin=%d T=%d axis=%d)", Cout, Cin, T, out_axis);
   cudaStream_t st = (cudaStream_t)stream;
@@ -232,7 +262,10 @@ extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis,
   if (pack_io || pack_oi) {
     const int64_t total = (int64_t)T * Cin * Cout;
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
-    wn_pack_kernel<<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi);
+    if (total < ((int64_t)1 << 31))
+      wn_pack_kernel<uint32_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
+    else
+      wn_pack_kernel<int64_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
     GLIS_CHECK_LAUNCH("glis_wn_prepare(pack)");
   }
   return GLIS_OK;
@@ -241,7 +274,14 @@ extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis,
 extern "C" int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
                                     float c, float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo,
                                     void* stream) {
+  return glis_wn_prepare_bf16_perm(w, scale, out_axis, Cout, Cin, T, c, norm, fwd_hi, fwd_lo, bwd_hi, bwd_lo, 0, 0, stream);
+}
+
+extern "C" int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                                         float c, float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo,
+                                         int perm_c, int perm_p, void* stream) {
   GLIS_REQUIRE(w && norm, GLIS_E_BADARG, "glis_wn_prepare_bf16: w/norm is NULL");
+  if (int rc = check_perm(out_axis, Cout, T, perm_c, perm_p, "glis_wn_prepare_bf16_perm")) return rc;
   GLIS_REQUIRE(Cout > 0 && Cin > 0 && T > 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
                "glis_wn_prepare_bf16: bad shape (Cout=%d Cin=%d T=%d axis=%d)", Cout, Cin, T, out_axis);
   GLIS_REQUIRE((fwd_hi || !fwd_lo) && (bwd_hi || !bwd_lo), GLIS_E_BADARG, "glis_wn_prepare_bf16: lo plane without hi");
@@ -251,8 +291,14 @@ extern "C" int glis_wn_prepare_bf16(const float* w, const float* scale, int out_
   if (fwd_hi || bwd_hi) {
     const int64_t total = (int64_t)T * Cin * Cout;
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
-    wn_pack_bf16_kernel<<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
-                                               (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi, (__nv_bfloat16*)bwd_lo);
+    if (total < ((int64_t)1 << 31))
+      wn_pack_bf16_kernel<uint32_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
+                                                           (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi,
+                                                           (__nv_bfloat16*)bwd_lo, perm_c, perm_p);
+    else
+      wn_pack_bf16_kernel<int64_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
+                                                          (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi,
+                                                          (__nv_bfloat16*)bwd_lo, perm_c, perm_p);
     GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(pack)");
   }
   return GLIS_OK;

@@ -25,7 +25,8 @@ class Geom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("act_a", C.c_void_p),
-                ("act_b", C.c_void_p), ("preact", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p)]
+                ("act_b", C.c_void_p), ("preact", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+                ("act_channels", C.c_int32)]
 
 
 _vp, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
@@ -51,6 +52,9 @@ SIGNATURES = {
     "glis_rmsprop": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "glis_randn": [_vp, _i64, _u64, _u64, _vp],
     "glis_uniform": [_vp, _i64, _u64, _u64, _vp],
+    "glis_wn_prepare_perm": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp],
+    "glis_wn_prepare_bf16_perm": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "glis_linear_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "glis_unfold4x4s2_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "glis_fold4x4s2": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "glis_wn_pack_matrix_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

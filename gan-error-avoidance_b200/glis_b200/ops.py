@@ -36,11 +36,14 @@ class ContractionSpec(object):
     """Static description of one WN layer's contraction (conv / transposed conv / linear)."""
 
     def __init__(self, transposed, kernel_size, stride, padding, dilation, output_padding=(0, 0),
-                 linear=False, precision=None):
+                 linear=False, precision=None, perm=None):
         self.transposed, self.linear = bool(transposed), bool(linear)
         self.kernel_size, self.stride, self.padding = tuple(kernel_size), tuple(stride), tuple(padding)
         self.dilation, self.output_padding = tuple(dilation), tuple(output_padding)
         self._precision = precision
+        # (C, P): a linear layer whose Cout = C*P output features are produced in NHWC order (row p*C + c of
+        # every pack = master row c*P + p), i.e. already laid out as the (C, h, w) map a following View makes
+        self.perm = None if perm is None else (int(perm[0]), int(perm[1]))
 
     @property
     def precision(self):
@@ -152,9 +155,10 @@ class PackedWeights(object):
             self.io = torch.empty(self.t, self.cin, self.cout, device=dev, dtype=torch.float32)
         if oi and self.oi is None:
             self.oi = torch.empty(self.t, self.cout, self.cin, device=dev, dtype=torch.float32)
-        L.call("glis_wn_prepare", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
+        pc, pp = self.spec.perm or (0, 0)
+        L.call("glis_wn_prepare_perm", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
                self.spec.norm_factor, L.ptr(self.norm), L.ptr(self.io if io else None),
-               L.ptr(self.oi if oi else None), L.stream(), kernels=2 if (io or oi) else 1)
+               L.ptr(self.oi if oi else None), pc, pp, L.stream(), kernels=2 if (io or oi) else 1)
         self.fresh.add("norm")
         if io:
             self.fresh.add("io")
@@ -193,9 +197,10 @@ class PackedWeights(object):
             self.bwd = planes(self.bwd, (self.t, self.cin, self.cout))
         fh, fl = self.fwd if fwd else (None, None)
         bh, bl = self.bwd if bwd else (None, None)
-        L.call("glis_wn_prepare_bf16", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
+        pc, pp = self.spec.perm or (0, 0)
+        L.call("glis_wn_prepare_bf16_perm", L.ptr(w), L.ptr(sc), self.out_axis, self.cout, self.cin, self.t,
                self.spec.norm_factor, L.ptr(self.norm), L.ptr16(fh), L.ptr16(fl if lo else None), L.ptr16(bh),
-               L.ptr16(bl if lo else None), L.stream(), kernels=2)
+               L.ptr16(bl if lo else None), pc, pp, L.stream(), kernels=2)
         self.fresh.add("norm")
         if fwd:
             self.fresh.add("fwd")
@@ -249,7 +254,7 @@ def _need_matrix(pw, lo):
 
 def _pack_key(weight, scale, spec):
     return (PARAM_EPOCH[0], getattr(weight, "_glis_epoch", 0), weight.data_ptr(), weight._version,
-            None if scale is None else scale._version, spec.precision, spec.transposed, spec.stride)
+            None if scale is None else scale._version, spec.precision, spec.transposed, spec.stride, spec.perm)
 
 
 def packed_weights(weight, scale, spec):
@@ -374,8 +379,14 @@ def _tag(relation, g):
 
 def _use_tc(spec, relation, in_shape, out_shape):
     """Whether the launch reading NCHW-shaped ``in_shape`` and writing ``out_shape`` runs on tcgen05."""
-    if spec.precision == L.PREC_FP32 or len(in_shape) != 4:
-        return False  # batch-sized linears stay on the FFMA kernel
+    if spec.precision == L.PREC_FP32:
+        return False
+    if len(in_shape) != 4:
+        # batch-sized linears stay on the FFMA kernel — except the FORWARD of a wide linear that feeds a
+        # feature map (spec.perm): 100+ channel tiles of 128 x batch, the fused TPReLU epilogue writes planes
+        if spec.perm is None or relation != L.CONV or len(in_shape) != 2:
+            return False
+        return tc_supported(spec.geom(relation, in_shape[0], 1, 1, in_shape[1], 1, 1, out_shape[1]))
     n, ci, hi, wi = in_shape
     _, co, ho, wo = out_shape
     return tc_supported(spec.geom(relation, n, hi, wi, ci, ho, wo, co))
@@ -493,14 +504,15 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
     preact = torch.empty_like(out) if want_preact else None
     use_tc = _use_tc(spec, relation, in_shape, out_shape)
     planes = None
-    if want_planes and prec != L.PREC_FP32 and out.dim() == 4 and g.Co > 4:
+    if want_planes and prec != L.PREC_FP32 and (out.dim() == 4 or spec.perm is not None) and g.Co > 4:
         planes = (torch.empty_like(out, dtype=torch.bfloat16),
                   torch.empty_like(out, dtype=torch.bfloat16) if lo else None)
     if use_tc:
         pw.need_bf16(forward_pack, not forward_pack, lo)
         wp = pw.fwd if forward_pack else pw.bwd
         xp = planes_of(x, lo)
-        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None)
+        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None,
+                        spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0)
         with L.timed(_tag(relation, g) + " tc"):
             L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
                    L.ptr16(wp[1]), C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
@@ -511,7 +523,8 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         pw.need_fp32(forward_pack, not forward_pack)
         wp = pw.io if forward_pack else pw.oi
         ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact),
-                        L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None)
+                        L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None,
+                        spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0)
         with L.timed(_tag(relation, g) + " fp32"):
             L.call("glis_conv_forward", C.byref(g), L.ptr(x), L.ptr(wp), C.byref(ep), L.ptr(out), L.PREC_FP32,
                    L.stream())
@@ -748,6 +761,10 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                 with L.timed(tag + " tc"):
                     L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
                            L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
+            elif spec.perm is not None:
+                with L.timed(tag + " fp32 (permuted rows)"):
+                    L.call("glis_linear_wgrad", L.ptr(small), L.ptr(big), L.ptr(graw), n, cout, cin, spec.perm[0],
+                           spec.perm[1], L.stream())
             else:
                 with L.timed(tag + " fp32"):
                     L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
@@ -907,6 +924,76 @@ class WNContractionTPReLU(torch.autograd.Function):
 
 def wn_contraction_tprelu(x, weight, scale, bias, a_raw, b_t, spec):
     out, hi, lo = WNContractionTPReLU.apply(x, weight, scale, bias, a_raw, b_t, spec)
+    if hi is not None:
+        attach_planes(out, (hi, lo))
+    return out
+
+
+class WNLinearViewTPReLU(torch.autograd.Function):
+    """``WeightNormalizedLinear -> View(C, h, w) -> TPReLU(C)`` — the head of the generators
+    (common/model.py:196-212, :94-104) — as ONE kernel.  The weight packs are row-permuted
+    (ContractionSpec.perm) so that the GEMM writes its features in NHWC order: the View is free, the
+    per-channel TPReLU sits in the epilogue (parameter index = feature % C) together with the
+    pre-activation and the bf16 planes for the first transposed convolution; on the tensor cores when
+    the precision allows.  Backward: TPReLU backward in NHWC, data gradient through the permuted pack,
+    weight gradient written back to master rows."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, a_raw, b_t, spec, view):
+        xc = _nhwc(x)
+        c, h, w = view
+        n, n_out = xc.shape[0], weight.shape[0]
+        pw = packed_weights(weight, scale, spec)
+        out, preact, planes = launch(spec, L.CONV, xc, (n, n_out), pw, forward_pack=True, act=L.ACT_TPRELU,
+                                     act_a=a_raw.detach().contiguous(), act_b=b_t.detach().contiguous(),
+                                     want_preact=True, want_planes=True)
+        ctx.spec, ctx.pw, ctx.view = spec, pw, view
+        ctx.save_for_backward(xc, preact, a_raw, b_t)
+        ctx.set_materialize_grads(False)
+        as_map = lambda t: t.view(n, h, w, c).permute(0, 3, 1, 2)     # NHWC memory, logical (N, C, h, w)
+        if planes is None:
+            return as_map(out), None, None
+        hi, lo = as_map(planes[0]), None if planes[1] is None else as_map(planes[1])
+        ctx.mark_non_differentiable(hi)
+        if lo is not None:
+            ctx.mark_non_differentiable(lo)
+        return as_map(out), hi, lo
+
+    @staticmethod
+    def backward(ctx, dout, _dhi, _dlo):
+        xc, preact, a_raw, b_t = ctx.saved_tensors
+        spec, c = ctx.spec, a_raw.numel()
+        n = xc.shape[0]
+        if dout is None:
+            dout = torch.zeros((n,) + tuple(ctx.view), device=xc.device)
+        doc = dout.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(n, -1)
+        ni = ctx.needs_input_grad
+        dy = torch.empty_like(preact)
+        ga, gb = _dense_grad(a_raw), _dense_grad(b_t)
+        want_ab = ni[3] or ni[4]
+        direct = ga is not None and gb is not None and ni[3] and ni[4]
+        if not want_ab:
+            da = db = None
+        elif direct:
+            da, db = ga, gb
+        else:
+            da = torch.zeros(c, device=doc.device, dtype=torch.float32)
+            db = torch.zeros(c, device=doc.device, dtype=torch.float32)
+        L.call("glis_tprelu_backward_planes", L.ptr(preact), L.ptr(a_raw.detach()), L.ptr(b_t.detach()), L.ptr(doc),
+               L.ptr(dy), None, None, L.ptr(da), L.ptr(db), preact.numel(), c, 1, L.stream())
+        if direct:
+            _touch_hooks(a_raw, b_t)
+            da = db = None
+        dx, dw, dscale, _ = _layer_backward(spec, ctx.pw, xc, dy, None, ni[0], ni[1],
+                                            ctx.pw.scale is not None and ni[2], False, None)
+        return dx, dw, dscale, da, db, None, None
+
+
+def wn_linear_view_tprelu(x, weight, scale, a_raw, b_t, view):
+    """See WNLinearViewTPReLU.  ``view`` = (C, h, w) of the View module between the linear and the TPReLU."""
+    c, h, w = (int(v) for v in view)
+    spec = ContractionSpec(False, (1, 1), (1, 1), (0, 0), (1, 1), linear=True, perm=(c, h * w))
+    out, hi, lo = WNLinearViewTPReLU.apply(x, weight, scale, a_raw, b_t, spec, (c, h, w))
     if hi is not None:
         attach_planes(out, (hi, lo))
     return out

@@ -69,6 +69,9 @@ typedef struct glis_epilogue {
   float* preact;       /* if non-NULL, y (before act) is also stored here (NHWC) */
   void* out_hi;        /* fp32 kernels only: if non-NULL, bf16 hi plane of the activated output */
   void* out_lo;        /*   ... and its lo plane (may be NULL) — feeds the next tensor-core layer */
+  int32_t act_channels; /* 0: act_a / act_b hold one value per OUTPUT channel; C > 0: the TPReLU has C channels and
+                         * output channel co uses act_a[co % C] (a linear layer whose output is a (C,h,w) map
+                         * written in NHWC feature order, see glis_wn_prepare_perm) */
 } glis_epilogue_t;
 
 const char* glis_last_error(void);
@@ -88,6 +91,20 @@ int glis_version(void);
  */
 int glis_wn_prepare(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
                     float c, float* norm, float* pack_io, float* pack_oi, void* stream);
+
+/* Row-permuted packs for a linear layer feeding View(C, h, w) (common/model.py:206-212): with P = h*w,
+ * pack row o' = p*C + c holds master row o = c*P + p, so the layer's output features come out in NHWC
+ * order and the View costs nothing on the device.  perm_c = C, perm_p = P (0, 0 = no permutation);
+ * requires T == 1, out_axis == 0 and Cout == C*P.  Otherwise as glis_wn_prepare / glis_wn_prepare_bf16. */
+int glis_wn_prepare_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T, float c,
+                         float* norm, float* pack_io, float* pack_oi, int perm_c, int perm_p, void* stream);
+int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T, float c,
+                              float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo, int perm_c,
+                              int perm_p, void* stream);
+/* Weight gradient of a linear layer, G[row(a)][b] += sum_m dy[m][a] * x[m][b] with dy in the permuted
+ * feature order of glis_wn_prepare_perm: row(a) = (a % perm_c)*perm_p + a / perm_c (identity if perm_c == 0). */
+int glis_linear_wgrad(const float* dy, const float* x, float* G, int M, int Ca, int Cb, int perm_c, int perm_p,
+                      void* stream);
 
 /* Backward of the normalisation: given the raw gradient G w.r.t. w_hat
  * (master layout), dw[o] (+)= (s/n)(G[o] - c w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n.

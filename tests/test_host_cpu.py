@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from glis_b200 import _lib
     assert ctypes.sizeof(_lib.Geom) == 16 * 4
-    assert ctypes.sizeof(_lib.Epilogue) == 7 * 8
+    assert ctypes.sizeof(_lib.Epilogue) == 8 * 8
 
 
 def test_error_convention_bad_args_no_gpu_needed():
