@@ -85,3 +85,47 @@ def test_gloo_world2_gradient_exchange_and_depth_agreement():
     want = torch.arange(1000, dtype=torch.float32) * 3  # (1 + 2) * i
     assert torch.equal(a["flat"], want) and torch.equal(b["flat"], want)
     assert a["gscale"] == 0.5 and a["bytes"] == 4000
+
+
+def test_overlapped_sync_counts_each_parameter_once(monkeypatch):
+    """A parameter is announced twice per backward — by the operator that added its gradient in place and
+    by autograd's post-accumulate hook, which torch also runs for parameter inputs a Function returned
+    None for.  A bucket must be sent only when every one of its parameters has reported (regression:
+    double counting sent buckets before their last gradients were written and the replicas diverged)."""
+    from glis_b200 import dp
+
+    class Flat(object):
+        def __init__(self, sizes):
+            self.params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+            self.offsets, off = [], 0
+            for n in sizes:
+                self.offsets.append(off)
+                off += n
+            self.numel = off
+            self.g = torch.zeros(off)
+
+    flat = Flat([4, 4, 8, 4, 4, 8])
+    sync = dp.OverlappedGradSync(world=2, bucket_mb=12 * 4 / float(1 << 20))   # 12 elements per bucket
+    sent = []
+    monkeypatch.setattr(sync, "_send", lambda st, b: (sent.append(b), st["sent"].__setitem__(b, True)))
+    sync.register("net", flat)
+    st = sync.sets["net"]
+    assert [sorted(m) for m in ([i for i, o in enumerate(st["owner"]) if o == b] for b in range(len(st["buckets"])))] \
+        == [[4, 5], [2, 3], [0, 1]]
+    sync.begin("net")
+    hooks = [p._glis_grad_hooks[0] for p in flat.params]
+    for idx in (5, 5, 5):                 # the same parameter announced three times: still one report
+        hooks[idx](flat.params[idx])
+    assert sent == []
+    hooks[4](flat.params[4])
+    assert sent == [0]
+    hooks[4](flat.params[4])              # late duplicate of a sent bucket: ignored
+    for idx in (3, 3, 2, 2):
+        hooks[idx](flat.params[idx])
+    assert sent == [0, 1]
+    sync.begin("net")                     # next backward: counters re-armed
+    sent.clear()
+    for idx in (5, 4, 3, 2, 1, 0):
+        hooks[idx](flat.params[idx])
+        hooks[idx](flat.params[idx])
+    assert sent == [0, 1, 2]

@@ -648,3 +648,138 @@ def test_host_fed_stepper_matches_direct_steps(precision):
             assert abs(a[k] - b[k]) <= 2e-3 * abs(a[k]), (i, k, a[k], b[k])
         assert len(a["r"]) == len(b["r"]) == 1
     assert (pa - pb).abs().max().item() <= 5 * 6.4 * 2e-5 + 1e-7
+
+
+# ---------------------------------------------------------------- kernels added for the image side / head
+def test_unfold_fold_kernels_match_torch():
+    """csrc/image_side.cu against torch: unfold = the 4x4/s2/p1 patches in (c, kh, kw) column order as
+    hi+lo bf16 planes; fold = its adjoint (+ bias, sigmoid)."""
+    import torch.nn.functional as F
+    from glis_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(21)
+    for (n, c, h, w) in ((3, 3, 8, 12), (2, 3, 80, 80), (2, 1, 6, 4)):
+        x = torch.rand(n, c, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+        hi, lo = ops.unfolded_planes(x)
+        got = (hi.float() + lo.float())                                   # (n, h/2, w/2, 16c)
+        want = F.unfold(x.contiguous(), 4, padding=1, stride=2)           # (n, c*16, L), rows (c, kh, kw)
+        want = want.view(n, c * 16, h // 2, w // 2).permute(0, 2, 3, 1)
+        assert rel_err(got, want) <= 2e-5, (n, c, h, w)
+        cols = torch.randn(n, h // 2, w // 2, 16 * c, generator=g).to(DEV)
+        bias = torch.randn(c, generator=g).to(DEV)
+        for act, fn in ((L.ACT_NONE, lambda t: t), (L.ACT_SIGMOID, torch.sigmoid)):
+            out = torch.empty(n, c, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+            L.call("glis_fold4x4s2", L.ptr(cols), n, h // 2, w // 2, c, L.ptr(bias), act, L.ptr(out), L.stream())
+            ref = F.fold(cols.permute(0, 3, 1, 2).reshape(n, 16 * c, -1), (h, w), 4, padding=1, stride=2)
+            ref = fn(ref + bias.view(1, c, 1, 1))
+            assert rel_err(out, ref) <= 1e-6, (n, c, h, w, act)
+
+
+def test_linear_wgrad_with_row_permutation():
+    """glis_linear_wgrad: G[row(a)][b] += sum_m dy[m][a] x[m][b], row(a) = (a % C)*P + a / C."""
+    from glis_b200 import _lib as L
+    g = torch.Generator().manual_seed(22)
+    for (m, c, p, k) in ((64, 8, 25, 40), (130, 16, 4, 256), (5, 3, 7, 9)):
+        ca = c * p
+        dy, x = torch.randn(m, ca, generator=g).to(DEV), torch.randn(m, k, generator=g).to(DEV)
+        G = torch.zeros(ca, k, device=DEV)
+        L.call("glis_linear_wgrad", L.ptr(dy), L.ptr(x), L.ptr(G), m, ca, k, c, p, L.stream())
+        rows = torch.tensor([(a % c) * p + a // c for a in range(ca)], device=DEV)
+        want = torch.zeros(ca, k, dtype=torch.float64, device=DEV)
+        want[rows] = dy.double().t() @ x.double()
+        assert rel_err(G, want) <= 1e-5, (m, c, p, k)
+        G2 = torch.zeros(ca, k, device=DEV)
+        L.call("glis_linear_wgrad", L.ptr(dy), L.ptr(x), L.ptr(G2), m, ca, k, 0, 0, L.stream())
+        assert rel_err(G2, dy.double().t() @ x.double()) <= 1e-5
+
+
+def test_generator_head_fused_matches_unfused(precision):
+    """linear -> View -> TPReLU as one kernel (row-permuted packs, NHWC output) against the three modules
+    run one by one; forward, input gradient and every parameter gradient."""
+    pm, pmod = _product()
+    from glis_b200 import ops
+    torch.manual_seed(23)
+    code, f, h, w, b = 32, 16, 5, 3, 6
+    lin = pmod.WeightNormalizedLinear(code, f * h * w, init_factor=0.01, scale=False, bias=False).to(DEV)
+    view, act = pmod.View(f, h, w), pmod.TPReLU(f).to(DEV)
+    with torch.no_grad():
+        act.weight.uniform_(-0.2, 1.2)
+        act.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(b, code, device=DEV, requires_grad=True)
+    r = torch.randn(b, f, h, w, device=DEV)
+    y1 = pm.run_layers([lin, view, act], x)                      # the fused operator
+    (y1 * r).sum().backward()
+    g1 = [x.grad.clone()] + [p.grad.clone() for p in (lin.weight, act.weight, act.bias)]
+    x.grad = None
+    for p in (lin.weight, act.weight, act.bias):
+        p.grad = None
+    y2 = act(view(lin(x)))                                       # module by module
+    (y2 * r).sum().backward()
+    g2 = [x.grad] + [p.grad for p in (lin.weight, act.weight, act.bias)]
+    tol = 1e-6 if precision == "fp32" else 2e-5
+    assert y1.shape == y2.shape and rel_err(y1, y2) <= tol
+    for a, bb in zip(g1, g2):
+        assert rel_err(a, bb) <= 10 * tol
+
+
+@pytest.mark.parametrize("knob", ["GLIS_TC_KSPLIT=1", "GLIS_TC_CLUSTER=2", "GLIS_TC_CLUSTER=4", "GLIS_WG_COLS=128"])
+def test_tensor_core_tuning_knobs_do_not_change_results(knob, monkeypatch):
+    """Split-K, the cluster multicast of the weight tile and the accumulator width are scheduling choices:
+    the contraction they compute is the same (summation order aside)."""
+    from glis_b200 import _lib
+    _lib.set_precision("bf16x3")
+    _, pmod = _product()
+
+    def run():
+        torch.manual_seed(24)
+        conv = pmod.WeightNormalizedConv2d(256, 128, 4, 2, 1, scale=False, bias=False).to(DEV)
+        x = torch.randn(6, 256, 10, 10, device=DEV, requires_grad=True)
+        y = conv(x)
+        (y * torch.linspace(-1, 1, y.numel(), device=DEV).view_as(y)).sum().backward()
+        return y.detach(), x.grad, conv.weight.grad
+
+    base = run()
+    name, val = knob.split("=")
+    monkeypatch.setenv(name, val)
+    for a, b in zip(run(), base):
+        assert rel_err(a, b) <= 2e-5, knob
+
+
+def test_side_stream_overlap_matches_single_stream(precision):
+    """The trainer's side-stream work (weight gradients, pack rebuilds) only reorders kernels: same losses
+    and gradients as the single-stream schedule.  The two trainers run in LOCKSTEP — before every iteration
+    the single-stream one takes the other's parameters and optimizer state — because training itself is
+    chaotic at rounding level (split-K sums arrive in a different order every run, RMSprop divides
+    near-zero gradients by eps, TPReLU masks flip): two runs of the SAME schedule drift apart by 1e-3 on
+    G's gradient within two iterations (tools/debug_overlap.py), which says nothing about the schedule."""
+    from glis_b200 import ops
+    from glis_b200.trainer import GLISTrainer
+    pm, _ = _product()
+
+    def make():
+        torch.manual_seed(25)
+        g = pm.GeneratorLearnedInputSpace(32, 32, 16, 3, 32, "weight", 1, "fractional").to(DEV)
+        d = pm.build_discriminator(32, 32, 16, 3, "weight", 0).to(DEV)
+        return GLISTrainer(g, d, lr=1e-4)
+
+    side, single = make(), make()
+    gen = torch.Generator().manual_seed(26)
+    try:
+        for it in range(4):
+            for fa, fb in ((side.gen_flat, single.gen_flat), (side.dis_flat, single.dis_flat)):
+                fb.p.copy_(fa.p)
+                fb.v.copy_(fa.v)
+                for p in fb.params:
+                    p._glis_epoch = getattr(p, "_glis_epoch", 0) + 1    # its packs are stale now
+            args = (torch.rand(8, 3, 32, 32, generator=gen).to(DEV), torch.randn(8, 32, generator=gen).to(DEV),
+                    torch.randn(8, 32, generator=gen).to(DEV), 1, 1)
+            outs = []
+            for tr, overlap in ((side, True), (single, False)):
+                ops.Overlap.enabled = overlap
+                o = tr.step(*args)
+                torch.cuda.synchronize()
+                outs.append([o[k].item() for k in ("d_real", "d_fake", "g")] + [r.item() for r in o["r"]])
+            assert np.allclose(outs[0], outs[1], rtol=1e-5), (it, outs)
+            for fa, fb in ((side.gen_flat, single.gen_flat), (side.dis_flat, single.dis_flat)):
+                assert rel_err(fa.g, fb.g) <= 1e-5, it
+    finally:
+        ops.Overlap.enabled = True
