@@ -20,13 +20,24 @@ from .modules.WeightNormalizedConv import _WeightNormalizedConvNd
 __all__ = ["build_discriminator", "build_generator", "GeneratorLearnedInputSpace", "build_reverser"]
 
 
-def run_layers(layers, x):
+def _planes_suffice(consumer, follower, out_shape):
+    """Does the module that consumes a fused pair's output read it through its bf16 planes only?  (Then
+    the pair does not write the fp32 copy of that activation: ops.consumes_planes_only.)"""
+    if not isinstance(consumer, _WeightNormalizedConvNd) or len(out_shape) != 4:
+        return False
+    return ops.consumes_planes_only(consumer._spec(), consumer.weight, out_shape, isinstance(follower, TPReLU))
+
+
+def run_layers(layers, x, following=()):
     """Apply ``layers`` in order, running every (weight-normalized layer, TPReLU) pair as ONE
     operator: the TPReLU moves into the contraction's epilogue (``ops.wn_contraction_tprelu``).
-    Module structure, parameters and results are those of calling the modules one by one."""
+    Module structure, parameters and results are those of calling the modules one by one.
+    ``following``: the modules the caller applies to the result next (only looked at, not run)."""
     layers = list(layers)
+    n_run = len(layers)
+    layers = layers + list(following)
     i = 0
-    while i < len(layers):
+    while i < n_run:
         m = layers[i]
         nxt = layers[i + 1] if i + 1 < len(layers) else None
         fusable = (isinstance(m, (_WeightNormalizedConvNd, WeightNormalizedLinear)) and isinstance(nxt, TPReLU)
@@ -37,12 +48,18 @@ def run_layers(layers, x):
                 and m.bias is None and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() == 2
                 and len(nxt.target_size) == 3 and after.weight.numel() == nxt.target_size[0]
                 and m.out_features == nxt.target_size[0] * nxt.target_size[1] * nxt.target_size[2])
-        if head:
-            x = ops.wn_linear_view_tprelu(x, m.weight, m.scale, after.weight, after.bias, nxt.target_size)
+        if head and i + 3 <= n_run:
+            consumer = layers[i + 3] if i + 3 < len(layers) else None
+            follower = layers[i + 4] if i + 4 < len(layers) else None
+            suffice = _planes_suffice(consumer, follower, (x.shape[0],) + tuple(nxt.target_size))
+            x = ops.wn_linear_view_tprelu(x, m.weight, m.scale, after.weight, after.bias, nxt.target_size, suffice)
             i += 3
-        elif fusable:
+        elif fusable and i + 2 <= n_run:
             spec = m._spec() if isinstance(m, _WeightNormalizedConvNd) else m._spec
-            x = ops.wn_contraction_tprelu(x, m.weight, m.scale, m.bias, nxt.weight, nxt.bias, spec)
+            consumer = layers[i + 2] if i + 2 < len(layers) else None
+            follower = layers[i + 3] if i + 3 < len(layers) else None
+            suffice = x.dim() == 4 and _planes_suffice(consumer, follower, ops.layer_out_shape(x.shape, m.weight, spec))
+            x = ops.wn_contraction_tprelu(x, m.weight, m.scale, m.bias, nxt.weight, nxt.bias, spec, suffice)
             i += 2
         else:
             x = m(x)
@@ -240,6 +257,6 @@ class GeneratorLearnedInputSpace(nn.Module):
         for i in range(self.lis_depth(n_execute_lis_layers)):
             x = x + self.lis_layers[i](x)
             lis_results.append(x)
-        x = run_layers(self.initial_linear, x)
+        x = run_layers(self.initial_linear, x, following=self.conv_layers)
         x = run_layers(self.conv_layers, x)
         return x, lis_results

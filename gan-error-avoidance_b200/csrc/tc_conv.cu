@@ -44,6 +44,8 @@ struct TcConvParams {
   int stages;
   int tiles_h;       // ceil(Hq_max / th)
   int tiles_x;       // pixel tiles per (phase, channel tile) = tiles_h * ceil(N / tn)
+  int a_rows;        // weight rows staged per tile: 128, or 64 when Co <= 64 (the MMA still reads 128 rows: the
+                     // upper 64 are whatever follows in the stage and only feed TMEM lanes nobody reads)
   int tiles_co;      // ceil(Co / 128)
   int total_tiles;   // tiles_x * tiles_co * phases
   int cluster;       // CTAs per cluster (1, 2, 4): the pixel tiles of a cluster share ONE weight tile, each
@@ -152,7 +154,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
 
   // ---- shared memory carve-up (1024-byte aligned operand tiles)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)P.n_mma * 128;
+  const uint32_t a_bytes = (uint32_t)P.a_rows * 128, b_bytes = (uint32_t)P.n_mma * 128;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.stages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -199,7 +201,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + ((P.debug & 4) ? 0u : box_rows * 128u));
       int s = 0; uint32_t parity = 0;
       int tr_n = 0;
-      const uint32_t w_rows = (uint32_t)(TC_BM / cs), w_slice = w_rows * 128u;   // this CTA's share of the weight tile
+      const uint32_t w_rows = (uint32_t)(P.a_rows / cs), w_slice = w_rows * 128u;   // this CTA's share of the weight tile
       for (int grp = cluster_id; grp < P.n_groups; grp += n_clusters) {
         const int id = grp * cs + crank;
         const TcTile tl = tc_tile(P, id);
@@ -350,6 +352,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           case 3: tc_epilogue_chunk<GLIS_ACT_NONE, false, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 7: tc_epilogue_chunk<GLIS_ACT_TPRELU, false, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 6: {   // split K: add this item's partial sums (one 128-byte reduction per warp and column)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -507,6 +510,15 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   }
   P.tw = Wq;
+  // Co <= 64: stage 64 weight rows instead of 128 (smaller stages -> a deeper TMA pipeline)
+  int a_rows = (g->Co <= 64 && cs == 1) ? 64 : TC_BM;
+  int depth_penalty = 0;
+  {
+    const char* e = getenv("GLIS_TC_AROWS");          // tuning knob: 128 = always stage full weight tiles
+    if (e && atoi(e) == 128) a_rows = TC_BM;
+    const char* d = getenv("GLIS_TC_DEPTH_PENALTY");  // tuning knob: % cost added to tiles that leave only 2 stages
+    depth_penalty = d ? atoi(d) : 0;
+  }
   const int kblocks = (g->Ci + TC_BK - 1) / TC_BK;
   const bool plain_out = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
   int ksplit_max = 8;
@@ -534,6 +546,8 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
         const long waves = (tiles * ks + slots - 1) / slots;
         const long steps = (long)ntaps_max * (kblocks / ks) + 4;
         long cost = waves * steps * (n + 128 / cs) + (ks > 1 ? waves * 2 * n + 1024 : 0);
+        const int ar = n >= 64 ? a_rows : TC_BM;
+        if ((219 * 1024) / (256 * (ar + n)) < 3) cost += cost * depth_penalty / 100;
         cost = cost * 1024 + n;   // tie-break: smaller tiles
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; best_tn = tn; best_ks = ks; }
       }
@@ -545,6 +559,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     P.tn = best_tn;
   }
   P.n_mma = round_up(P.tw * P.th * P.tn, 16);
+  P.a_rows = P.n_mma >= 64 ? a_rows : TC_BM;   // (a 128-row MMA read starting in the lo tile must stay inside the stage)
   P.tmem_cols = 64;  // two accumulators of tmem_cols / 2 columns each
   while (P.tmem_cols < 2 * P.n_mma) P.tmem_cols *= 2;
   P.kblocks = (g->Ci + TC_BK - 1) / TC_BK;
@@ -557,7 +572,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.cluster = cs;
   P.ksplit = best_ks;
   P.n_groups = P.total_tiles / cs * best_ks;
-  const size_t stage_bytes = 2 * (size_t)TC_BM * 128 + 2 * (size_t)P.n_mma * 128;
+  const size_t stage_bytes = 2 * (size_t)P.a_rows * 128 + 2 * (size_t)P.n_mma * 128;
   int stages = (int)((219 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: tile does not fit shared memory");
@@ -571,6 +586,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   else if (ep->act == GLIS_ACT_NONE && !ep->preact && !out_f32 && out_hi) P.ep_mode = 3;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && !out_hi) P.ep_mode = 4;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && out_hi) P.ep_mode = 5;
+  else if (ep->act == GLIS_ACT_TPRELU && !ep->preact && !out_f32 && out_hi) P.ep_mode = 7;   // no-grad forward
   if (best_ks > 1) {
     P.ep_mode = 6;
     cudaError_t me = cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)g->N * g->Ho * g->Wo * g->Co, st);
@@ -589,7 +605,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   {
     const uint64_t dims[3] = {(uint64_t)g->Ci, (uint64_t)g->Co, (uint64_t)T};
     const uint64_t strides[2] = {(uint64_t)g->Ci * 2, (uint64_t)g->Ci * g->Co * 2};
-    const uint32_t box[3] = {TC_BK, (uint32_t)(TC_BM / cs), 1};   // one CTA's share of the (multicast) weight tile
+    const uint32_t box[3] = {TC_BK, (uint32_t)(P.a_rows / cs), 1};   // one CTA's share of the (multicast) weight tile
     int rc = make_bf16_map(&mw_hi, w_hi, 3, dims, strides, box);
     if (rc) return rc;
     rc = make_bf16_map(&mw_lo, passes == 3 ? w_lo : w_hi, 3, dims, strides, box);

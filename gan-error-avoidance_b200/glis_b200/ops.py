@@ -21,10 +21,22 @@ def _nhwc(x):
     if x.dtype != torch.float32:
         raise RuntimeError("glis_b200: fp32 tensors required, got %s" % x.dtype)
     if x.dim() == 4:
-        return x.contiguous(memory_format=torch.channels_last)
-    if x.dim() == 2:
-        return x.contiguous()
-    raise RuntimeError("glis_b200: expected a 2-D or 4-D tensor, got %d-D" % x.dim())
+        xc = x.contiguous(memory_format=torch.channels_last)
+    elif x.dim() == 2:
+        xc = x.contiguous()
+    else:
+        raise RuntimeError("glis_b200: expected a 2-D or 4-D tensor, got %d-D" % x.dim())
+    if xc is not x:
+        _require_f32(x, "a layout conversion")
+    return xc
+
+
+def _require_f32(t, what):
+    """Inside a fused chain an activation may exist ONLY as bf16 planes (its fp32 buffer is allocated but
+    never written: ``launch(..., want_f32=False)``); anything that needs the fp32 values must not get one."""
+    if getattr(t, "_glis_f32_invalid", False):
+        raise RuntimeError("glis_b200: %s needs the fp32 values of a planes-only activation "
+                           "(internal planning error)" % what)
 
 
 def _empty_nhwc(n, c, h, w, like):
@@ -351,6 +363,7 @@ def planes_of(t, lo=True):
     tag = getattr(t, "_glis_planes", None)
     if tag is not None and tag[2] == t.data_ptr() and tag[3] == t._version and (tag[1] is not None or not lo):
         return tag[0], tag[1]
+    _require_f32(t, "a bf16 split")
     return split_bf16(t, lo)
 
 
@@ -427,6 +440,7 @@ def unfolded_planes(x, lo=True):
     tag = getattr(x, "_glis_unfolded", None)
     if tag is not None and tag[2] == x.data_ptr() and tag[3] == x._version and (tag[1] is not None or not lo):
         return tag[0], tag[1]
+    _require_f32(x, "an unfold")
     n, c, h, w = x.shape
     hi = torch.empty((n, h // 2, w // 2, 16 * c), device=x.device, dtype=torch.bfloat16)
     lo_t = torch.empty_like(hi) if lo else None
@@ -439,7 +453,7 @@ def unfolded_planes(x, lo=True):
 
 
 def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
-                       want_preact, want_planes):
+                       want_preact, want_planes, want_f32=True):
     """The two image-side launches as 1x1 tensor-core products (see image_side_mode)."""
     prec = spec.precision
     lo = prec == L.PREC_BF16X3
@@ -459,11 +473,14 @@ def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bia
             planes = (torch.empty_like(out, dtype=torch.bfloat16),
                       torch.empty_like(out, dtype=torch.bfloat16) if lo else None)
         wp = pw.mat
+        skip_f32 = planes is not None and not want_f32       # the consumer reads the planes only
         ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None)
         with L.timed("image_side unfold M=%d N=%d K=%d tc" % (n * ho * wo, co, j)):
             L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]), L.ptr16(wp[1]),
-                   C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
+                   C.byref(ep), None if skip_f32 else L.ptr(out), L.ptr16(planes[0]) if planes else None,
                    L.ptr16(planes[1]) if planes else None, prec, L.stream())
+        if skip_f32:
+            out._glis_f32_invalid = True
         return out, preact, planes
     # fold: cols[pix][j] = sum_ci x[pix][ci] * E^T[j][ci];  out = fold(cols) + bias
     xp = planes_of(x, lo)
@@ -481,12 +498,14 @@ def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bia
 
 
 def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_NONE, act_a=None, act_b=None,
-           want_preact=False, want_planes=False):
+           want_preact=False, want_planes=False, want_f32=True):
     """One gather-GEMM launch (tensor cores when the geometry tiles, FFMA otherwise).
 
     ``x``: fp32 NHWC-dense (or 2-D) input; ``forward_pack`` selects the layer's forward
     ([T][Cout][Cin] K-major / [T][Cin][Cout] fp32) or data-gradient packs.
-    Returns (out_fp32, preact or None, (hi, lo) planes of out or None).
+    Returns (out_fp32, preact or None, (hi, lo) planes of out or None).  ``want_f32=False`` (the caller
+    knows that every consumer of the output reads its planes): a tensor-core launch that writes planes
+    leaves the fp32 buffer unwritten and marks it ``_glis_f32_invalid``.
     """
     in_shape = tuple(x.shape)
     prec = spec.precision
@@ -498,7 +517,7 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         mode = None
     if mode is not None:
         return _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
-                                  want_preact, want_planes)
+                                  want_preact, want_planes, want_f32)
     like = x._glis_planes_only[0] if isinstance(x, PlanesOnly) else x
     g, out = _launch_geom(spec, relation, in_shape, out_shape, like)
     preact = torch.empty_like(out) if want_preact else None
@@ -511,15 +530,19 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         pw.need_bf16(forward_pack, not forward_pack, lo)
         wp = pw.fwd if forward_pack else pw.bwd
         xp = planes_of(x, lo)
+        skip_f32 = planes is not None and not want_f32
         ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None,
                         spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0)
         with L.timed(_tag(relation, g) + " tc"):
             L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
-                   L.ptr16(wp[1]), C.byref(ep), L.ptr(out), L.ptr16(planes[0]) if planes else None,
-                   L.ptr16(planes[1]) if planes else None, prec, L.stream())
+                   L.ptr16(wp[1]), C.byref(ep), None if skip_f32 else L.ptr(out),
+                   L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None, prec, L.stream())
+        if skip_f32:
+            out._glis_f32_invalid = True
     else:
         if isinstance(x, PlanesOnly):
             raise RuntimeError("glis_b200: planes-only gradient reached an fp32 kernel (internal planning error)")
+        _require_f32(x, "an fp32 contraction")
         pw.need_fp32(forward_pack, not forward_pack)
         wp = pw.io if forward_pack else pw.oi
         ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact),
@@ -557,6 +580,13 @@ def _layer_shapes(xc, weight, spec):
         raise RuntimeError("glis_b200: input has %d channels, weight expects %d"
                            % (ci, weight.shape[1 - out_axis]))
     return shape
+
+
+def layer_out_shape(x_shape, weight, spec):
+    """NCHW shape of a 4-D WN layer's output for an input of shape ``x_shape``."""
+    n, _, h, w = x_shape
+    ho, wo = spec.out_hw(h, w)
+    return (n, weight.shape[1 if spec.transposed else 0], ho, wo)
 
 
 def _dense_grad(p):
@@ -698,6 +728,32 @@ def _image_side_wgrad(spec, x_shape, dy_shape):
     return (n, ho, wo, cout, cin) if ok else None
 
 
+def consumes_planes_only(spec, weight, x_shape, followed_by_tprelu):
+    """True when a WN layer with this ``spec`` / ``weight`` reads an input of (NCHW) shape ``x_shape`` through
+    its bf16 planes ONLY — forward on tcgen05 (or as the image-side "fold" product) and weight gradient on
+    tcgen05 too — so that whoever produces that input need not write its fp32 copy."""
+    if spec.precision == L.PREC_FP32 or len(x_shape) != 4 or spec.perm is not None:
+        return False
+    out_axis = 1 if spec.transposed else 0
+    n, cin, h, w = x_shape
+    if cin != weight.shape[1 - out_axis]:
+        return False
+    cout = weight.shape[out_axis]
+    ho, wo = spec.out_hw(h, w)
+    out_shape = (n, cout, ho, wo)
+    rel = L.TCONV if spec.transposed else L.CONV
+    mode = image_side_mode(spec, rel, tuple(x_shape), out_shape)
+    if mode == "fold" and followed_by_tprelu:
+        mode = None                      # launch() sends a TPReLU epilogue down the generic path
+    if mode == "unfold" or (mode is None and not _use_tc(spec, rel, tuple(x_shape), out_shape)):
+        return False
+    if _image_side_wgrad(spec, tuple(x_shape), out_shape) is not None:
+        return spec.transposed           # transposed: x is the small operand (planes); conv: unfold(x) reads fp32
+    g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin) if spec.transposed else \
+        spec.geom(L.CONV, n, h, w, cin, ho, wo, cout)
+    return bool(L.load().glis_wgrad_tc_supported(C.byref(g)))
+
+
 def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale, need_dbias, bias_shape,
                     pw_bias=None):
     """dgrad + wgrad + weight-norm projection + bias gradient of one WN layer.
@@ -762,10 +818,13 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                     L.call("glis_conv_wgrad_bf16", C.byref(g), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
                            L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
             elif spec.perm is not None:
+                _require_f32(big, "an fp32 weight gradient")
                 with L.timed(tag + " fp32 (permuted rows)"):
                     L.call("glis_linear_wgrad", L.ptr(small), L.ptr(big), L.ptr(graw), n, cout, cin, spec.perm[0],
                            spec.perm[1], L.stream())
             else:
+                _require_f32(small, "an fp32 weight gradient")
+                _require_f32(big, "an fp32 weight gradient")
                 with L.timed(tag + " fp32"):
                     L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
                            L.stream())
@@ -823,6 +882,7 @@ class WNContraction(torch.autograd.Function):
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
         ctx.x_unfolded = getattr(xc, "_glis_unfolded", None)
+        ctx.x_f32_invalid = getattr(xc, "_glis_f32_invalid", False)
         ctx.save_for_backward(xc)
         return out
 
@@ -833,6 +893,8 @@ class WNContraction(torch.autograd.Function):
             xc._glis_planes = ctx.x_planes
         if ctx.x_unfolded is not None:
             xc._glis_unfolded = ctx.x_unfolded
+        if ctx.x_f32_invalid:
+            xc._glis_f32_invalid = True
         dyc = _nhwc(dy)
         ni = ctx.needs_input_grad
         dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dyc, None, ni[0], ni[1],
@@ -853,7 +915,9 @@ class WNContractionTPReLU(torch.autograd.Function):
     Reference: the (conv, tprelu) pairs of common/model.py:31-45, :112-127, :222-251."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, bias, a_raw, b_t, spec):
+    def forward(ctx, x, weight, scale, bias, a_raw, b_t, spec, flags=(True, True)):
+        # flags = (a backward may follow: keep the pre-activation, some consumer reads the fp32 output)
+        need_bwd, want_f32 = flags
         xc = _nhwc(x)
         shape = _layer_shapes(xc, weight, spec)
         pw = packed_weights(weight, scale, spec)
@@ -861,13 +925,15 @@ class WNContractionTPReLU(torch.autograd.Function):
         rel_f = L.TCONV if spec.transposed else L.CONV
         out, preact, planes = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_TPRELU,
                                      act_a=a_raw.detach().contiguous(), act_b=b_t.detach().contiguous(),
-                                     want_preact=True,
-                                     want_planes=True)
+                                     want_preact=need_bwd, want_planes=True, want_f32=want_f32)
+        _ELIDED[0] = getattr(out, "_glis_f32_invalid", False)
         ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
         ctx.x_unfolded = getattr(xc, "_glis_unfolded", None)
-        ctx.save_for_backward(xc, preact, a_raw, b_t)
+        ctx.x_f32_invalid = getattr(xc, "_glis_f32_invalid", False)
+        if need_bwd:
+            ctx.save_for_backward(xc, preact, a_raw, b_t)
         ctx.set_materialize_grads(False)   # no zero tensors for the (non-differentiable) plane outputs
         if planes is None:
             return out, None, None
@@ -883,6 +949,8 @@ class WNContractionTPReLU(torch.autograd.Function):
             xc._glis_planes = ctx.x_planes
         if ctx.x_unfolded is not None:
             xc._glis_unfolded = ctx.x_unfolded
+        if ctx.x_f32_invalid:
+            xc._glis_f32_invalid = True
         spec = ctx.spec
         c = a_raw.numel()
         if dout is None:
@@ -919,13 +987,26 @@ class WNContractionTPReLU(torch.autograd.Function):
         dx, dw, dscale, dbias = _layer_backward(spec, ctx.pw, xc, dy, (dy_hi, dy_lo) if want_planes else None,
                                                 ni[0], ni[1], ctx.pw.scale is not None and ni[2],
                                                 ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)
-        return dx, dw, dscale, dbias, da, db, None
+        return dx, dw, dscale, dbias, da, db, None, None
 
 
-def wn_contraction_tprelu(x, weight, scale, bias, a_raw, b_t, spec):
-    out, hi, lo = WNContractionTPReLU.apply(x, weight, scale, bias, a_raw, b_t, spec)
+_ELIDED = [False]    # did the last fused forward leave its fp32 output unwritten (see launch)
+
+
+def _may_need_backward(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def wn_contraction_tprelu(x, weight, scale, bias, a_raw, b_t, spec, planes_suffice=False):
+    """``planes_suffice``: the caller guarantees that the result is consumed through its bf16 planes only
+    (see ``consumes_planes_only``); its fp32 buffer may then stay unwritten."""
+    need_bwd = _may_need_backward(x, weight, scale, bias, a_raw, b_t)
+    out, hi, lo = WNContractionTPReLU.apply(x, weight, scale, bias, a_raw, b_t, spec,
+                                            (need_bwd, not planes_suffice))
     if hi is not None:
         attach_planes(out, (hi, lo))
+    if _ELIDED[0]:
+        out._glis_f32_invalid = True
     return out
 
 
@@ -939,16 +1020,19 @@ class WNLinearViewTPReLU(torch.autograd.Function):
     weight gradient written back to master rows."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, a_raw, b_t, spec, view):
+    def forward(ctx, x, weight, scale, a_raw, b_t, spec, view, flags=(True, True)):
+        need_bwd, want_f32 = flags
         xc = _nhwc(x)
         c, h, w = view
         n, n_out = xc.shape[0], weight.shape[0]
         pw = packed_weights(weight, scale, spec)
         out, preact, planes = launch(spec, L.CONV, xc, (n, n_out), pw, forward_pack=True, act=L.ACT_TPRELU,
                                      act_a=a_raw.detach().contiguous(), act_b=b_t.detach().contiguous(),
-                                     want_preact=True, want_planes=True)
+                                     want_preact=need_bwd, want_planes=True, want_f32=want_f32)
+        _ELIDED[0] = getattr(out, "_glis_f32_invalid", False)
         ctx.spec, ctx.pw, ctx.view = spec, pw, view
-        ctx.save_for_backward(xc, preact, a_raw, b_t)
+        if need_bwd:
+            ctx.save_for_backward(xc, preact, a_raw, b_t)
         ctx.set_materialize_grads(False)
         as_map = lambda t: t.view(n, h, w, c).permute(0, 3, 1, 2)     # NHWC memory, logical (N, C, h, w)
         if planes is None:
@@ -986,16 +1070,21 @@ class WNLinearViewTPReLU(torch.autograd.Function):
             da = db = None
         dx, dw, dscale, _ = _layer_backward(spec, ctx.pw, xc, dy, None, ni[0], ni[1],
                                             ctx.pw.scale is not None and ni[2], False, None)
-        return dx, dw, dscale, da, db, None, None
+        return dx, dw, dscale, da, db, None, None, None
 
 
-def wn_linear_view_tprelu(x, weight, scale, a_raw, b_t, view):
-    """See WNLinearViewTPReLU.  ``view`` = (C, h, w) of the View module between the linear and the TPReLU."""
+def wn_linear_view_tprelu(x, weight, scale, a_raw, b_t, view, planes_suffice=False):
+    """See WNLinearViewTPReLU.  ``view`` = (C, h, w) of the View module between the linear and the TPReLU;
+    ``planes_suffice`` as in ``wn_contraction_tprelu``."""
     c, h, w = (int(v) for v in view)
     spec = ContractionSpec(False, (1, 1), (1, 1), (0, 0), (1, 1), linear=True, perm=(c, h * w))
-    out, hi, lo = WNLinearViewTPReLU.apply(x, weight, scale, a_raw, b_t, spec, (c, h, w))
+    need_bwd = _may_need_backward(x, weight, scale, a_raw, b_t)
+    out, hi, lo = WNLinearViewTPReLU.apply(x, weight, scale, a_raw, b_t, spec, (c, h, w),
+                                           (need_bwd, not planes_suffice))
     if hi is not None:
         attach_planes(out, (hi, lo))
+    if _ELIDED[0]:
+        out._glis_f32_invalid = True
     return out
 
 
