@@ -61,6 +61,11 @@ def run_layers(layers, x, following=()):
             suffice = x.dim() == 4 and _planes_suffice(consumer, follower, ops.layer_out_shape(x.shape, m.weight, spec))
             x = ops.wn_contraction_tprelu(x, m.weight, m.scale, m.bias, nxt.weight, nxt.bias, spec, suffice)
             i += 2
+        elif (isinstance(m, _WeightNormalizedConvNd) and type(nxt) is nn.Sigmoid and i + 2 <= n_run
+              and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() == 4):
+            # the generators' last two modules: the sigmoid moves into the contraction's epilogue
+            x = ops.wn_contraction_sigmoid(x, m.weight, m.scale, m.bias, m._spec())
+            i += 2
         else:
             x = m(x)
             i += 1

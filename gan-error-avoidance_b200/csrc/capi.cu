@@ -21,6 +21,7 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
 int simt_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st);
 
 int tc_conv_supported(const glis_geom_t* g);
+int tc_conv_plan_ksplit(const glis_geom_t* g);
 int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
@@ -75,6 +76,11 @@ extern "C" int glis_conv_wgrad(const glis_geom_t* g, const float* small, const f
 extern "C" int glis_conv_tc_supported(const glis_geom_t* g) {
   if (validate_geom(g, "glis_conv_tc_supported") != GLIS_OK) return 0;
   return tc_conv_supported(g);
+}
+
+extern "C" int glis_conv_tc_ksplit(const glis_geom_t* g) {
+  if (validate_geom(g, "glis_conv_tc_ksplit") != GLIS_OK) return 1;
+  return tc_conv_plan_ksplit(g);
 }
 
 extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x_lo, const void* w_hi,

@@ -26,6 +26,40 @@ tprelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
   }
 }
 
+// NHWC TPReLU forward writing fp32 and/or bf16 hi/lo planes, four consecutive channels per thread.
+__global__ void __launch_bounds__(PW_NT)
+tprelu_fwd_planes_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
+                         float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                         int64_t numel, int C, int CA) {
+  const int64_t n4 = numel >> 2;   // C % 4 == 0: a group of four never straddles a pixel
+  for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < n4; q += (int64_t)gridDim.x * PW_NT) {
+    const float4 v = reinterpret_cast<const float4*>(x)[q];
+    const int c0 = (int)((q * 4) % C);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (c0 + j) % CA;
+      const float bb = __ldg(b + c), a = clamp01(__ldg(a_raw + c));
+      const float t = o[j] - bb;
+      o[j] = (t > 0.f ? t : a * t) + bb;
+      sm100::split_bf16(o[j], h[j], l[j]);
+    }
+    if (out) reinterpret_cast<float4*>(out)[q] = make_float4(o[0], o[1], o[2], o[3]);
+    if (hi) reinterpret_cast<uint2*>(hi)[q] = *reinterpret_cast<uint2*>(h);
+    if (lo) reinterpret_cast<uint2*>(lo)[q] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// dy = dout * s * (1 - s): the backward of a sigmoid fused into a contraction's epilogue.
+__global__ void __launch_bounds__(PW_NT)
+sigmoid_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dout, float* __restrict__ dy, int64_t numel) {
+  for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
+    const float v = s[i];
+    dy[i] = dout[i] * v * (1.f - v);
+  }
+}
+
 // Adds `v` into acc[c]; when the whole warp targets one channel the warp reduces first.
 __device__ __forceinline__ void channel_accumulate(float* acc, int c, float v, bool active) {
   const unsigned full = 0xffffffffu;
@@ -324,6 +358,31 @@ extern "C" int glis_tprelu_forward(const float* x, const float* a_raw, const flo
   if (numel == 0) return GLIS_OK;
   tprelu_fwd_kernel<<<pw_blocks(numel), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, out, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_tprelu_forward");
+  return GLIS_OK;
+}
+
+extern "C" int glis_sigmoid_backward(const float* s, const float* dout, float* dy, int64_t numel, void* stream) {
+  GLIS_REQUIRE(s && dout && dy && numel >= 0, GLIS_E_BADARG, "glis_sigmoid_backward: bad arguments");
+  if (numel == 0) return GLIS_OK;
+  sigmoid_bwd_kernel<<<pw_blocks(numel), PW_NT, 0, (cudaStream_t)stream>>>(s, dout, dy, numel);
+  GLIS_CHECK_LAUNCH("glis_sigmoid_backward");
+  return GLIS_OK;
+}
+
+extern "C" int glis_tprelu_forward_planes(const float* x, const float* a_raw, const float* b, float* out,
+                                          void* out_hi, void* out_lo, int64_t numel, int C, int act_channels,
+                                          void* stream) {
+  GLIS_REQUIRE(x && a_raw && b && (out || out_hi), GLIS_E_BADARG, "glis_tprelu_forward_planes: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && act_channels >= 0, GLIS_E_BADARG, "glis_tprelu_forward_planes: bad sizes");
+  GLIS_REQUIRE(C % 4 == 0 && numel % C == 0, GLIS_E_UNSUPPORTED,
+               "glis_tprelu_forward_planes: C must be a multiple of 4 and numel a multiple of C");
+  GLIS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 7) == 0,
+               GLIS_E_BADARG, "glis_tprelu_forward_planes: misaligned buffer");
+  if (numel == 0) return GLIS_OK;
+  tprelu_fwd_planes_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+      x, a_raw, b, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C, act_channels > 0 ? act_channels : C);
+  GLIS_CHECK_LAUNCH("glis_tprelu_forward_planes");
   return GLIS_OK;
 }
 

@@ -469,14 +469,21 @@ int tc_conv_supported(const glis_geom_t* g) {
   return 1;
 }
 
-int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
-                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
-                    __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st) {
-  GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: geometry not tileable for tcgen05");
-  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
-  GLIS_REQUIRE(x_hi && w_hi && (passes == 1 || (x_lo && w_lo)), GLIS_E_BADARG,
-               "glis_conv_forward_bf16: missing hi/lo operand planes");
-  TcConvParams P;
+static int tc_num_sms() {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  return num_sms;
+}
+
+// Tile shape, K split and work-item counts of one launch (everything that does not depend on the
+// operand pointers).  `plain_out`: the launch writes fp32 sums only (no activation, pre-activation or
+// planes), which is what allows a K split.
+static int tc_plan(const glis_geom_t* g, bool plain_out, TcConvParams& P) {
   P.g = *g;
   int nphase = 1, Hq = g->Ho, Wq = g->Wo;
   if (g->relation == GLIS_TCONV) {
@@ -488,13 +495,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   // The main loop is bound by shared-memory traffic — per k-step the MMAs read 128 weight rows plus
   // N pixel rows — and by how evenly the tiles fill the SMs, so pick the shape that minimises
   //   waves(tiles / #SMs) x (N + 128).
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = tc_num_sms();
   static int nmax_cfg = 0;
   if (!nmax_cfg) {
     const char* e = getenv("GLIS_TC_NMAX");   // tuning knob: upper bound on columns per tile (16..256)
@@ -520,8 +521,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     depth_penalty = d ? atoi(d) : 0;
   }
   const int kblocks = (g->Ci + TC_BK - 1) / TC_BK;
-  const bool plain_out = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
-  int ksplit_max = 8;
+  int ksplit_max = 32;
   {
     const char* e = getenv("GLIS_TC_KSPLIT");   // tuning knob: upper bound on the K split (1 = off)
     if (e) ksplit_max = atoi(e);
@@ -542,9 +542,11 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
       const long tiles = tiles_x * co_tiles * nphase;
       const long slots = num_sms / cs * cs;
       for (int ks = 1; ks <= ksplit_max && ks <= kblocks; ks *= 2) {
-        if (ks > 1 && (!plain_out || cs > 1 || kblocks % ks != 0)) break;
+        if (ks > 1 && (!plain_out || cs > 1)) break;
+        // uneven shares are fine (tc_tile cuts the blocks proportionally) once every share has a few blocks
+        if (ks > 1 && kblocks % ks != 0 && kblocks < 4 * ks) break;
         const long waves = (tiles * ks + slots - 1) / slots;
-        const long steps = (long)ntaps_max * (kblocks / ks) + 4;
+        const long steps = (long)ntaps_max * ((kblocks + ks - 1) / ks) + 4;
         long cost = waves * steps * (n + 128 / cs) + (ks > 1 ? waves * 2 * n + 1024 : 0);
         const int ar = n >= 64 ? a_rows : TC_BM;
         if ((219 * 1024) / (256 * (ar + n)) < 3) cost += cost * depth_penalty / 100;
@@ -563,7 +565,6 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.tmem_cols = 64;  // two accumulators of tmem_cols / 2 columns each
   while (P.tmem_cols < 2 * P.n_mma) P.tmem_cols *= 2;
   P.kblocks = (g->Ci + TC_BK - 1) / TC_BK;
-  P.passes = passes;
   P.tiles_h = (Hq + P.th - 1) / P.th;
   const int tiles_n = (g->N + P.tn - 1) / P.tn;
   P.tiles_x = (P.tiles_h * tiles_n + cs - 1) / cs * cs;   // padded: the tiles of a cluster share (phase, channel tile)
@@ -572,6 +573,35 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   P.cluster = cs;
   P.ksplit = best_ks;
   P.n_groups = P.total_tiles / cs * best_ks;
+  return GLIS_OK;
+}
+
+// The K split a plain-output launch of this geometry would use (1 = none): lets the host decide to run a
+// fused-epilogue layer as split-K sums + one pointwise pass when its tiles alone cannot fill the machine.
+int tc_conv_plan_ksplit(const glis_geom_t* g) {
+  if (!tc_conv_supported(g)) return 1;
+  TcConvParams P;
+  if (tc_plan(g, true, P) != GLIS_OK) return 1;
+  return P.ksplit;
+}
+
+int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                    const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                    __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st) {
+  GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: geometry not tileable for tcgen05");
+  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
+  GLIS_REQUIRE(x_hi && w_hi && (passes == 1 || (x_lo && w_lo)), GLIS_E_BADARG,
+               "glis_conv_forward_bf16: missing hi/lo operand planes");
+  TcConvParams P;
+  {
+    const bool plain = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
+    int rc = tc_plan(g, plain, P);
+    if (rc != GLIS_OK) return rc;
+  }
+  const int cs = P.cluster;
+  const int best_ks = P.ksplit;
+  const int num_sms = tc_num_sms();
+  P.passes = passes;
   const size_t stage_bytes = 2 * (size_t)P.a_rows * 128 + 2 * (size_t)P.n_mma * 128;
   int stages = (int)((219 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -395,14 +395,32 @@ def _use_tc(spec, relation, in_shape, out_shape):
     if spec.precision == L.PREC_FP32:
         return False
     if len(in_shape) != 4:
-        # batch-sized linears stay on the FFMA kernel — except the FORWARD of a wide linear that feeds a
-        # feature map (spec.perm): 100+ channel tiles of 128 x batch, the fused TPReLU epilogue writes planes
-        if spec.perm is None or relation != L.CONV or len(in_shape) != 2:
+        # batch-sized linears stay on the FFMA kernel — except the wide linear that feeds a feature map
+        # (spec.perm).  Forward: 100+ channel tiles of 128 x batch, the fused TPReLU epilogue writes planes;
+        # data gradient: a 12800-deep contraction into 256 columns, split 32 ways over K
+        if spec.perm is None or len(in_shape) != 2:
             return False
         return tc_supported(spec.geom(relation, in_shape[0], 1, 1, in_shape[1], 1, 1, out_shape[1]))
     n, ci, hi, wi = in_shape
     _, co, ho, wo = out_shape
     return tc_supported(spec.geom(relation, n, hi, wi, ci, ho, wo, co))
+
+
+SPLIT_K_FORWARD = os.environ.get("GLIS_SPLIT_K_FORWARD", "1") != "0"
+
+
+def _split_k_forward(g, relation):
+    """Run a TPReLU-epilogue launch as split-K sums + one pointwise pass?  Yes when the kernel's own plan
+    would split a plain-output launch of this geometry at least 4 ways, or 2 ways over a deep contraction
+    (>= 64 k-steps): few pixels and a deep K — D's last level — whose tiles alone leave most SMs idle.
+    Measured (tools/tc_microbench.py k1 k8): 256->512 5x5 at batch 64 48.9 -> 25.3 us, at 128 49.6 -> 39.3 us."""
+    if not SPLIT_K_FORWARD:
+        return False
+    ks = int(L.load().glis_conv_tc_ksplit(C.byref(g)))
+    if ks >= 4:
+        return True
+    taps = g.KH * g.KW if relation == L.CONV else -(-g.KH // g.stride_h) * -(-g.KW // g.stride_w)
+    return ks >= 2 and taps * ((g.Ci + 63) // 64) >= 64
 
 
 _SPEC_1X1 = None
@@ -531,12 +549,24 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         wp = pw.fwd if forward_pack else pw.bwd
         xp = planes_of(x, lo)
         skip_f32 = planes is not None and not want_f32
-        ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None,
-                        spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0)
-        with L.timed(_tag(relation, g) + " tc"):
-            L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
-                   L.ptr16(wp[1]), C.byref(ep), None if skip_f32 else L.ptr(out),
-                   L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None, prec, L.stream())
+        act_ch = spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0
+        if act == L.ACT_TPRELU and planes is not None and g.Co % 4 == 0 and _split_k_forward(g, relation):
+            # split-K sums (+ bias) into the pre-activation buffer, then TPReLU + planes as one pointwise pass
+            sums = preact if preact is not None else torch.empty_like(out)
+            ep = L.Epilogue(L.ptr(bias), L.ACT_NONE, None, None, None, None, None, 0)
+            with L.timed(_tag(relation, g) + " tc"):
+                L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
+                       L.ptr16(wp[1]), C.byref(ep), L.ptr(sums), None, None, prec, L.stream())
+            L.call("glis_tprelu_forward_planes", L.ptr(sums), L.ptr(act_a), L.ptr(act_b),
+                   None if skip_f32 else L.ptr(out), L.ptr16(planes[0]), L.ptr16(planes[1]), sums.numel(), g.Co,
+                   act_ch, L.stream())
+        else:
+            ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None, act_ch)
+            with L.timed(_tag(relation, g) + " tc"):
+                L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
+                       L.ptr16(wp[1]), C.byref(ep), None if skip_f32 else L.ptr(out),
+                       L.ptr16(planes[0]) if planes else None, L.ptr16(planes[1]) if planes else None, prec,
+                       L.stream())
         if skip_f32:
             out._glis_f32_invalid = True
     else:
@@ -907,6 +937,50 @@ def wn_contraction(x, weight, scale, bias, spec):
     return WNContraction.apply(x, weight, scale, bias, spec)
 
 
+class WNContractionSigmoid(torch.autograd.Function):
+    """A WN layer followed by ``nn.Sigmoid`` — the last two modules of the generators (common/model.py:131-136,
+    :256-259) — with the sigmoid in the contraction's epilogue (for the 3-channel image layer: in the fold
+    kernel).  Backward: ``dy = dout * s * (1 - s)`` from the saved output, then the layer's backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, bias, spec):
+        xc = _nhwc(x)
+        shape = _layer_shapes(xc, weight, spec)
+        pw = packed_weights(weight, scale, spec)
+        b = None if bias is None else bias.detach().reshape(-1).contiguous()
+        rel_f = L.TCONV if spec.transposed else L.CONV
+        out, _, _ = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_SIGMOID)
+        ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.x_planes = getattr(xc, "_glis_planes", None)
+        ctx.x_unfolded = getattr(xc, "_glis_unfolded", None)
+        ctx.x_f32_invalid = getattr(xc, "_glis_f32_invalid", False)
+        ctx.save_for_backward(xc, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, s = ctx.saved_tensors
+        if ctx.x_planes is not None:
+            xc._glis_planes = ctx.x_planes
+        if ctx.x_unfolded is not None:
+            xc._glis_unfolded = ctx.x_unfolded
+        if ctx.x_f32_invalid:
+            xc._glis_f32_invalid = True
+        dout_c = _nhwc(dout)
+        dy = torch.empty_like(s)
+        L.call("glis_sigmoid_backward", L.ptr(s), L.ptr(dout_c), L.ptr(dy), s.numel(), L.stream())
+        ni = ctx.needs_input_grad
+        dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dy, None, ni[0], ni[1],
+                                                ctx.pw.scale is not None and ni[2],
+                                                ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)
+        return dx, dw, dscale, dbias, None
+
+
+def wn_contraction_sigmoid(x, weight, scale, bias, spec):
+    return WNContractionSigmoid.apply(x, weight, scale, bias, spec)
+
+
 class WNContractionTPReLU(torch.autograd.Function):
     """A WN layer followed by TPReLU as ONE forward kernel: the GEMM epilogue applies the bias and
     the translated PReLU, stores the pre-activation for backward and (tensor-core mode) the bf16
@@ -1053,6 +1127,11 @@ class WNLinearViewTPReLU(torch.autograd.Function):
         doc = dout.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(n, -1)
         ni = ctx.needs_input_grad
         dy = torch.empty_like(preact)
+        # the data gradient runs on tensor cores (split-K over the 12800 features): dy also as planes
+        tc_dx = ni[0] and _use_tc(spec, L.TCONV, tuple(preact.shape), tuple(xc.shape))
+        lo = spec.precision == L.PREC_BF16X3
+        dy_hi = torch.empty_like(preact, dtype=torch.bfloat16) if tc_dx else None
+        dy_lo = torch.empty_like(preact, dtype=torch.bfloat16) if (tc_dx and lo) else None
         ga, gb = _dense_grad(a_raw), _dense_grad(b_t)
         want_ab = ni[3] or ni[4]
         direct = ga is not None and gb is not None and ni[3] and ni[4]
@@ -1064,11 +1143,11 @@ class WNLinearViewTPReLU(torch.autograd.Function):
             da = torch.zeros(c, device=doc.device, dtype=torch.float32)
             db = torch.zeros(c, device=doc.device, dtype=torch.float32)
         L.call("glis_tprelu_backward_planes", L.ptr(preact), L.ptr(a_raw.detach()), L.ptr(b_t.detach()), L.ptr(doc),
-               L.ptr(dy), None, None, L.ptr(da), L.ptr(db), preact.numel(), c, 1, L.stream())
+               L.ptr(dy), L.ptr16(dy_hi), L.ptr16(dy_lo), L.ptr(da), L.ptr(db), preact.numel(), c, 1, L.stream())
         if direct:
             _touch_hooks(a_raw, b_t)
             da = db = None
-        dx, dw, dscale, _ = _layer_backward(spec, ctx.pw, xc, dy, None, ni[0], ni[1],
+        dx, dw, dscale, _ = _layer_backward(spec, ctx.pw, xc, dy, (dy_hi, dy_lo) if tc_dx else None, ni[0], ni[1],
                                             ctx.pw.scale is not None and ni[2], False, None)
         return dx, dw, dscale, da, db, None, None, None
 

@@ -138,6 +138,10 @@ int glis_wn_prepare_bf16(const float* w, const float* scale, int out_axis, int C
 /* 1 if glis_conv_forward_bf16 can tile this geometry (Ci % 8 == 0 and >= 32 or a multiple of 64, no dilation, input
  * divisible by the stride for GLIS_CONV, output rows <= 256 pixels, Cout >= 32), else 0. */
 int glis_conv_tc_supported(const glis_geom_t* g);
+/* The K split (1 = none) glis_conv_forward_bf16 would use for a PLAIN-output launch (fp32 sums only) of this
+ * geometry.  A caller whose fused-epilogue launch cannot fill the machine with its tiles alone (few pixels,
+ * deep K: D's last level at batch 64) may then run it as split-K sums + glis_tprelu_forward_planes. */
+int glis_conv_tc_ksplit(const glis_geom_t* g);
 
 /* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
  * TMEM, epilogue fused.  x planes [N,Hi,Wi,Ci] bf16, w packs [KH*KW][Co][Ci] bf16.  Outputs
@@ -184,6 +188,14 @@ int glis_wn_pack_matrix_bf16(const float* w, const float* scale, const float* no
  * (i / inner) % C  (inner = 1 for NHWC and (B,C); H*W for NCHW-contiguous). a_raw is clamped here. */
 int glis_tprelu_forward(const float* x, const float* a_raw, const float* b, float* out,
                         int64_t numel, int C, int inner, void* stream);
+/* TPReLU forward of an NHWC / (B,C) tensor of pre-activations x (channel of element i = (i % C) % act_channels,
+ * act_channels = 0 meaning C) writing the fp32 result (out may be NULL) and/or its bf16 hi/lo planes (hi may be
+ * NULL; lo may be NULL): the epilogue of a split-K tensor-core launch, as one pointwise pass. */
+int glis_tprelu_forward_planes(const float* x, const float* a_raw, const float* b, float* out, void* out_hi,
+                               void* out_lo, int64_t numel, int C, int act_channels, void* stream);
+/* dy = dout * s * (1 - s), s = the sigmoid a contraction's epilogue applied (GLIS_ACT_SIGMOID): backward of the
+ * nn.Sigmoid that ends the generators (common/model.py:136, :259), same element order for all three. */
+int glis_sigmoid_backward(const float* s, const float* dout, float* dy, int64_t numel, void* stream);
 /* dx = dout*(t<=0 ? clamp(a) : 1); da_raw += sum dout*t*[t<=0]*[0<=a_raw<=1]; db += sum dout*[t<=0]*(1-clamp(a)). */
 int glis_tprelu_backward(const float* x, const float* a_raw, const float* b, const float* dout,
                          float* dx, float* da, float* db, int64_t numel, int C, int inner,

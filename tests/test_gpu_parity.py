@@ -783,3 +783,137 @@ def test_side_stream_overlap_matches_single_stream(precision):
                 assert rel_err(fa.g, fb.g) <= 1e-5, it
     finally:
         ops.Overlap.enabled = True
+
+
+# ---------------------------------------------------------------- split-K forward, planes-only activations
+def test_tprelu_forward_planes_kernel_matches_torch():
+    """glis_tprelu_forward_planes (the pointwise epilogue of a split-K launch) against torch, incl. the
+    generator head's channel = feature % C indexing."""
+    import torch.nn.functional as F
+    from glis_b200 import _lib as L
+    g = torch.Generator().manual_seed(41)
+    for (pix, c, ca) in ((50, 512, 0), (7, 8, 0), (6, 240, 16)):
+        x = torch.randn(pix, c, generator=g).to(DEV)
+        cc = ca or c
+        a, b = (torch.rand(cc, generator=g) * 1.4 - 0.2).to(DEV), (torch.randn(cc, generator=g) * 0.3).to(DEV)
+        out = torch.empty_like(x)
+        hi, lo = torch.empty_like(x, dtype=torch.bfloat16), torch.empty_like(x, dtype=torch.bfloat16)
+        L.call("glis_tprelu_forward_planes", L.ptr(x), L.ptr(a), L.ptr(b), L.ptr(out), L.ptr16(hi), L.ptr16(lo),
+               x.numel(), c, ca, L.stream())
+        idx = torch.arange(c, device=DEV) % cc
+        t = x - b[idx]
+        want = torch.where(t > 0, t, a.clamp(0, 1)[idx] * t) + b[idx]
+        assert rel_err(out, want) <= 1e-6
+        assert rel_err(hi.float() + lo.float(), want) <= 2e-5
+        out2 = torch.empty_like(x)
+        L.call("glis_tprelu_forward_planes", L.ptr(x), L.ptr(a), L.ptr(b), L.ptr(out2), None, None,
+               x.numel(), c, ca, L.stream())
+        assert torch.equal(out2, out)
+
+
+def test_split_k_forward_matches_fused_epilogue():
+    """D's last level at batch 64 (256 -> 512 channels, 10x10 -> 5x5: 1600 pixels, 64 k-steps) runs as split-K
+    sums + one pointwise TPReLU pass; same forward, input gradient and parameter gradients as the fused launch."""
+    from glis_b200 import _lib, ops
+    _lib.set_precision("bf16x3")
+    pm, pmod = _product()
+    spec_g = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1)).geom(_lib.CONV, 64, 10, 10, 256, 5, 5, 512)
+    assert ops._split_k_forward(spec_g, _lib.CONV)
+    wide = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1)).geom(_lib.CONV, 128, 40, 40, 64, 20, 20, 128)
+    assert not ops._split_k_forward(wide, _lib.CONV)      # 256 tiles fill the machine on their own
+
+    def run(split):
+        ops.SPLIT_K_FORWARD = split
+        torch.manual_seed(42)
+        conv = pmod.WeightNormalizedConv2d(256, 512, 4, 2, 1, scale=False, bias=False).to(DEV)
+        act = pmod.TPReLU(512).to(DEV)
+        with torch.no_grad():
+            act.weight.uniform_(-0.2, 1.2)
+            act.bias.uniform_(-0.3, 0.3)
+        x = torch.randn(64, 256, 10, 10, device=DEV, requires_grad=True)
+        y = pm.run_layers([conv, act], x)
+        (y * torch.linspace(-1, 1, y.numel(), device=DEV).view_as(y)).sum().backward()
+        return y.detach(), x.grad, conv.weight.grad, act.weight.grad, act.bias.grad
+
+    try:
+        a, b = run(True), run(False)
+    finally:
+        ops.SPLIT_K_FORWARD = True
+    assert rel_err(a[0], b[0]) <= 2e-5
+    # The two launches add the K blocks in a different order, so 1-2 of the 819 200 pre-activations that sit
+    # within rounding distance of their TPReLU kink take the other branch (DESIGN.md, "TPReLU mask flips");
+    # such an element moves its own gradients by (1 - a) * dout and nothing else: bound the flips, hold the rest
+    # to rounding.
+    for u, v in zip(a[1:], b[1:]):
+        d = (u - v).abs() / v.abs().max()
+        assert d.max().item() <= 5e-2
+        assert (d > 2e-5).float().mean().item() <= 2e-3
+
+
+def test_planes_only_activations_in_chains():
+    """Inside a fused chain a tensor-core layer does not write the fp32 copy of an activation whose consumer
+    reads bf16 planes; the chain's result and every gradient are those of the fully materialised chain, the
+    elided tensor is marked, and anything that would read its fp32 values fails loudly."""
+    from glis_b200 import _lib, ops
+    _lib.set_precision("bf16x3")
+    pm, pmod = _product()
+
+    def build():
+        torch.manual_seed(43)
+        layers = [pmod.WeightNormalizedConv2d(32, 64, 4, 2, 1, scale=False, bias=False), pmod.TPReLU(64),
+                  pmod.WeightNormalizedConv2d(64, 64, 4, 2, 1, scale=False, bias=False), pmod.TPReLU(64),
+                  pmod.WeightNormalizedConv2d(64, 8, (5, 5))]
+        return [m.to(DEV) for m in layers]
+
+    def run(elide):
+        layers = build()
+        x = torch.randn(6, 32, 20, 20, device=DEV, requires_grad=True)
+        if elide:
+            y = pm.run_layers(layers, x)
+        else:          # pair by pair: no pair sees its consumer, every activation is materialised
+            y = x
+            for i in (0, 2):
+                y = pm.run_layers(layers[i:i + 2], y)
+            y = layers[4](y)
+        (y * torch.linspace(-1, 1, y.numel(), device=DEV).view_as(y)).sum().backward()
+        return [y.detach(), x.grad] + [p.grad for m in layers for p in m.parameters()]
+
+    for u, v in zip(run(True), run(False)):
+        assert rel_err(u, v) <= 1e-6
+    layers = build()
+    x = torch.randn(6, 32, 20, 20, device=DEV)
+    with torch.no_grad():
+        mid = pm.run_layers(layers[:2], x, following=layers[2:])
+        assert getattr(mid, "_glis_f32_invalid", False) and getattr(mid, "_glis_planes", None) is not None
+        last = pm.run_layers(layers[2:4], mid, following=layers[4:])     # consumer = the 5x5 head: fp32 kernel
+        assert not getattr(last, "_glis_f32_invalid", False)
+        mid._glis_planes = None                  # without its planes the tensor is unusable, and says so
+        with pytest.raises(RuntimeError, match="planes-only"):
+            ops.planes_of(mid)
+        with pytest.raises(RuntimeError, match="planes-only"):
+            layers[4](mid)
+
+
+def test_generator_tail_sigmoid_fused():
+    """Last transposed convolution + nn.Sigmoid of the generators as one operator (sigmoid in the fold kernel /
+    the contraction's epilogue) against the two modules run one by one."""
+    pm, pmod = _product()
+    for (cin, size) in ((64, 10), (32, 6)):
+        torch.manual_seed(44)
+        conv = pmod.WeightNormalizedConvTranspose2d(cin, 3, 4, 2, 1).to(DEV)
+        sig = torch.nn.Sigmoid()
+        with torch.no_grad():
+            conv.bias.uniform_(-0.5, 0.5)
+            conv.scale.uniform_(0.5, 2.0)
+        res = []
+        for fused in (True, False):
+            x = torch.randn(4, cin, size, size, device=DEV, requires_grad=True)
+            for p in conv.parameters():
+                p.grad = None
+            torch.manual_seed(45)
+            x.data.normal_()
+            y = pm.run_layers([conv, sig], x) if fused else sig(conv(x))
+            (y * torch.linspace(-1, 1, y.numel(), device=DEV).view_as(y)).sum().backward()
+            res.append([y.detach(), x.grad] + [p.grad.clone() for p in conv.parameters()])
+        for u, v in zip(*res):
+            assert rel_err(u, v) <= 2e-6
