@@ -25,6 +25,10 @@ int tc_conv_plan_ksplit(const glis_geom_t* g);
 int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
+int tc_pm_supported(const glis_geom_t* g);
+int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                  const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                  __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
 int tc_wgrad_supported(const glis_geom_t* g);
 int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo, const __nv_bfloat16* b_hi,
              const __nv_bfloat16* b_lo, float* G, int precision, cudaStream_t st);
@@ -96,6 +100,10 @@ extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, co
   GLIS_REQUIRE(ep->act == GLIS_ACT_NONE || ep->act == GLIS_ACT_SIGMOID ||
                    (ep->act == GLIS_ACT_TPRELU && ep->act_a && ep->act_b),
                GLIS_E_BADARG, "glis_conv_forward_bf16: bad activation descriptor");
+  if (tc_pm_supported(g) && (ep->act_channels == 0 || ep->act_channels == g->Co))   // image-side 1x1 products
+    return tc_pm_forward(g, (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (const __nv_bfloat16*)w_hi,
+                         (const __nv_bfloat16*)w_lo, ep, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                         precision, (cudaStream_t)stream);
   return tc_conv_forward(g, (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (const __nv_bfloat16*)w_hi,
                          (const __nv_bfloat16*)w_lo, ep, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
                          precision, (cudaStream_t)stream);
