@@ -51,6 +51,22 @@ class FlatParams(object):
     def zero_grad(self):
         self.gs.zero_()
 
+    def zero_grad_async(self):
+        """Clear the gradients on the side stream (they are not touched before the next backward); returns the
+        event the stream that runs that backward has to wait for, or None when done in place."""
+        if not (ops.Overlap.enabled and torch.cuda.is_available()):
+            self.gs.zero_()
+            return None
+        side, main = ops.Overlap.stream(), torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)                 # everything that read the old gradients has been enqueued
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self.gs.zero_()
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
     def rebind_grads(self):
         """Autograd may have replaced ``.grad`` (it does not for in-place accumulation, but a
         user could); make sure every parameter still accumulates into the flat buffer."""
@@ -178,12 +194,17 @@ class GLISTrainer(object):
         # BCE means are taken over their own halves, so the gradients are exactly the sum of the
         # reference's two backward passes (g_lis/main.py:555-565) at half the kernel launches.
         self._set_dis_requires_grad(True)
-        self.dis_flat.zero_grad()
+        # both networks' gradients were consumed by the previous iteration's optimizer steps: cleared on the
+        # side stream, under G's forward
+        zeroed_d = self.dis_flat.zero_grad_async()
+        zeroed_g = self.gen_flat.zero_grad_async()
         with torch.no_grad():
             fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
         both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
         logits = dis_logits(dis, both)
         self._sync_begin("dis")
+        if zeroed_d is not None:
+            torch.cuda.current_stream().wait_event(zeroed_d)
         ops.Overlap.begin()
         if logits is not None:     # losses and d(loss)/d(logits) from one kernel per half; backward starts at the logits
             (loss_d_real, loss_d_fake), dl = bce_on_logits(logits, [1.0, 0.0])
@@ -200,11 +221,12 @@ class GLISTrainer(object):
 
         # ---- G step
         self._set_dis_requires_grad(False)
-        self.gen_flat.zero_grad()
         fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
         logits = dis_logits(dis, fake)
         loss_r = []
         self._sync_begin("gen")
+        if zeroed_g is not None:
+            torch.cuda.current_stream().wait_event(zeroed_g)
         ops.Overlap.begin()
         if logits is not None:
             # roots of backward: the logits and every LIS output, each with its kernel-computed gradient
