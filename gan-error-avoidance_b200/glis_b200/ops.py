@@ -309,9 +309,38 @@ def refresh_packs(flat, part="all", side=True):
         return
     use_side = side and Overlap.enabled and torch.cuda.is_available()
     if not use_side:
-        for pw in todo:
-            pw._wait(PackedWeights.FORWARD_KINDS + PackedWeights.BACKWARD_KINDS)
+        all_kinds = PackedWeights.FORWARD_KINDS + PackedWeights.BACKWARD_KINDS
+        if not (Overlap.enabled and torch.cuda.is_available() and len(todo) > 2):
+            for pw in todo:
+                pw._wait(all_kinds)
+                pw.refresh(part)
+            return
+        # Needed by the very next kernel (G's forward packs at the end of an iteration): the layers are
+        # independent and each is a pair of short launches, so build them on three streams at once — the
+        # heaviest layer (G's initial linear, 3.3 M weights) bounds the wait instead of the sum of all
+        main = torch.cuda.current_stream()
+        lanes = [main] + Overlap.aux_streams(2)
+        load = [0] * len(lanes)
+        plan = [[] for _ in lanes]
+        for pw in sorted(todo, key=lambda q: -q.weight.numel()):
+            k = load.index(min(load))
+            plan[k].append(pw)
+            load[k] += pw.weight.numel() + 200000      # + a launch pair's fixed cost
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for s, pws in zip(lanes[1:], plan[1:]):
+            s.wait_event(ready)
+            with torch.cuda.stream(s):
+                for pw in pws:
+                    pw._wait(all_kinds)
+                    pw.refresh(part)
+        for pw in plan[0]:
+            pw._wait(all_kinds)
             pw.refresh(part)
+        for s in lanes[1:]:
+            done = torch.cuda.Event()
+            done.record(s)
+            main.wait_event(done)
         return
     kinds = set(PackedWeights.FORWARD_KINDS if part in ("all", "forward") else ()) | \
         set(PackedWeights.BACKWARD_KINDS if part in ("all", "backward") else ()) | {"norm"}
@@ -681,6 +710,15 @@ class Overlap(object):
         if cls._side is None:
             cls._side = torch.cuda.Stream()
         return cls._side
+
+    _aux = []
+
+    @classmethod
+    def aux_streams(cls, n):
+        """``n`` more streams for short independent bursts (parallel pack builds)."""
+        while len(cls._aux) < n:
+            cls._aux.append(torch.cuda.Stream())
+        return cls._aux[:n]
 
     @classmethod
     def begin(cls):
