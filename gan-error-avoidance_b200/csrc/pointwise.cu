@@ -410,7 +410,11 @@ extern "C" int glis_tprelu_backward_planes(const float* x, const float* a_raw, c
   if (inner == 1 && C % 4 == 0 && C / 4 <= PW_NT && aligned) {
     const int64_t rows = numel / C;
     const int rows_per_iter = PW_NT / (C / 4);
-    int64_t want = (rows + rows_per_iter * 8 - 1) / (rows_per_iter * 8);
+    // up to 8 row groups per thread (amortises the per-block sums) once that still gives every SM 4 blocks;
+    // small tensors (the LIS module, the 5x5 maps) get one row group per thread: more, shorter blocks
+    int64_t per = rows / ((int64_t)rows_per_iter * 148 * 4);
+    per = per < 1 ? 1 : (per > 8 ? 8 : per);
+    int64_t want = (rows + rows_per_iter * per - 1) / (rows_per_iter * per);
     const int blocks = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
     tprelu_bwd_nhwc_kernel<<<blocks, PW_NT, 0, (cudaStream_t)stream>>>(
         x, a_raw, b, dout, dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, da, db, rows, C);

@@ -97,8 +97,10 @@ class OverlappedGradSync(object):
     fused RMSprop.  Everything is stream-ordered, so the whole thing can sit inside a CUDA graph.
     """
 
-    def __init__(self, world, bucket_mb=8.0, group=None):
+    def __init__(self, world, bucket_mb=None, group=None):
         self.world, self.group = world, group
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("GLIS_DP_BUCKET_MB", "2"))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
         self.sets = {}
