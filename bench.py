@@ -379,6 +379,7 @@ def run_ours(args, rank, world, local):
         tc = {t: v for t, v in fam.items() if t.endswith(" tc")}
         roofline["peak"] = peaks["tf_burst"]
         roofline["frac"] = roofline["achieved"] / peaks["tf_burst"]
+        roofline["frac_mma_pipe"] = roofline["mma_pipe_tflops"] / peaks["tf_burst"]
         roofline["peak_source"] = peaks["source"] + " bf16 dense cuBLAS, burst (kernel timed alone)"
         roofline["tensor_core_launches_per_step"] = sum(c for c, _ in tc.values()) / n
         roofline["tensor_core_gflop_per_step"] = sum(flops(t) * c for t, (c, m) in tc.items()) / n / 1e9
