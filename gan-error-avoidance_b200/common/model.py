@@ -72,6 +72,20 @@ def run_layers(layers, x, following=()):
     return x
 
 
+def lis_residual(block, x):
+    """``x + block(x)`` for one LIS block (model.py:281-297); one cluster kernel when the block is the
+    norm='weight' form ``WN linear -> TPReLU -> WN linear`` (no scale / bias) and the code size fits."""
+    mods = list(block.children())
+    if (len(mods) == 3 and isinstance(mods[0], WeightNormalizedLinear) and isinstance(mods[1], TPReLU)
+            and isinstance(mods[2], WeightNormalizedLinear) and x.is_cuda and x.dtype == ops.torch.float32
+            and x.dim() == 2 and all(m.scale is None and m.bias is None for m in (mods[0], mods[2]))
+            and mods[0].in_features == mods[0].out_features == mods[2].in_features == mods[2].out_features
+            == x.shape[1] == mods[1].weight.numel() and ops.lis_supported(x.shape[1])):
+        return ops.lis_module(x, mods[0].weight, mods[2].weight, mods[1].weight, mods[1].bias,
+                              mods[0]._spec, mods[2]._spec)
+    return x + block(x)
+
+
 class DottedSequential(_DottedSequential):
     """Sequential container with reference-compatible dotted child names whose forward fuses
     (WN layer, TPReLU) pairs."""
@@ -260,7 +274,7 @@ class GeneratorLearnedInputSpace(nn.Module):
     def forward(self, x, n_execute_lis_layers=None):
         lis_results = []
         for i in range(self.lis_depth(n_execute_lis_layers)):
-            x = x + self.lis_layers[i](x)
+            x = lis_residual(self.lis_layers[i], x)
             lis_results.append(x)
         x = run_layers(self.initial_linear, x, following=self.conv_layers)
         x = run_layers(self.conv_layers, x)

@@ -41,6 +41,9 @@ SIGNATURES = {
     "glis_wn_prepare_bf16": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "glis_conv_tc_supported": [C.POINTER(Geom)],
     "glis_conv_tc_ksplit": [C.POINTER(Geom)],
+    "glis_lis_supported": [_i],
+    "glis_lis_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "glis_lis_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "glis_sigmoid_backward": [_vp, _vp, _vp, _i64, _vp],
     "glis_tprelu_forward_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_conv_forward_bf16": [C.POINTER(Geom), _vp, _vp, _vp, _vp, C.POINTER(Epilogue), _vp, _vp, _vp, _i, _vp],

