@@ -28,12 +28,17 @@ tprelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
 
 // NHWC TPReLU forward writing fp32 and/or bf16 hi/lo planes, four consecutive channels per thread.
 __global__ void __launch_bounds__(PW_NT)
-tprelu_fwd_planes_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
-                         float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                         int64_t numel, int C, int CA) {
+tprelu_fwd_planes_kernel(const float* __restrict__ x, int nslabs, int64_t slab_stride, const float* __restrict__ a_raw,
+                         const float* __restrict__ b, float* __restrict__ preact, float* __restrict__ out,
+                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t numel, int C, int CA) {
   const int64_t n4 = numel >> 2;   // C % 4 == 0: a group of four never straddles a pixel
   for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < n4; q += (int64_t)gridDim.x * PW_NT) {
-    const float4 v = reinterpret_cast<const float4*>(x)[q];
+    float4 v = reinterpret_cast<const float4*>(x)[q];
+    for (int s = 1; s < nslabs; ++s) {     // the partial sums of a split-K launch, always in this order
+      const float4 w = reinterpret_cast<const float4*>(x + (int64_t)s * slab_stride)[q];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    if (preact) reinterpret_cast<float4*>(preact)[q] = v;
     const int c0 = (int)((q * 4) % C);
     float o[4] = {v.x, v.y, v.z, v.w};
     __nv_bfloat16 h[4], l[4];
@@ -381,8 +386,30 @@ extern "C" int glis_tprelu_forward_planes(const float* x, const float* a_raw, co
                GLIS_E_BADARG, "glis_tprelu_forward_planes: misaligned buffer");
   if (numel == 0) return GLIS_OK;
   tprelu_fwd_planes_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
-      x, a_raw, b, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C, act_channels > 0 ? act_channels : C);
+      x, 1, 0, a_raw, b, nullptr, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C,
+      act_channels > 0 ? act_channels : C);
   GLIS_CHECK_LAUNCH("glis_tprelu_forward_planes");
+  return GLIS_OK;
+}
+
+extern "C" int glis_tprelu_forward_planes_sum(const float* slabs, int nslabs, int64_t slab_stride, const float* a_raw,
+                                              const float* b, float* preact, float* out, void* out_hi, void* out_lo,
+                                              int64_t numel, int C, int act_channels, void* stream) {
+  GLIS_REQUIRE(slabs && a_raw && b && (out || out_hi || preact), GLIS_E_BADARG,
+               "glis_tprelu_forward_planes_sum: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && C > 0 && act_channels >= 0 && nslabs >= 1 && (nslabs == 1 || slab_stride >= numel),
+               GLIS_E_BADARG, "glis_tprelu_forward_planes_sum: bad sizes");
+  GLIS_REQUIRE(C % 4 == 0 && numel % C == 0 && slab_stride % 4 == 0, GLIS_E_UNSUPPORTED,
+               "glis_tprelu_forward_planes_sum: C and the slab stride must be multiples of 4, numel a multiple of C");
+  GLIS_REQUIRE(((reinterpret_cast<uintptr_t>(slabs) | reinterpret_cast<uintptr_t>(out) |
+                 reinterpret_cast<uintptr_t>(preact)) & 15) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 7) == 0,
+               GLIS_E_BADARG, "glis_tprelu_forward_planes_sum: misaligned buffer");
+  if (numel == 0) return GLIS_OK;
+  tprelu_fwd_planes_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+      slabs, nslabs, slab_stride, a_raw, b, preact, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C,
+      act_channels > 0 ? act_channels : C);
+  GLIS_CHECK_LAUNCH("glis_tprelu_forward_planes_sum");
   return GLIS_OK;
 }
 

@@ -56,6 +56,7 @@ struct TcConvParams {
   const float* bias; int act; const float* act_a; const float* act_b; int act_channels;
   float* preact; float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int ep_mode;       // compile-time specialised epilogue (0 = generic)
+  long long slab_stride;   // split K without atomics: share s stores its sums at out_f32 + s * slab_stride
   unsigned long long* trace;  // optional timeline buffer (GLIS_TC_TRACE): CTA 0 logs globaltimer per event
   int debug;         // GLIS_TC_DEBUG bits (profiling experiments only): 1 = no stores, 2 = no MMA, 4 = no x loads
 };
@@ -353,6 +354,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           case 4: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, false>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 5: tc_epilogue_chunk<GLIS_ACT_TPRELU, true, true, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
           case 7: tc_epilogue_chunk<GLIS_ACT_TPRELU, false, false, true>(v, nvalid, base, rc, bias, ta, tb, P.preact, P.out_f32, P.out_hi, P.out_lo); break;
+          case 8: {   // split K, deterministic form: this share's partial sums into its own slab
+            float* slab = P.out_f32 + (long long)tl.split * P.slab_stride;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) slab[base + rc[j]] = __uint_as_float(v[j]) + bias;
+            break;
+          }
           case 6: {   // split K: add this item's partial sums (one 128-byte reduction per warp and column)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -617,7 +625,13 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && !out_hi) P.ep_mode = 4;
   else if (ep->act == GLIS_ACT_TPRELU && ep->preact && out_f32 && out_hi) P.ep_mode = 5;
   else if (ep->act == GLIS_ACT_TPRELU && !ep->preact && !out_f32 && out_hi) P.ep_mode = 7;   // no-grad forward
-  if (best_ks > 1) {
+  P.slab_stride = 0;
+  if (best_ks > 1 && ep->split_slabs > 0) {
+    GLIS_REQUIRE(ep->split_slabs >= best_ks, GLIS_E_BADARG, "glis_conv_forward_bf16: %d slabs for a %d-way K split",
+                 ep->split_slabs, best_ks);
+    P.ep_mode = 8;
+    P.slab_stride = (long long)g->N * g->Ho * g->Wo * g->Co;
+  } else if (best_ks > 1) {
     P.ep_mode = 6;
     cudaError_t me = cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)g->N * g->Ho * g->Wo * g->Co, st);
     GLIS_REQUIRE(me == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16: memset failed: %s", cudaGetErrorString(me));

@@ -26,7 +26,7 @@ class Geom(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("act_a", C.c_void_p),
                 ("act_b", C.c_void_p), ("preact", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-                ("act_channels", C.c_int32)]
+                ("act_channels", C.c_int32), ("split_slabs", C.c_int32)]
 
 
 _vp, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
@@ -41,6 +41,7 @@ SIGNATURES = {
     "glis_wn_prepare_bf16": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "glis_conv_tc_supported": [C.POINTER(Geom)],
     "glis_conv_tc_ksplit": [C.POINTER(Geom)],
+    "glis_tprelu_forward_planes_sum": [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_lis_supported": [_i],
     "glis_lis_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "glis_lis_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -580,15 +580,17 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         skip_f32 = planes is not None and not want_f32
         act_ch = spec.perm[0] if (spec.perm and act == L.ACT_TPRELU) else 0
         if act == L.ACT_TPRELU and planes is not None and g.Co % 4 == 0 and _split_k_forward(g, relation):
-            # split-K sums (+ bias) into the pre-activation buffer, then TPReLU + planes as one pointwise pass
-            sums = preact if preact is not None else torch.empty_like(out)
-            ep = L.Epilogue(L.ptr(bias), L.ACT_NONE, None, None, None, None, None, 0)
+            # split-K partial sums (+ bias) into one slab per share — stores, not atomics: the forward pass stays
+            # bit-reproducible — then sum + TPReLU + planes as one pointwise pass
+            ks = int(L.load().glis_conv_tc_ksplit(C.byref(g)))
+            slabs = torch.empty((ks,) + tuple(out.shape), device=out.device, dtype=torch.float32)
+            ep = L.Epilogue(L.ptr(bias), L.ACT_NONE, None, None, None, None, None, 0, ks)
             with L.timed(_tag(relation, g) + " tc"):
                 L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]),
-                       L.ptr16(wp[1]), C.byref(ep), L.ptr(sums), None, None, prec, L.stream())
-            L.call("glis_tprelu_forward_planes", L.ptr(sums), L.ptr(act_a), L.ptr(act_b),
-                   None if skip_f32 else L.ptr(out), L.ptr16(planes[0]), L.ptr16(planes[1]), sums.numel(), g.Co,
-                   act_ch, L.stream())
+                       L.ptr16(wp[1]), C.byref(ep), L.ptr(slabs), None, None, prec, L.stream())
+            L.call("glis_tprelu_forward_planes_sum", L.ptr(slabs), ks, out.numel(), L.ptr(act_a), L.ptr(act_b),
+                   L.ptr(preact), None if skip_f32 else L.ptr(out), L.ptr16(planes[0]), L.ptr16(planes[1]),
+                   out.numel(), g.Co, act_ch, L.stream())
         else:
             ep = L.Epilogue(L.ptr(bias), act, L.ptr(act_a), L.ptr(act_b), L.ptr(preact), None, None, act_ch)
             with L.timed(_tag(relation, g) + " tc"):

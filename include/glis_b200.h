@@ -72,6 +72,11 @@ typedef struct glis_epilogue {
   int32_t act_channels; /* 0: act_a / act_b hold one value per OUTPUT channel; C > 0: the TPReLU has C channels and
                          * output channel co uses act_a[co % C] (a linear layer whose output is a (C,h,w) map
                          * written in NHWC feature order, see glis_wn_prepare_perm) */
+  int32_t split_slabs;  /* glis_conv_forward_bf16, plain-output launches only: when > 0 and the launch splits K
+                         * (glis_conv_tc_ksplit) the partial sums of share s are STORED at out_f32 + s * N*Ho*Wo*Co
+                         * (the caller provides that many slabs, >= the K split) instead of being added atomically
+                         * into one zero-filled output: a deterministic split-K (summed by
+                         * glis_tprelu_forward_planes_sum in a fixed order) */
 } glis_epilogue_t;
 
 const char* glis_last_error(void);
@@ -209,6 +214,11 @@ int glis_tprelu_forward(const float* x, const float* a_raw, const float* b, floa
  * NULL; lo may be NULL): the epilogue of a split-K tensor-core launch, as one pointwise pass. */
 int glis_tprelu_forward_planes(const float* x, const float* a_raw, const float* b, float* out, void* out_hi,
                                void* out_lo, int64_t numel, int C, int act_channels, void* stream);
+/* As glis_tprelu_forward_planes on x = slab_0 + slab_1 + ... (nslabs partial sums, slab_stride elements apart,
+ * added in that order); preact (may be NULL) receives x. */
+int glis_tprelu_forward_planes_sum(const float* slabs, int nslabs, int64_t slab_stride, const float* a_raw,
+                                   const float* b, float* preact, float* out, void* out_hi, void* out_lo,
+                                   int64_t numel, int C, int act_channels, void* stream);
 /* dy = dout * s * (1 - s), s = the sigmoid a contraction's epilogue applied (GLIS_ACT_SIGMOID): backward of the
  * nn.Sigmoid that ends the generators (common/model.py:136, :259), same element order for all three. */
 int glis_sigmoid_backward(const float* s, const float* dout, float* dy, int64_t numel, void* stream);

@@ -818,6 +818,14 @@ def test_tprelu_forward_planes_kernel_matches_torch():
         L.call("glis_tprelu_forward_planes", L.ptr(x), L.ptr(a), L.ptr(b), L.ptr(out2), None, None,
                x.numel(), c, ca, L.stream())
         assert torch.equal(out2, out)
+        # three partial-sum slabs (a split-K launch's shares), summed in order, pre-activation written too
+        parts = torch.randn(3, pix, c, generator=g).to(DEV)
+        parts[2] = x - parts[0] - parts[1]
+        pre, out3 = torch.empty_like(x), torch.empty_like(x)
+        L.call("glis_tprelu_forward_planes_sum", L.ptr(parts), 3, x.numel(), L.ptr(a), L.ptr(b), L.ptr(pre),
+               L.ptr(out3), None, None, x.numel(), c, ca, L.stream())
+        assert torch.equal(pre, parts[0] + parts[1] + parts[2])
+        assert rel_err(out3, want) <= 1e-5
 
 
 def test_split_k_forward_matches_fused_epilogue():
@@ -845,10 +853,11 @@ def test_split_k_forward_matches_fused_epilogue():
         return y.detach(), x.grad, conv.weight.grad, act.weight.grad, act.bias.grad
 
     try:
-        a, b = run(True), run(False)
+        a, b, a2 = run(True), run(False), run(True)
     finally:
         ops.SPLIT_K_FORWARD = True
     assert rel_err(a[0], b[0]) <= 2e-5
+    assert torch.equal(a[0], a2[0])      # per-share slabs summed in a fixed order: the forward is bit-reproducible
     # The two launches add the K blocks in a different order, so 1-2 of the 819 200 pre-activations that sit
     # within rounding distance of their TPReLU kink take the other branch ("TPReLU mask flips");
     # such an element moves its own gradients by (1 - a) * dout and nothing else: bound the flips, hold the rest
