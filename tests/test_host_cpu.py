@@ -125,3 +125,38 @@ def test_lis_depth_rule_product():
     g.rng = Seq([0.9, 0.9, 0.9]); assert g.lis_depth() == 3
     g.eval(); g.rng = Seq([0.0, 0.0, 0.0]); assert g.lis_depth() == 3
     g.train(); g.rng = Seq([0.5] * 3); assert g.lis_depth(2) == 2 and g.rng.n == 3
+
+
+def test_tensor_core_planning_queries():
+    """Host-side planning (no GPU needed): which launches split K, which fused forwards run as split-K sums +
+    a pointwise pass, which activations may stay planes-only, which code sizes the LIS kernel takes."""
+    import ctypes as C
+    import torch
+    from glis_b200 import _lib as L, ops
+    lib = L.load()
+    spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
+    geom = lambda n, hi, ci, ho, co: spec.geom(L.CONV, n, hi, hi, ci, ho, ho, co)
+    d3_b, d3_2b = geom(64, 10, 256, 5, 512), geom(128, 10, 256, 5, 512)
+    d1_2b, d2_b = geom(128, 40, 64, 20, 128), geom(64, 20, 128, 10, 256)
+    assert lib.glis_conv_tc_ksplit(C.byref(d3_b)) >= 4 and ops._split_k_forward(d3_b, L.CONV)
+    assert lib.glis_conv_tc_ksplit(C.byref(d3_2b)) >= 2 and ops._split_k_forward(d3_2b, L.CONV)     # 64 k-steps
+    assert lib.glis_conv_tc_ksplit(C.byref(d1_2b)) == 1 and not ops._split_k_forward(d1_2b, L.CONV)
+    assert not ops._split_k_forward(d2_b, L.CONV)                     # a 2-way split over 32 k-steps does not pay
+    # the generator head's data gradient: 200 blocks of 64 features into 256 columns -> a deep split
+    head = ops.ContractionSpec(False, (1, 1), (1, 1), (0, 0), (1, 1), linear=True, perm=(512, 25))
+    g = head.geom(L.TCONV, 64, 1, 1, 12800, 1, 1, 256)
+    assert lib.glis_conv_tc_supported(C.byref(g)) == 1 and lib.glis_conv_tc_ksplit(C.byref(g)) >= 16
+    assert lib.glis_lis_supported(256) == 1 and lib.glis_lis_supported(128) == 1
+    assert lib.glis_lis_supported(512) == 0 and lib.glis_lis_supported(48) == 0
+    # planes-only activations: a tensor-core conv consumer (forward + weight gradient on tcgen05) suffices,
+    # D's 5x5 head (one output channel: fp32 kernel) does not, nothing does in fp32 mode
+    w_conv, w_head = torch.zeros(256, 128, 4, 4), torch.zeros(1, 512, 5, 5)
+    head_spec = ops.ContractionSpec(False, (5, 5), (1, 1), (0, 0), (1, 1))
+    assert ops.consumes_planes_only(spec, w_conv, (64, 128, 20, 20), True)
+    assert not ops.consumes_planes_only(head_spec, w_head, (64, 512, 5, 5), False)
+    assert not ops.consumes_planes_only(ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1), precision=L.PREC_FP32),
+                                        w_conv, (64, 128, 20, 20), True)
+    # G's last layer (64 -> 3, transposed, followed by the sigmoid): the "fold" product reads planes
+    tspec = ops.ContractionSpec(True, (4, 4), (2, 2), (1, 1), (1, 1))
+    assert ops.consumes_planes_only(tspec, torch.zeros(64, 3, 4, 4), (64, 64, 40, 40), False)
+    assert not ops.consumes_planes_only(tspec, torch.zeros(64, 3, 4, 4), (64, 64, 40, 40), True)
