@@ -22,6 +22,7 @@ int simt_conv_wgrad(const glis_geom_t* g, const float* small, const float* big, 
 
 int tc_conv_supported(const glis_geom_t* g);
 int tc_conv_plan_ksplit(const glis_geom_t* g);
+int tc_conv_plan_describe(const glis_geom_t* g, int plain_out, int out[15]);
 int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
@@ -85,6 +86,14 @@ extern "C" int glis_conv_tc_supported(const glis_geom_t* g) {
 extern "C" int glis_conv_tc_ksplit(const glis_geom_t* g) {
   if (validate_geom(g, "glis_conv_tc_ksplit") != GLIS_OK) return 1;
   return tc_conv_plan_ksplit(g);
+}
+
+extern "C" int glis_conv_tc_plan(const glis_geom_t* g, int plain_out, int* out15) {
+  int rc = validate_geom(g, "glis_conv_tc_plan");
+  if (rc != GLIS_OK) return rc;
+  GLIS_REQUIRE(out15 != nullptr, GLIS_E_BADARG, "glis_conv_tc_plan: NULL output");
+  GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_tc_plan: geometry not tileable for tcgen05");
+  return tc_conv_plan_describe(g, plain_out, out15);
 }
 
 extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x_lo, const void* w_hi,

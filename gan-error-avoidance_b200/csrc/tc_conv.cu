@@ -593,6 +593,24 @@ int tc_conv_plan_ksplit(const glis_geom_t* g) {
   return P.ksplit;
 }
 
+// The whole plan, for inspection (tests/test_host_cpu.py checks its invariants over many geometries):
+// out = {tw, th, tn, n_mma, tmem_cols, kblocks, ksplit, a_rows, stages, tiles_h, tiles_x, tiles_co, total_tiles,
+//        n_groups, dynamic shared memory bytes}
+int tc_conv_plan_describe(const glis_geom_t* g, int plain_out, int out[15]) {
+  if (!tc_conv_supported(g)) return GLIS_E_UNSUPPORTED;
+  TcConvParams P;
+  int rc = tc_plan(g, plain_out != 0, P);
+  if (rc != GLIS_OK) return rc;
+  const size_t stage_bytes = 2 * (size_t)P.a_rows * 128 + 2 * (size_t)P.n_mma * 128;
+  int stages = (int)((219 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
+  const int v[15] = {P.tw, P.th, P.tn, P.n_mma, P.tmem_cols, P.kblocks, P.ksplit, P.a_rows, stages, P.tiles_h,
+                     P.tiles_x, P.tiles_co, P.total_tiles, P.n_groups, (int)smem};
+  for (int i = 0; i < 15; ++i) out[i] = v[i];
+  return GLIS_OK;
+}
+
 int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st) {

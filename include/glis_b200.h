@@ -147,6 +147,10 @@ int glis_conv_tc_supported(const glis_geom_t* g);
  * geometry.  A caller whose fused-epilogue launch cannot fill the machine with its tiles alone (few pixels,
  * deep K: D's last level at batch 64) may then run it as split-K sums + glis_tprelu_forward_planes. */
 int glis_conv_tc_ksplit(const glis_geom_t* g);
+/* The launch plan glis_conv_forward_bf16 would use (host only, for inspection and tests): out15 = {tile width,
+ * tile rows, tile images, UMMA N, TMEM columns, 64-channel blocks, K split, staged weight rows, pipeline stages,
+ * row tiles per image, pixel tiles, channel tiles, tiles, work items, dynamic shared memory bytes}. */
+int glis_conv_tc_plan(const glis_geom_t* g, int plain_out, int* out15);
 
 /* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
  * TMEM, epilogue fused.  x planes [N,Hi,Wi,Ci] bf16, w packs [KH*KW][Co][Ci] bf16.  Outputs

@@ -160,3 +160,62 @@ def test_tensor_core_planning_queries():
     tspec = ops.ContractionSpec(True, (4, 4), (2, 2), (1, 1), (1, 1))
     assert ops.consumes_planes_only(tspec, torch.zeros(64, 3, 4, 4), (64, 64, 40, 40), False)
     assert not ops.consumes_planes_only(tspec, torch.zeros(64, 3, 4, 4), (64, 64, 40, 40), True)
+
+
+def test_tc_conv_plan_invariants():
+    """Property test of the tcgen05 launch planner (host code, no GPU): for every geometry the kernel claims to
+    support, the plan tiles all pixels and channels, fits TMEM and shared memory, keeps at least two pipeline
+    stages, and only splits K where the epilogue allows it."""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    from glis_b200 import _lib as L, ops
+    lib = L.load()
+    cdiv = lambda a, b: -(-a // b)
+
+    def check(relation, kernel, stride, pad, n, h, w, ci, co, plain):
+        spec = ops.ContractionSpec(relation == L.TCONV, (kernel, kernel), (stride, stride), (pad, pad), (1, 1))
+        if relation == L.CONV:
+            ho, wo = spec.__class__(False, (kernel, kernel), (stride, stride), (pad, pad), (1, 1)).out_hw(h, w)
+            if ho < 1 or wo < 1:
+                return
+            g = spec.geom(L.CONV, n, h, w, ci, ho, wo, co)
+        else:
+            ho, wo = spec.out_hw(h, w)
+            g = spec.geom(L.TCONV, n, h, w, ci, ho, wo, co)
+        if not lib.glis_conv_tc_supported(C.byref(g)):
+            return
+        out = (C.c_int * 15)()
+        assert lib.glis_conv_tc_plan(C.byref(g), int(plain), out) == 0, lib.glis_last_error()
+        (tw, th, tn, n_mma, tmem, kblocks, ksplit, a_rows, stages, tiles_h, tiles_x, tiles_co, total, groups,
+         smem) = list(out)
+        nphase = stride * stride if relation == L.TCONV else 1
+        hq, wq = (cdiv(ho, stride), cdiv(wo, stride)) if relation == L.TCONV else (ho, wo)
+        assert tw == wq and 1 <= th <= hq and 1 <= tn <= n and (tn == 1 or th == hq)
+        assert tw * th * tn <= n_mma <= 256 and n_mma % 16 == 0 and n_mma - tw * th * tn < 16
+        assert tiles_h == cdiv(hq, th) and tiles_x >= tiles_h * cdiv(n, tn) and tiles_co == cdiv(co, 128)
+        assert total == tiles_x * tiles_co * nphase and groups == total * ksplit
+        assert tmem in (64, 128, 256, 512) and tmem >= 2 * n_mma
+        assert kblocks == cdiv(ci, 64) and 1 <= ksplit <= min(32, kblocks) and (plain or ksplit == 1)
+        assert a_rows in (64, 128) and (a_rows == 128 or (co <= 64 and n_mma >= 64))
+        stage = 2 * a_rows * 128 + 2 * n_mma * 128
+        assert 2 <= stages <= 4 and smem == stages * stage + 2304 and smem <= 227 * 1024
+        assert a_rows * 128 + 128 * 128 <= stage          # the 128-row MMA read that starts in the lo weight tile
+
+    geometry = st.tuples(st.sampled_from([(L.CONV, 4, 2, 1), (L.TCONV, 4, 2, 1), (L.CONV, 3, 1, 1), (L.CONV, 1, 1, 0),
+                                          (L.CONV, 5, 1, 0)]),
+                         st.integers(1, 130), st.integers(1, 100).map(lambda v: 2 * v), st.integers(1, 100).map(lambda v: 2 * v),
+                         st.sampled_from([32, 40, 48, 64, 72, 96, 128, 200, 256, 512, 1024]),
+                         st.sampled_from([32, 33, 40, 48, 64, 100, 128, 129, 192, 256, 512]), st.booleans())
+
+    @settings(max_examples=600, deadline=None)
+    @given(geometry)
+    def run(case):
+        (relation, kernel, stride, pad), n, h, w, ci, co, plain = case
+        check(relation, kernel, stride, pad, n, h, w, ci, co, plain)
+
+    run()
+    # the layers of configs 2 and 4 explicitly
+    for (rel, n, h, ci, co) in ((L.CONV, 128, 40, 64, 128), (L.CONV, 64, 10, 256, 512), (L.TCONV, 64, 5, 512, 256),
+                                (L.TCONV, 64, 20, 128, 64), (L.CONV, 32, 80, 64, 128), (L.TCONV, 32, 40, 128, 64)):
+        check(rel, 4, 2, 1, n, h, h, ci, co, True)
+        check(rel, 4, 2, 1, n, h, h, ci, co, False)
