@@ -1041,6 +1041,7 @@ class WNContractionTPReLU(torch.autograd.Function):
                                      act_a=a_raw.detach().contiguous(), act_b=b_t.detach().contiguous(),
                                      want_preact=need_bwd, want_planes=True, want_f32=want_f32)
         _ELIDED[0] = getattr(out, "_glis_f32_invalid", False)
+        PreactTap.report(a_raw, b_t, preact)
         ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
@@ -1107,6 +1108,31 @@ class WNContractionTPReLU(torch.autograd.Function):
 _ELIDED = [False]    # did the last fused forward leave its fp32 output unwritten (see launch)
 
 
+class PreactTap(object):
+    """Test hook: ``with PreactTap() as tap:`` collects ``(TPReLU slope, translation, pre-activation)`` of every
+    TPReLU forward that keeps its pre-activation for a backward pass (logical ``(N, C, ...)`` shape, the very
+    tensor backward reads its branch mask from).  The parity tests hand those masks to the oracle so that both
+    sides differentiate the same piecewise-linear function (oracle/flipaware.py)."""
+
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        self._prev, PreactTap.active = PreactTap.active, self
+        return self
+
+    def __exit__(self, *exc):
+        PreactTap.active = self._prev
+        return False
+
+    @classmethod
+    def report(cls, a_raw, b_t, preact):
+        if cls.active is not None and preact is not None:
+            cls.active.records.append((a_raw, b_t, preact))
+
+
 def _may_need_backward(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -1149,6 +1175,8 @@ class WNLinearViewTPReLU(torch.autograd.Function):
             ctx.save_for_backward(xc, preact, a_raw, b_t)
         ctx.set_materialize_grads(False)
         as_map = lambda t: t.view(n, h, w, c).permute(0, 3, 1, 2)     # NHWC memory, logical (N, C, h, w)
+        if preact is not None:
+            PreactTap.report(a_raw, b_t, as_map(preact))
         if planes is None:
             return as_map(out), None, None
         hi, lo = as_map(planes[0]), None if planes[1] is None else as_map(planes[1])
@@ -1226,6 +1254,7 @@ class LISModuleFunction(torch.autograd.Function):
                L.ptr(b_t.detach().contiguous()), L.ptr(pw2.io), None, n, code, L.ptr(h), L.ptr(act), L.ptr(out),
                L.stream())
         ctx.pw1, ctx.pw2, ctx.spec1, ctx.spec2 = pw1, pw2, spec1, spec2
+        PreactTap.report(a_raw, b_t, h)
         if need_bwd:
             ctx.save_for_backward(uc, h, act, a_raw, b_t)
         return out
@@ -1299,6 +1328,8 @@ class TPReLUFunction(torch.autograd.Function):
         L.call("glis_tprelu_forward", L.ptr(xc), L.ptr(a_raw.detach()), L.ptr(b.detach()), L.ptr(out),
                xc.numel(), c, inner, L.stream())
         ctx.inner = inner
+        if any(ctx.needs_input_grad):
+            PreactTap.report(a_raw, b, xc)
         ctx.save_for_backward(xc, a_raw, b)
         return out
 

@@ -39,8 +39,14 @@ def _zero_fill(module):
             p.grad.zero_()
 
 
+def adversarial_loss(ls):
+    """``lossfunc`` of g_lis/main.py:308-311 and r_iterative/main.py:208-211: ``nn.MSELoss()`` on D's
+    (sigmoid) output under ``--ls``, else ``nn.BCELoss()``."""
+    return F.mse_loss if ls else F.binary_cross_entropy
+
+
 def glis_iteration(gen, dis, gen_state, dis_state, real, z_d, z_g, lr, lambda_r=0.9,
-                   depth_d=None, depth_g=None, alpha=0.9, eps=1e-6):
+                   depth_d=None, depth_g=None, alpha=0.9, eps=1e-6, ls=False):
     """One iteration: D on real, D on fake (G under no_grad), D update, G+LIS update.
 
     ``depth_d`` / ``depth_g`` force the number of LIS modules run in the D-fake and G
@@ -50,16 +56,17 @@ def glis_iteration(gen, dis, gen_state, dis_state, real, z_d, z_g, lr, lambda_r=
     B = real.size(0)
     ones = torch.ones(B, 1, dtype=real.dtype)
     zeros = torch.zeros(B, 1, dtype=real.dtype)
+    lossfunc = adversarial_loss(ls)
 
     # ---- D step (:537-568)
     for p in dis.parameters():
         p.requires_grad_(True)
     _zero_fill(dis)
-    loss_d_real = F.binary_cross_entropy(dis(real), ones)
+    loss_d_real = lossfunc(dis(real), ones)
     loss_d_real.backward()
     with torch.no_grad():
         fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
-    loss_d_fake = F.binary_cross_entropy(dis(fake.detach()), zeros)
+    loss_d_fake = lossfunc(dis(fake.detach()), zeros)
     loss_d_fake.backward()
     rmsprop_update(list(dis.parameters()), dis_state, lr, alpha, eps)
 
@@ -68,7 +75,7 @@ def glis_iteration(gen, dis, gen_state, dis_state, real, z_d, z_g, lr, lambda_r=
         p.requires_grad_(False)
     _zero_fill(gen)
     fake, lis_g = gen(z_g, n_execute_lis_layers=depth_g)
-    loss_g = F.binary_cross_entropy(dis(fake), ones)
+    loss_g = lossfunc(dis(fake), ones)
     loss_g.backward(retain_graph=(lambda_r > 0 and len(lis_g) > 0))
     loss_r = []
     if lambda_r > 0:
@@ -87,18 +94,18 @@ def glis_iteration(gen, dis, gen_state, dis_state, real, z_d, z_g, lr, lambda_r=
 class GLISOracleTrainer:
     """Holds G, D and both RMSprop states; ``step`` = :func:`glis_iteration`."""
 
-    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6):
+    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6, ls=False):
         self.gen, self.dis = gen, dis
-        self.lr, self.lambda_r, self.alpha, self.eps = lr, lambda_r, alpha, eps
+        self.lr, self.lambda_r, self.alpha, self.eps, self.ls = lr, lambda_r, alpha, eps, ls
         self.gen_state, self.dis_state = {}, {}
 
     def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
         return glis_iteration(self.gen, self.dis, self.gen_state, self.dis_state, real, z_d, z_g,
-                              self.lr, self.lambda_r, depth_d, depth_g, self.alpha, self.eps)
+                              self.lr, self.lambda_r, depth_d, depth_g, self.alpha, self.eps, self.ls)
 
 
 def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, reals, lr, lambda_r=0.9,
-                    r_iterations=3, train_flags=None, alpha=0.9, eps=1e-6):
+                    r_iterations=3, train_flags=None, alpha=0.9, eps=1e-6, ls=False):
     """One outer iteration of the R-iterative trainer, restated from ``r_iterative/main.py:428-535``.
 
     A chain of ``1 + r_iterations`` hops: hop 0 starts from ``first_code`` (noise), hop r > 0 from
@@ -116,12 +123,14 @@ def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, 
     if train_flags is None:
         train_flags = [True] * hops
     reals = list(reals)
+    lossfunc = adversarial_loss(ls)
     out = []
     last_images, last_code = None, None
     for r_idx in range(hops):
         code = first_code if last_images is None else rev(last_images.detach())
         if not train_flags[r_idx]:
-            last_images = gen(code.detach())
+            with torch.no_grad():      # (:468: the images are only ever used detached, :459)
+                last_images = gen(code.detach())
             last_code = code
             out.append(None)
             continue
@@ -131,14 +140,14 @@ def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, 
         for p in dis.parameters():
             p.requires_grad_(False)
         generated = gen(code.detach())
-        loss_g = F.binary_cross_entropy(dis(generated), ones)
+        loss_g = lossfunc(dis(generated), ones)
         loss_g.backward()
         rmsprop_update(list(gen.parameters()), gen_state, lr, alpha, eps)
         rec["g"] = loss_g.item()
         # ---- R
         if last_code is not None:
             _zero_fill(rev)
-            loss_g2 = F.binary_cross_entropy(dis(gen(code)), ones)
+            loss_g2 = lossfunc(dis(gen(code)), ones)
             loss_r = F.mse_loss(code, first_code.detach())
             lar = lambda_r ** r_idx
             (lar * loss_r + (1 - lar) * loss_g2).backward()
@@ -148,9 +157,9 @@ def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, 
         _zero_fill(dis)
         for p in dis.parameters():
             p.requires_grad_(True)
-        loss_d_real = F.binary_cross_entropy(dis(reals.pop(0)), ones)
+        loss_d_real = lossfunc(dis(reals.pop(0)), ones)
         loss_d_real.backward()
-        loss_d_fake = F.binary_cross_entropy(dis(generated.detach()), zeros)
+        loss_d_fake = lossfunc(dis(generated.detach()), zeros)
         loss_d_fake.backward()
         rmsprop_update(list(dis.parameters()), dis_state, lr, alpha, eps)
         rec["d_real"], rec["d_fake"] = loss_d_real.item(), loss_d_fake.item()

@@ -24,7 +24,12 @@ What is written (all float64, tiny shapes, ``.npz``):
                       reference-built G-LIS + D with stock ``torch.optim.RMSprop`` /
                       ``nn.BCELoss`` / ``nn.MSELoss``: losses and every parameter after
                       each iteration, with stochastic LIS depth forced per iteration
-                      (including a skipped module, exercising the zero-fill rule).
+                      (including a skipped module, exercising the zero-fill rule);
+* ``glis_steps_ls.npz`` – two such iterations with ``--ls`` (``lossfunc = nn.MSELoss()`` on D's sigmoid
+                      output, g_lis/main.py:308-311);
+* ``riter_steps.npz`` – two outer iterations of the R-iterative trainer (r_iterative/main.py:428-535) on
+                      reference-built plain G + reverser R + D with three stock RMSprops: all hops trained,
+                      then the schedule [skip, train, train].
 """
 import contextlib
 import os
@@ -287,7 +292,125 @@ def main():
             for k, v in undot(d.state_dict()).items():
                 put(steps, pre + "/d", **{k: v})
         np.savez_compressed(os.path.join(OUT, "glis_steps.npz"), **steps)
-    for f in ("modules.npz", "models.npz", "glis_steps.npz"):
+
+        # ---- --ls: the same iteration with nn.MSELoss() as the adversarial loss (g_lis/main.py:308-311)
+        steps = {}
+        torch.manual_seed(8)
+        g = ref.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis_layers=n_lis, upscaling="fractional").double()
+        d = ref.build_discriminator(W, H, nf, nl, "weight", 0).double()
+        g.train(); d.train()
+        lsq, mse = nn.MSELoss(), nn.MSELoss()
+        g_opt = torch.optim.RMSprop(g.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        d_opt = torch.optim.RMSprop(d.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        for k, v in undot(g.state_dict()).items():
+            put(steps, "init/g", **{k: v})
+        for k, v in undot(d.state_dict()).items():
+            put(steps, "init/d", **{k: v})
+        depths = [(2, 2), (1, 0)]
+        put(steps, "cfg", W=W, H=H, B=B, code=code, nf=nf, nl=nl, n_lis=n_lis, lr=lr, lam=lam, depths=np.array(depths))
+        for it, (kd, kg) in enumerate(depths):
+            real, zd, zg = t64(B, 3, H, W, lo=0, gen=gen), torch.randn(B, code, dtype=torch.float64, generator=gen), \
+                torch.randn(B, code, dtype=torch.float64, generator=gen)
+            for p in d.parameters():
+                p.requires_grad = True
+            d.zero_grad(set_to_none=False)
+            l_real = lsq(d(real), ones); l_real.backward()
+            with torch.no_grad():
+                fake, _ = g(zd, n_execute_lis_layers=kd)
+            l_fake = lsq(d(fake.detach()), zeros); l_fake.backward()
+            d_opt.step()
+            for p in d.parameters():
+                p.requires_grad = False
+            g.zero_grad(set_to_none=False)
+            fake, lis = g(zg, n_execute_lis_layers=kg)
+            l_g = lsq(d(fake), ones)
+            l_g.backward(retain_graph=len(lis) > 0)
+            l_r = []
+            for i, u in enumerate(lis):
+                l = mse(u, zg) * (lam ** (i + 1))
+                l.backward(retain_graph=(i + 1) < len(lis))
+                l_r.append(l.item())
+            g_opt.step()
+            pre = "it%d" % it
+            put(steps, pre, real=real, zd=zd, zg=zg, d_real=l_real.item(), d_fake=l_fake.item(),
+                g=l_g.item(), r=np.array(l_r, dtype=np.float64))
+            for k, v in undot(g.state_dict()).items():
+                put(steps, pre + "/g", **{k: v})
+            for k, v in undot(d.state_dict()).items():
+                put(steps, pre + "/d", **{k: v})
+        np.savez_compressed(os.path.join(OUT, "glis_steps_ls.npz"), **steps)
+
+        # ---- R-iterative outer iterations (r_iterative/main.py:428-535; nets :195-215)
+        steps = {}
+        R = 2
+        torch.manual_seed(9)
+        g = ref.build_generator(W, H, nf, nl, code, "weight").double()
+        rv = ref.build_reverser(W, H, nf // 2, nl, code, "weight", 0).double()
+        d = ref.build_discriminator(W, H, nf, nl, "weight", 0).double()   # (:205 passes 5 arguments: a TypeError upstream)
+        for net in (g, rv, d):
+            net.train()
+        lossfunc, lossfunc_r = nn.BCELoss(), nn.MSELoss()
+        g_opt = torch.optim.RMSprop(g.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        r_opt = torch.optim.RMSprop(rv.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        d_opt = torch.optim.RMSprop(d.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        for tag, net in (("g", g), ("r", rv), ("d", d)):
+            for k, v in undot(net.state_dict()).items():
+                put(steps, "init/" + tag, **{k: v})
+        schedules = [[True, True, True], [False, True, True]]
+        put(steps, "cfg", W=W, H=H, B=B, code=code, nf=nf, nl=nl, R=R, lr=lr, lam=lam,
+            schedules=np.array(schedules, dtype=np.int64))
+        for it, flags in enumerate(schedules):
+            pre = "it%d" % it
+            first_code = last_code = last_images = None
+            z = torch.randn(B, code, dtype=torch.float64, generator=gen)
+            put(steps, pre, z=z)
+            n_real = 0
+            for r_idx in range(1 + R):
+                do_train = flags[r_idx]
+                if last_images is None:
+                    codev = z
+                    first_code = codev
+                else:
+                    codev = rv(last_images.detach())
+                if not do_train:
+                    last_images = g(codev.detach())
+                    last_code = codev
+                    continue
+                g.zero_grad(set_to_none=False)
+                for p in d.parameters():
+                    p.requires_grad = False
+                generated = g(codev.detach())
+                loss_g = lossfunc(d(generated), ones)
+                loss_g.backward()
+                g_opt.step()
+                rec = {"g": loss_g.item()}
+                if last_code is not None:
+                    rv.zero_grad(set_to_none=False)
+                    loss_g2 = lossfunc(d(g(codev)), ones)
+                    loss_r = lossfunc_r(codev, first_code.detach())
+                    lar = lam ** r_idx
+                    (lar * loss_r + (1 - lar) * loss_g2).backward()
+                    r_opt.step()
+                    rec["r"] = loss_r.item()
+                d.zero_grad(set_to_none=False)
+                for p in d.parameters():
+                    p.requires_grad = True
+                real = t64(B, 3, H, W, lo=0, gen=gen)
+                put(steps, pre, **{"real%d" % n_real: real})
+                n_real += 1
+                loss_d_real = lossfunc(d(real), ones)
+                loss_d_real.backward()
+                loss_d_fake = lossfunc(d(generated.detach()), zeros)
+                loss_d_fake.backward()
+                d_opt.step()
+                rec["d_real"], rec["d_fake"] = loss_d_real.item(), loss_d_fake.item()
+                put(steps, pre + "/hop%d" % r_idx, **rec)
+                last_images, last_code = generated, codev
+            for tag, net in (("g", g), ("r", rv), ("d", d)):
+                for k, v in undot(net.state_dict()).items():
+                    put(steps, pre + "/" + tag, **{k: v})
+        np.savez_compressed(os.path.join(OUT, "riter_steps.npz"), **steps)
+    for f in ("modules.npz", "models.npz", "glis_steps.npz", "glis_steps_ls.npz", "riter_steps.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

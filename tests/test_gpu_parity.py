@@ -13,11 +13,14 @@ import torch
 
 import oracle
 from oracle.step import GLISOracleTrainer
-from util import copy_params, randomize_params_, rel_err, rel_l2
+from util import FlipAwarePair, copy_params, randomize_params_, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 
 FWD_TOL, GRAD_TOL = 1e-4, 1e-3
+# A TPReLU branch mask may differ from the fp64 oracle's only where the oracle's pre-activation lies within the
+# forward tolerance of the kink (oracle/flipaware.py); everywhere else a differing bit is an error.
+FLIP_TOL = FWD_TOL
 DEV = "cuda"
 
 
@@ -309,34 +312,21 @@ def _flat_grads(flat):
     return [flat.g[o:o + p.numel()].view(p.shape).clone() for p, o in zip(flat.params, flat.offsets)]
 
 
-def _chain_grad_tol():
-    """Per-op gradient parity is GRAD_TOL in every mode (test_wn_conv2d & co.).  Through the whole
-    step two effects add up in the split-bf16 tensor-core mode (2^-17 per product instead of 2^-24):
-    a gradient crosses up to ten chained contractions with heavy cancellation, and — the larger
-    one — a pre-activation that lands within ~1e-5 of a TPReLU kink flips its mask bit, which moves
-    that element's gradient by a factor 1/a.  About one element in 1e5 does so; a per-channel sum
-    containing one (TPReLU bias gradients, the following layer's weight gradient) then shows a
-    percent-level deviation although every op is exact to 1e-5 (tools/debug_grad2.py: the same D with
-    another input batch shows 5e-6 on every tensor); a flip in a top layer also perturbs every
-    gradient below it by ~1/sqrt(#elements).  The fp32 kernels are not immune: their sums differ
-    from the fp64 oracle's by ~1e-7 relative, so a pre-activation within that distance of a kink
-    flips too.  Measured with tools/debug_flip.py at the config-1 shape (~4 M pre-activations per
-    iteration): 26 of 36 iterations agree with the oracle to 1-4e-6 on EVERY gradient, the other 10
-    contain a flip and sit between 4e-4 and 1.6e-2 (deterministic for a given seed and summation
-    order; the probability scales with the number of pre-activation elements).  Hence `_run_steps`
-    holds EVERY iteration to the flip bound (5e-2 max-norm, 3e-2 in L2, both modes) and, in fp32
-    mode, at least half of the iterations of a run to the per-op bound GRAD_TOL = 1e-3."""
-    return 5e-2
-
-
 def _lib_precision_is_fp32():
     from glis_b200 import _lib
     return _lib.default_precision == _lib.PREC_FP32
 
 
-def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
-    """Runs both trainers; checks losses (1e-4), every gradient of every iteration (against the
-    fp64 oracle, relative to the tensor's max |grad|) and the parameters after each update.
+def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5, stats=None):
+    """Runs both trainers; checks losses (1e-4), EVERY gradient of every iteration at the per-op bound
+    GRAD_TOL = 1e-3 (against the fp64 oracle, relative to the tensor's max |grad|) in both contraction modes,
+    and the parameters after each update.
+
+    Flip-aware (oracle/flipaware.py): the product runs first and reports the pre-activation of every TPReLU it
+    differentiates; the oracle's backward uses those branch masks, and `check` asserts that they differ from the
+    oracle's own only within FLIP_TOL of the kink.  Without that, one pre-activation landing on the other side
+    of a kink (probability ~ rounding error x element count) moves every gradient below it by percents and says
+    nothing about the kernels.
 
     The first RMSprop steps behave like lr*g/(0.32|g|+eps): where |g| ~ eps = 1e-6 the update
     amplifies gradient error by lr/eps, so the parameter check bounds |dp - dp_ref| by
@@ -344,18 +334,19 @@ def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
     from glis_b200.trainer import GLISTrainer
     ot = GLISOracleTrainer(og, od, lr=lr, lambda_r=0.9)
     pt = GLISTrainer(pg, pd, lr=lr, lambda_r=0.9)
+    fa = FlipAwarePair([(og, pg), (od, pd)])
     gen = torch.Generator().manual_seed(seed)
-    # (one flipped element carries a 1/B share of a batch-mean gradient: the config-4 run at B = 2 saw 5.4e-2 on
-    # the generator head's weight once the LIS kernels changed the summation order)
-    gtol = _chain_grad_tol() * max(1.0, 4.0 / B)
-    worst_per_iteration = []
     for it, (kd, kg) in enumerate(depths):
-        worst = 0.0
         real = torch.rand(B, 3, H, W, generator=gen)
         zd, zg = torch.randn(B, code, generator=gen), torch.randn(B, code, generator=gen)
         before = [[p.detach().clone() for p in net.parameters()] for net in (og, od)]
+        with fa.tap():
+            lp = pt.step(real.to(DEV), zd.to(DEV), zg.to(DEV), kd, kg)
+        fa.feed()
         lo = ot.step(real.double(), zd.double(), zg.double(), kd, kg)
-        lp = pt.step(real.to(DEV), zd.to(DEV), zg.to(DEV), kd, kg)
+        flips, total, worst_flip = fa.check(FLIP_TOL)
+        if stats is not None:
+            stats.append((flips, total, worst_flip))
         for name in ("d_real", "d_fake", "g"):
             assert abs(lp[name].item() - lo[name]) <= FWD_TOL * abs(lo[name]), (it, name, lp[name].item(), lo[name])
         assert len(lp["r"]) == len(lo["r"]) and lp["depth_g"] == lo["depth_g"] and lp["depth_d"] == lo["depth_d"]
@@ -367,12 +358,10 @@ def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
                 go = po.grad if po.grad is not None else torch.zeros_like(po)
                 gmax = go.abs().max().item()
                 if gmax > 0:
-                    worst = max(worst, rel_err(gp, go))
-                    assert rel_err(gp, go) <= gtol, (it, tag, n, rel_err(gp, go))
-                    assert rel_l2(gp, go) <= max(GRAD_TOL, gtol * 0.6), (it, tag, n, rel_l2(gp, go))
+                    assert rel_err(gp, go) <= GRAD_TOL, (it, tag, n, rel_err(gp, go), "flips", flips)
                 else:
                     assert gp.abs().max().item() == 0, (it, tag, n)
-                bound = lr * (gtol * gmax / 1e-6 + 3.2e-3)
+                bound = lr * (GRAD_TOL * gmax / 1e-6 + 3.2e-3)
                 err = ((pp.detach().cpu().double() - p0) - (po.detach() - p0)).abs().max().item()
                 assert err <= bound, (it, tag, n, err, bound)
         # RMSprop's early steps are sign-like, so fp32 and fp64 trajectories drift apart at elements
@@ -385,10 +374,9 @@ def _run_steps(og, od, pg, pd, B, H, W, code, depths, lr, seed=5):
                     pp.copy_(po.float())
                     v = state.get(po)
                     flat.v[o:o + po.numel()].copy_((v if v is not None else torch.zeros_like(po)).reshape(-1).float())
-        worst_per_iteration.append(worst)
-    if _lib_precision_is_fp32():   # iterations without a mask flip must meet the per-op gradient bound
-        strict = sum(1 for w in worst_per_iteration if w <= GRAD_TOL)
-        assert strict >= len(worst_per_iteration) // 2, worst_per_iteration
+                for pp in flat.params:
+                    pp._glis_epoch = getattr(pp, "_glis_epoch", 0) + 1      # cached weight packs are stale now
+    fa.remove()
     return ot, pt
 
 
@@ -553,8 +541,6 @@ def test_step_parity_config4_geometry():
     """BASELINE config 4 geometry: 160x160, five levels (the extra G/D layer), 1 LIS module; reduced
     width (nfeature 32) and batch so that the fp64 oracle stays fast.  Exercises 80- and 40-wide maps."""
     og, od, pg, pd = _make_pair_kw(160, 160, 32, 5, 64, 1)
-    # ~1M activations per pass: even fp32-vs-fp64 sees an occasional TPReLU mask flip (see
-    # _chain_grad_tol), so the end-of-chain bound is 1e-2 here in fp32 mode as well
     _run_steps(og, od, pg, pd, 2, 160, 160, 64, [(1, 1)], 2e-5)
 
 
@@ -563,6 +549,153 @@ def test_step_parity_config5b_nearest_upsampling():
     nearest-neighbour upsample), 1 LIS module."""
     og, od, pg, pd = _make_pair_kw(32, 32, 32, 3, 32, 1, upscaling="nearest")
     _run_steps(og, od, pg, pd, 4, 32, 32, 32, [(1, 1), (0, 1)], 1e-3)
+
+
+# ---------------------------------------------------------------- the benchmarked shapes, at size
+def _tc_plan(relation, n, hi, wi, ci, ho, wo, co, plain, k=4, s=2, p=1):
+    """The launch plan `tc_conv_kernel` uses for this geometry (glis_conv_tc_plan), or None off the tensor cores."""
+    import ctypes as C
+    from glis_b200 import _lib as L, ops
+    g = ops.ContractionSpec(False, (k, k), (s, s), (p, p), (1, 1)).geom(relation, n, hi, wi, ci, ho, wo, co)
+    lib = L.load()
+    if not lib.glis_conv_tc_supported(C.byref(g)):
+        return None
+    out = (C.c_int * 15)()
+    assert lib.glis_conv_tc_plan(C.byref(g), int(plain), out) == 0
+    names = "tw th tn n_mma tmem kblocks ksplit a_rows stages tiles_h tiles_x tiles_co total groups smem".split()
+    return dict(zip(names, list(out)))
+
+
+def _num_sms():
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
+# (kind, Cin, Cout, input H = W, batch): every conv / transposed-conv layer of BASELINE config 2 (80x80, nfeature
+# 64, 4 levels, code 256) at the batch the benchmark runs it with — D on the 2B = 128 image batch of the D update
+# and on the B = 64 batch of the G update, G at B = 64 — each as the fused (WN layer, TPReLU) pair of the builders.
+CFG2_LAYERS = [
+    ("conv", 3, 64, 80, 128), ("conv", 64, 128, 40, 128), ("conv", 128, 256, 20, 128), ("conv", 256, 512, 10, 128),
+    ("conv", 3, 64, 80, 64), ("conv", 64, 128, 40, 64), ("conv", 128, 256, 20, 64), ("conv", 256, 512, 10, 64),
+    ("deconv", 512, 256, 5, 64), ("deconv", 256, 128, 10, 64), ("deconv", 128, 64, 20, 64),
+    ("deconv_sigmoid", 64, 3, 40, 64),
+    ("head", 256, 512, 5, 64),
+]
+
+
+def _check_chain(ref_layers, prod_layers, x, seed=0):
+    """Oracle (fp64, CPU) against the product's fused chain (`run_layers`) on equal parameters: forward <= 1e-4,
+    input and every parameter gradient <= 1e-3, flip-aware (see `_run_steps`)."""
+    pm, _ = _product()
+    ref = torch.nn.Sequential(*ref_layers).double()
+    prod = torch.nn.Sequential(*prod_layers)
+    fa = FlipAwarePair([(ref, prod)])
+    gen = torch.Generator().manual_seed(seed)
+    xr = x.double().clone().requires_grad_(True)
+    xp = x.float().to(DEV).requires_grad_(True)
+    with fa.tap():
+        yp = pm.run_layers(prod_layers, xp)
+    r = torch.rand(yp.shape, generator=gen, dtype=torch.float64) * 2 - 1
+    (yp * r.float().to(DEV)).sum().backward()
+    fa.feed()
+    yr = ref(xr)
+    assert tuple(yr.shape) == tuple(yp.shape)
+    (yr * r).sum().backward()
+    flips, total, worst = fa.check(FLIP_TOL)
+    fa.remove()
+    assert rel_err(yp, yr) <= FWD_TOL, "forward %g" % rel_err(yp, yr)
+    assert rel_err(xp.grad, xr.grad) <= GRAD_TOL, "dx %g (flips %d of %d)" % (rel_err(xp.grad, xr.grad), flips, total)
+    for (n, pr), (_, pp) in zip(ref.named_parameters(), prod.named_parameters()):
+        e = rel_err(pp.grad, pr.grad)
+        assert e <= GRAD_TOL, "grad %s %g (flips %d of %d)" % (n, e, flips, total)
+    return flips, total
+
+
+@pytest.mark.parametrize("case", CFG2_LAYERS, ids=lambda c: "%s_%dto%d_%d_n%d" % c)
+def test_cfg2_layer_at_size(case, precision):
+    """Forward + data gradient + weight gradient of every config-2 layer at the benchmark's batch against the fp64
+    oracle.  These are the launches bench.py times: persistent CTAs walking SEVERAL tiles (accumulator double
+    buffering, the shared-memory ring running across tile boundaries), 208-column tiles with 2 pipeline stages,
+    split-K shares, 1600 pixel tiles on the pixel-major kernel — none of which the small shapes above reach."""
+    from glis_b200 import _lib as L
+    _, pmod = _product()
+    kind, ci, co, h, n = case
+    gen = torch.Generator().manual_seed(100 + CFG2_LAYERS.index(case))
+    if kind == "head":
+        f, hh = co, h
+        mk = lambda M: [M.WeightNormalizedLinear(ci, f * hh * hh, init_factor=0.01, scale=False, bias=False),
+                        M.View(f, hh, hh), M.TPReLU(f)]
+        x = torch.randn(n, ci, generator=gen)
+    elif kind == "deconv_sigmoid":
+        mk = lambda M: [M.WeightNormalizedConvTranspose2d(ci, co, 4, 2, 1), torch.nn.Sigmoid()]
+        x = torch.rand(n, ci, h, h, generator=gen) * 2 - 1
+    else:
+        layer = "WeightNormalizedConv2d" if kind == "conv" else "WeightNormalizedConvTranspose2d"
+        mk = lambda M: [getattr(M, layer)(ci, co, 4, 2, 1, scale=False, bias=False), M.TPReLU(co)]
+        x = torch.rand(n, ci, h, h, generator=gen) * 2 - 1
+    ref_layers = mk(oracle)
+    ref_net = torch.nn.Sequential(*ref_layers)
+    randomize_params_(ref_net, gen)
+    prod_layers = mk(pmod)
+    copy_params(torch.nn.Sequential(*prod_layers), ref_net)
+    prod_layers = [m.to(DEV) for m in prod_layers]
+    _check_chain(ref_layers, prod_layers, x)
+    if precision != "bf16x3" or kind in ("head", "deconv_sigmoid") or ci == 3:
+        return
+    # the launches really are the multi-tile ones (plans are a function of the geometry and the SM count)
+    sms = _num_sms()
+    if kind == "conv":
+        fwd = _tc_plan(L.CONV, n, h, h, ci, h // 2, h // 2, co, False)
+        dgrad = _tc_plan(L.TCONV, n, h // 2, h // 2, co, h, h, ci, True)
+    else:
+        fwd = _tc_plan(L.TCONV, n, h, h, ci, 2 * h, 2 * h, co, False)
+        dgrad = _tc_plan(L.CONV, n, 2 * h, 2 * h, co, h, h, ci, True)
+    assert fwd is not None and dgrad is not None
+    if (kind, ci, n) == ("conv", 64, 128):         # D level 1 of the 2B pass: the roofline kernel of bench.py
+        assert fwd["groups"] > sms and fwd["n_mma"] == 208 and fwd["stages"] == 2, fwd
+        assert dgrad["groups"] > 4 * sms, dgrad
+    if (kind, ci, n) == ("deconv", 128, 64):       # G level 1: 512 work items, 64-row weight stages
+        assert fwd["groups"] > 3 * sms and fwd["a_rows"] == 64, fwd
+    if (kind, ci, n) == ("conv", 128, 128):
+        assert dgrad["groups"] > sms and dgrad["n_mma"] == 208 and dgrad["stages"] == 2, dgrad
+
+
+def test_persistent_multi_tile_paths_are_covered():
+    """The plans of the config-2 launches at the benchmark's batch: at least one fused-epilogue forward and one
+    plain-output data gradient run more work items than there are SMs (so test_cfg2_layer_at_size exercises the
+    persistent loop), and the pixel-major image-side product runs 1600 pixel tiles."""
+    from glis_b200 import _lib as L
+    sms = _num_sms()
+    fwd = _tc_plan(L.CONV, 128, 40, 40, 64, 20, 20, 128, False)
+    assert fwd["groups"] == 256 and fwd["groups"] > sms and fwd["n_mma"] == 208 and fwd["stages"] == 2
+    assert _tc_plan(L.TCONV, 128, 20, 20, 128, 40, 40, 64, True)["groups"] == 1024
+    assert _tc_plan(L.TCONV, 64, 20, 20, 128, 40, 40, 64, False)["groups"] == 512
+    assert 128 * 40 * 40 // 128 == 1600            # D level 0 at 2B images: M = 128 pixels per tile
+
+
+def _whole_iteration_at_size(W, H, B, nf, nl, code, n_lis, depths, seed):
+    og, od, pg, pd = _make_pair_kw(W, H, nf, nl, code, n_lis, seed=seed)
+    stats = []
+    _run_steps(og, od, pg, pd, B, H, W, code, depths, 2e-5, stats=stats)
+    return stats
+
+
+def test_whole_iteration_config2_at_size():
+    """BASELINE configs[1] exactly as bench.py runs it: 80x80, batch 64, nfeature 64, 4 levels, code 256, 1 LIS
+    module, lr 2e-5 — one full iteration (D on 2B images, D update, G + LIS against D, G update) against the fp64
+    oracle: losses 1e-4, every gradient 1e-3, the RMSprop update."""
+    stats = _whole_iteration_at_size(80, 80, 64, 64, 4, 256, 1, [(1, 1)], seed=71)
+    flips, total, _ = stats[0]
+    assert total > 30e6 and flips <= total * 1e-4, stats      # ~39 M differentiated pre-activations per iteration
+
+
+def test_whole_iteration_config3_at_size():
+    """BASELINE configs[2]: as config 2 with 3 chained LIS modules (all run in the G update, two in the D update)."""
+    _whole_iteration_at_size(80, 80, 64, 64, 4, 256, 3, [(2, 3)], seed=72)
+
+
+def test_whole_iteration_config4_at_size():
+    """BASELINE configs[3]: 160x160, batch 32, nfeature 64, 5 levels (K = 8192 layers, 80- and 40-wide maps)."""
+    _whole_iteration_at_size(160, 160, 32, 64, 5, 256, 1, [(1, 1)], seed=73)
 
 
 def test_discriminator_dropout_runs_and_matches_in_eval():

@@ -100,15 +100,16 @@ def test_models_match_reference(golden_dir, case):
         np.testing.assert_allclose(got, ref, err_msg=n, **TOL)
 
 
-def test_glis_iterations_match_reference(golden_dir):
-    s = _load(golden_dir, "glis_steps.npz")
+@pytest.mark.parametrize("fixture,ls", [("glis_steps.npz", False), ("glis_steps_ls.npz", True)])
+def test_glis_iterations_match_reference(golden_dir, fixture, ls):
+    s = _load(golden_dir, fixture)
     cfg = _group(s, "cfg")
     W, H, B, code, nf, nl, n_lis = (int(cfg[k]) for k in ("W", "H", "B", "code", "nf", "nl", "n_lis"))
     gen = oracle.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis, "fractional").double()
     dis = oracle.build_discriminator(W, H, nf, nl, "weight", 0).double()
     gen.load_state_dict({k: _t(v) for k, v in _group(s, "init/g").items()})
     dis.load_state_dict({k: _t(v) for k, v in _group(s, "init/d").items()})
-    tr = GLISOracleTrainer(gen, dis, lr=float(cfg["lr"]), lambda_r=float(cfg["lam"]))
+    tr = GLISOracleTrainer(gen, dis, lr=float(cfg["lr"]), lambda_r=float(cfg["lam"]), ls=ls)
     for it, (kd, kg) in enumerate(cfg["depths"]):
         g = _group(s, "it%d" % it)
         out = tr.step(_t(g["real"]), _t(g["zd"]), _t(g["zg"]), depth_d=int(kd), depth_g=int(kg))
@@ -146,3 +147,34 @@ def test_builder_errors():
         oracle.GeneratorLearnedInputSpace(16, 15, 4, 2, 8, "weight", 1, "fractional")
     with pytest.raises(Exception):
         oracle.GeneratorLearnedInputSpace(16, 16, 4, 2, 8, "weight", 1, "cubic")
+
+
+def test_r_iterative_iterations_match_reference(golden_dir):
+    """oracle.riter_iteration against two outer iterations of r_iterative/main.py:428-535 run on the reference's
+    own builders with three stock RMSprops (all hops trained; then [skip, train, train])."""
+    from oracle.step import riter_iteration
+    s = _load(golden_dir, "riter_steps.npz")
+    cfg = _group(s, "cfg")
+    W, H, B, code, nf, nl, R = (int(cfg[k]) for k in ("W", "H", "B", "code", "nf", "nl", "R"))
+    gen = oracle.build_generator(W, H, nf, nl, code, "weight").double()
+    rev = oracle.build_reverser(W, H, nf // 2, nl, code, "weight", 0).double()
+    dis = oracle.build_discriminator(W, H, nf, nl, "weight", 0).double()
+    for tag, net in (("g", gen), ("r", rev), ("d", dis)):
+        net.load_state_dict({k: _t(v) for k, v in _group(s, "init/" + tag).items()})
+    gs, rs, ds = {}, {}, {}
+    for it, flags in enumerate(cfg["schedules"]):
+        flags = [bool(f) for f in flags]
+        g = _group(s, "it%d" % it)
+        reals = [_t(g["real%d" % i]) for i in range(sum(flags))]
+        out = riter_iteration(gen, rev, dis, gs, rs, ds, _t(g["z"]), reals, float(cfg["lr"]), float(cfg["lam"]), R, flags)
+        for hop, rec in enumerate(out):
+            assert (rec is None) == (not flags[hop])
+            if rec is None:
+                continue
+            want = _group(s, "it%d/hop%d" % (it, hop))
+            assert sorted(rec) == sorted(want)
+            for k in rec:
+                np.testing.assert_allclose(rec[k], want[k], err_msg="it%d hop%d %s" % (it, hop, k), **TOL)
+        for tag, net in (("g", gen), ("r", rev), ("d", dis)):
+            for k, v in net.state_dict().items():
+                np.testing.assert_allclose(v.numpy(), g[tag + "/" + k], err_msg="it%d %s %s" % (it, tag, k), **TOL)

@@ -40,3 +40,46 @@ def randomize_params_(module, gen, tprelu_range=(-0.2, 1.2)):
                 p.copy_(r * 0.4 - 0.2)
             else:
                 p.copy_(p * (0.5 + r))
+
+
+class FlipAwarePair(object):
+    """Couples the product's TPReLU pre-activation tap (``ops.PreactTap``) with the oracle's mask injection
+    (``oracle.flipaware``): run the product inside ``with pair.tap():``, call ``feed()``, run the oracle, call
+    ``check()``.
+
+    ``pairs``: [(oracle network, product network), ...] with identical parameter order.  The gradient
+    comparison that follows may then use the per-op tolerance through whole chains: both sides differentiate
+    the same piecewise-linear function, and ``check`` has verified that their masks differ only where the
+    oracle's pre-activation lies within ``tol`` (relative to the tensor's max) of the TPReLU kink."""
+
+    def __init__(self, pairs):
+        from oracle.flipaware import FlipAware
+        from oracle.modules import TPReLU as OracleTPReLU
+        self.fa = FlipAware(*[o for o, _ in pairs])
+        self.owner = []          # (product slope Parameter, oracle TPReLU module)
+        for onet, pnet in pairs:
+            slope_owner = {id(m.weight): m for m in onet.modules() if isinstance(m, OracleTPReLU)}
+            for po, pp in zip(onet.parameters(), pnet.parameters()):
+                if id(po) in slope_owner:
+                    self.owner.append((pp, slope_owner[id(po)]))
+        self._tap = None
+
+    def tap(self):
+        from glis_b200 import ops
+        self._tap = ops.PreactTap()
+        return self._tap
+
+    def feed(self):
+        """Hand the branch masks of everything recorded since ``tap()`` to the oracle's modules."""
+        by_ptr = {pp.data_ptr(): m for pp, m in self.owner}     # (parameters may have been re-homed since)
+        for a_raw, b_t, preact in self._tap.records:
+            shape = (1, -1) + (1,) * (preact.dim() - 2)
+            neg = ~((preact - b_t.detach().view(shape)) > 0)    # the kernels' own expression: !(t > 0)
+            self.fa.feed(by_ptr[a_raw.data_ptr()], neg)
+        self._tap.records = []
+
+    def check(self, tol):
+        return self.fa.check(tol)
+
+    def remove(self):
+        self.fa.remove()
