@@ -1109,9 +1109,9 @@ _ELIDED = [False]    # did the last fused forward leave its fp32 output unwritte
 
 
 class PreactTap(object):
-    """Test hook: ``with PreactTap() as tap:`` collects ``(TPReLU slope, translation, pre-activation)`` of every
-    TPReLU forward that keeps its pre-activation for a backward pass (logical ``(N, C, ...)`` shape, the very
-    tensor backward reads its branch mask from).  The parity tests hand those masks to the oracle so that both
+    """Test hook: ``with PreactTap() as tap:`` collects ``(TPReLU slope Parameter, branch mask)`` of every
+    TPReLU forward that keeps its pre-activation for a backward pass (logical ``(N, C, ...)`` shape; the mask is
+    taken from the very tensor backward reads it from).  The parity tests hand those masks to the oracle so that both
     sides differentiate the same piecewise-linear function (oracle/flipaware.py)."""
 
     active = None
@@ -1130,7 +1130,11 @@ class PreactTap(object):
     @classmethod
     def report(cls, a_raw, b_t, preact):
         if cls.active is not None and preact is not None:
-            cls.active.records.append((a_raw, b_t, preact))
+            # the branch mask as the backward kernels will compute it, !(t > 0) with t = y - b in fp32 — taken NOW:
+            # by the time a whole training iteration has run the optimizer has moved b
+            shape = (1, -1) + (1,) * (preact.dim() - 2)
+            neg = ~((preact.detach() - b_t.detach().view(shape)) > 0)
+            cls.active.records.append((a_raw, neg))
 
 
 def _may_need_backward(*tensors):

@@ -72,9 +72,7 @@ class FlipAwarePair(object):
     def feed(self):
         """Hand the branch masks of everything recorded since ``tap()`` to the oracle's modules."""
         by_ptr = {pp.data_ptr(): m for pp, m in self.owner}     # (parameters may have been re-homed since)
-        for a_raw, b_t, preact in self._tap.records:
-            shape = (1, -1) + (1,) * (preact.dim() - 2)
-            neg = ~((preact - b_t.detach().view(shape)) > 0)    # the kernels' own expression: !(t > 0)
+        for a_raw, neg in self._tap.records:
             self.fa.feed(by_ptr[a_raw.data_ptr()], neg)
         self._tap.records = []
 
