@@ -28,11 +28,12 @@ def _planes_suffice(consumer, follower, out_shape):
     return ops.consumes_planes_only(consumer._spec(), consumer.weight, out_shape, isinstance(follower, TPReLU))
 
 
-def run_layers(layers, x, following=()):
+def run_layers(layers, x, following=(), out=None):
     """Apply ``layers`` in order, running every (weight-normalized layer, TPReLU) pair as ONE
     operator: the TPReLU moves into the contraction's epilogue (``ops.wn_contraction_tprelu``).
     Module structure, parameters and results are those of calling the modules one by one.
-    ``following``: the modules the caller applies to the result next (only looked at, not run)."""
+    ``following``: the modules the caller applies to the result next (only looked at, not run).
+    ``out``: caller-owned buffer for the result of a trailing (WN layer, Sigmoid) pair (no_grad only)."""
     layers = list(layers)
     n_run = len(layers)
     layers = layers + list(following)
@@ -64,7 +65,8 @@ def run_layers(layers, x, following=()):
         elif (isinstance(m, _WeightNormalizedConvNd) and type(nxt) is nn.Sigmoid and i + 2 <= n_run
               and x.is_cuda and x.dtype == ops.torch.float32 and x.dim() == 4):
             # the generators' last two modules: the sigmoid moves into the contraction's epilogue
-            x = ops.wn_contraction_sigmoid(x, m.weight, m.scale, m.bias, m._spec())
+            x = ops.wn_contraction_sigmoid(x, m.weight, m.scale, m.bias, m._spec(),
+                                           out=out if i + 2 == n_run else None)
             i += 2
         else:
             x = m(x)
@@ -90,8 +92,28 @@ class DottedSequential(_DottedSequential):
     """Sequential container with reference-compatible dotted child names whose forward fuses
     (WN layer, TPReLU) pairs."""
 
+    def forward(self, input, out=None):
+        return run_layers(self._modules.values(), input, out=out)
+
+
+class PhiloxDropout(nn.Dropout):
+    """``nn.Dropout`` (the reference's module at model.py:52-53) whose training-mode mask comes from the
+    counter-based generator of ``glis_dropout``: capturable into the iteration's CUDA graph (a replay draws a
+    fresh mask), nothing stored for backward, reproducible on the host from (seed, counter, call)."""
+
     def forward(self, input):
-        return run_layers(self._modules.values(), input)
+        if not self.training or self.p == 0 or not input.is_cuda:
+            return super(PhiloxDropout, self).forward(input)
+        return ops.dropout(input, self.p, channel_mode=False)
+
+
+class PhiloxDropout2d(nn.Dropout2d):
+    """``nn.Dropout2d`` (model.py:344-346) on the same generator: one mask element per (image, channel)."""
+
+    def forward(self, input):
+        if not self.training or self.p == 0 or not input.is_cuda:
+            return super(PhiloxDropout2d, self).forward(input)
+        return ops.dropout(input, self.p, channel_mode=True)
 
 
 def _require_even(w, h, what):
@@ -130,7 +152,7 @@ def _encoder_levels(net, w, h, f_first, num_levels, norm, dropout2d=0):
         net.add_module("level.{0}.conv".format(level),
                        WeightNormalizedConv2d(f_prev, f, 4, 2, (1 + ph, 1 + pw), scale=affine, bias=affine))
         if level >= 1 and dropout2d > 0:
-            net.add_module("level.{0}.sd".format(level), nn.Dropout2d(dropout2d))
+            net.add_module("level.{0}.sd".format(level), PhiloxDropout2d(dropout2d))
         kind, act = _activation(norm, f)
         net.add_module("level.{0}.{1}".format(level, kind), act)
         f_prev, f = f, 2 * f
@@ -143,7 +165,7 @@ def build_discriminator(w_in, h_in, f_first, num_down_layers, norm, p_dropout=0)
     net = DottedSequential()
     f_prev, w, h = _encoder_levels(net, w_in, h_in, f_first, num_down_layers, norm)
     if p_dropout > 0:
-        net.add_module("final.dropout", nn.Dropout(p_dropout))
+        net.add_module("final.dropout", PhiloxDropout(p_dropout))
     net.add_module("final.conv", WeightNormalizedConv2d(f_prev, 1, (h, w)))
     net.add_module("final.sigmoid", nn.Sigmoid())
     net.add_module("final.view", View(1))
@@ -271,11 +293,12 @@ class GeneratorLearnedInputSpace(nn.Module):
                 return i
         return n
 
-    def forward(self, x, n_execute_lis_layers=None):
+    def forward(self, x, n_execute_lis_layers=None, out=None):
+        """``out`` (additive, no_grad only): NHWC buffer the generated images are written into."""
         lis_results = []
         for i in range(self.lis_depth(n_execute_lis_layers)):
             x = lis_residual(self.lis_layers[i], x)
             lis_results.append(x)
         x = run_layers(self.initial_linear, x, following=self.conv_layers)
-        x = run_layers(self.conv_layers, x)
+        x = run_layers(self.conv_layers, x, out=out)
         return x, lis_results

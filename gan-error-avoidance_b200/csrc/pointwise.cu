@@ -255,6 +255,24 @@ bce_logits_kernel(const float* __restrict__ logit, float target, int B, float gs
   if (threadIdx.x == 0) loss[0] = acc / (float)B;
 }
 
+// --ls: nn.MSELoss() on D's sigmoid output against a constant target (g_lis/main.py:308-311):
+// L = mean((p - t)^2), dL/dl = 2 (p - t) p (1 - p) / B.  One block, as bce_logits_kernel.
+__global__ void __launch_bounds__(PW_NT)
+lsq_logits_kernel(const float* __restrict__ logit, float target, int B, float gscale, float* __restrict__ loss,
+                  float* __restrict__ dlogit, float* __restrict__ prob) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += PW_NT) {
+    const float p = 1.f / (1.f + expf(-logit[i]));
+    const float d = p - target;
+    acc = fmaf(d, d, acc);
+    if (dlogit) dlogit[i] = gscale * 2.f * d * p * (1.f - p) / (float)B;
+    if (prob) prob[i] = p;
+  }
+  acc = block_sum<PW_NT>(acc, red);
+  if (threadIdx.x == 0) loss[0] = acc / (float)B;
+}
+
 __global__ void __launch_bounds__(PW_NT)
 mse_scaled_kernel(const float* __restrict__ u, const float* __restrict__ z, int64_t numel, float lambda,
                   float* __restrict__ loss, float* __restrict__ du, int accumulate) {
@@ -264,10 +282,10 @@ mse_scaled_kernel(const float* __restrict__ u, const float* __restrict__ z, int6
   for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
     const float d = u[i] - z[i];
     acc = fmaf(d, d, acc);
-    if (du) du[i] = accumulate ? du[i] + k * d : k * d;
+    if (du) du[i] = (accumulate & 1) ? du[i] + k * d : k * d;
   }
   acc = block_sum<PW_NT>(acc, red);
-  if (threadIdx.x == 0) atomicAdd(loss, acc * lambda / (float)numel);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * ((accumulate & 2) ? 1.f : lambda) / (float)numel);
 }
 
 __global__ void __launch_bounds__(PW_NT)
@@ -351,6 +369,64 @@ philox_fill_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint64
       if (q * 4 + j < numel) out[q * 4 + j] = v[j];
   }
 }
+
+// ---- dropout (nn.Dropout / nn.Dropout2d, common/model.py:52-53, :344-346) -------------------------------------
+// keep(e) for mask element e of a draw = u01(Philox4x32-10(key = seed, counter = {e / 4, stream})[e % 4]) >= p, with
+// stream = *counter + call: `counter` lives in device memory and is advanced once per training iteration
+// (glis_counter_add), `call` numbers the dropout calls inside an iteration — so a CUDA-graph replay draws a fresh
+// mask every time, forward and backward of one call regenerate the SAME mask (nothing is stored), and the host can
+// reproduce any mask from (seed, counter value, call).  Element mode: one mask element per tensor element (storage
+// order); channel mode (Dropout2d): one per (n, c), tensor element i of an NHWC tensor -> (i / (HW*C)) * C + i % C.
+__device__ __forceinline__ void philox4_stream(uint64_t seed, uint64_t quad, uint64_t stream, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c, k);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+__global__ void __launch_bounds__(PW_NT)
+dropout_elem_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, float p, float keep_scale,
+                    uint64_t seed, const uint64_t* __restrict__ counter, uint64_t call) {
+  const uint64_t stream = (counter ? *counter : 0ull) + call;
+  const int64_t quads = (numel + 3) >> 2;
+  const bool vec = ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0;
+  for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PW_NT) {
+    uint32_t r[4];
+    philox4_stream(seed, (uint64_t)q, stream, r);
+    if (vec && q * 4 + 3 < numel) {
+      float4 v = reinterpret_cast<const float4*>(x)[q];
+      v.x = u01(r[0]) >= p ? v.x * keep_scale : 0.f;
+      v.y = u01(r[1]) >= p ? v.y * keep_scale : 0.f;
+      v.z = u01(r[2]) >= p ? v.z * keep_scale : 0.f;
+      v.w = u01(r[3]) >= p ? v.w * keep_scale : 0.f;
+      reinterpret_cast<float4*>(out)[q] = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (q * 4 + j < numel) out[q * 4 + j] = u01(r[j]) >= p ? x[q * 4 + j] * keep_scale : 0.f;
+    }
+  }
+}
+
+// channel mode: `chan_stride` = elements per image (H*W*C for NHWC with inner == 1; C*inner images laid out NCHW use
+// element -> (i / (C*inner)) * C + (i / inner) % C)
+__global__ void __launch_bounds__(PW_NT)
+dropout_channel_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, int C, int64_t per_image,
+                       int inner, float p, float keep_scale, uint64_t seed, const uint64_t* __restrict__ counter,
+                       uint64_t call) {
+  const uint64_t stream = (counter ? *counter : 0ull) + call;
+  for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
+    const int64_t e = (i / per_image) * C + (i / inner) % C;
+    uint32_t r[4];
+    philox4_stream(seed, (uint64_t)(e >> 2), stream, r);
+    const uint32_t w = (e & 3) == 0 ? r[0] : (e & 3) == 1 ? r[1] : (e & 3) == 2 ? r[2] : r[3];
+    out[i] = u01(w) >= p ? x[i] * keep_scale : 0.f;
+  }
+}
+
+__global__ void counter_add_kernel(uint64_t* counter, uint64_t inc) { *counter += inc; }
 
 }  // namespace glis
 
@@ -483,6 +559,42 @@ extern "C" int glis_bce_logits(const float* logit, float target, int B, float gs
   GLIS_REQUIRE(B > 0, GLIS_E_BADARG, "glis_bce_logits: empty batch");
   bce_logits_kernel<<<1, PW_NT, 0, (cudaStream_t)stream>>>(logit, target, B, gscale, loss, dlogit, prob);
   GLIS_CHECK_LAUNCH("glis_bce_logits");
+  return GLIS_OK;
+}
+
+extern "C" int glis_lsq_logits(const float* logit, float target, int B, float gscale, float* loss, float* dlogit,
+                               float* prob, void* stream) {
+  GLIS_REQUIRE(logit && loss, GLIS_E_BADARG, "glis_lsq_logits: NULL pointer");
+  GLIS_REQUIRE(B > 0, GLIS_E_BADARG, "glis_lsq_logits: empty batch");
+  lsq_logits_kernel<<<1, PW_NT, 0, (cudaStream_t)stream>>>(logit, target, B, gscale, loss, dlogit, prob);
+  GLIS_CHECK_LAUNCH("glis_lsq_logits");
+  return GLIS_OK;
+}
+
+extern "C" int glis_dropout(const float* x, float* out, int64_t numel, int C, int inner, int64_t per_image,
+                            int channel_mode, float p, uint64_t seed, const void* counter, uint64_t call,
+                            void* stream) {
+  GLIS_REQUIRE(x && out, GLIS_E_BADARG, "glis_dropout: NULL pointer");
+  GLIS_REQUIRE(numel >= 0 && p >= 0.f && p < 1.f, GLIS_E_BADARG, "glis_dropout: bad size or probability (0 <= p < 1)");
+  if (numel == 0) return GLIS_OK;
+  const float keep_scale = 1.f / (1.f - p);
+  if (channel_mode) {
+    GLIS_REQUIRE(C > 0 && inner > 0 && per_image > 0 && per_image % ((int64_t)C * inner) == 0, GLIS_E_BADARG,
+                 "glis_dropout: channel mode needs C, inner and the elements per image");
+    dropout_channel_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+        x, out, numel, C, per_image, inner, p, keep_scale, seed, (const uint64_t*)counter, call);
+  } else {
+    dropout_elem_kernel<<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(
+        x, out, numel, p, keep_scale, seed, (const uint64_t*)counter, call);
+  }
+  GLIS_CHECK_LAUNCH("glis_dropout");
+  return GLIS_OK;
+}
+
+extern "C" int glis_counter_add(void* counter, uint64_t inc, void* stream) {
+  GLIS_REQUIRE(counter, GLIS_E_BADARG, "glis_counter_add: NULL pointer");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)counter, inc);
+  GLIS_CHECK_LAUNCH("glis_counter_add");
   return GLIS_OK;
 }
 

@@ -8,7 +8,8 @@
 Every flag of the reference script (g_lis/main.py:41-166) is accepted with the same name, type
 and default.  Added: ``--synthetic`` (uniform [0,1) images generated on the device; no dataset
 needed), ``--seed``, ``--precision fp32|bf16x3|bf16``, ``--no_graph``, ``--log_interval``; under
-``torchrun`` the batch is sharded over the ranks (``--batch_size`` is per GPU).
+``torchrun`` the batch is sharded over the ranks (``--batch_size`` is per GPU; every rank draws its own latent
+codes and images, the LIS depths agree across ranks).  ``--ls`` and ``--d_dropout`` run on the kernels too.
 
 What runs on the device is one `GLISTrainer.step` per iteration (g_lis/main.py:526-589).  Host-side
 extras of the reference that are out of this path's scope (loss plots, t-SNE, Inception score)
@@ -18,6 +19,7 @@ state}.pt`, reference key names) and the latent-reconstruction test are.
 from __future__ import print_function
 
 import argparse
+import contextlib
 import os
 import random
 import sys
@@ -103,20 +105,66 @@ def resolve_geometry(opt):
     return opt
 
 
+class NoiseSource(object):
+    """The two latent batches of an iteration (``torch.randn(B, code)`` at g_lis/main.py:561,576) from the device
+    Philox generator, keyed by the PER-RANK data seed and the iteration number: data-parallel ranks draw different
+    codes (N ranks x B samples are N*B distinct samples), nothing crosses PCIe, and a resumed run continues the
+    stream where the checkpoint left it."""
+
+    STRIDE = 1 << 22          # Philox counter blocks reserved per iteration (4 floats each: B*code <= 16 M)
+
+    def __init__(self, batch, code, device, data_seed):
+        from glis_b200 import ops
+        self.ops, self.seed = ops, int(data_seed)
+        self.z_d = torch.empty(batch, code, device=device)
+        self.z_g = torch.empty(batch, code, device=device)
+
+    @staticmethod
+    def streams(data_seed, iteration):
+        """((seed, offset) of z_d, (seed, offset) of z_g) for one iteration."""
+        off = int(iteration) * NoiseSource.STRIDE
+        return (int(data_seed) + 7, off), (int(data_seed) + 13, off)
+
+    def draw(self, iteration):
+        (sd, od), (sg, og) = self.streams(self.seed, iteration)
+        self.ops.randn_(self.z_d, sd, od)
+        self.ops.randn_(self.z_g, sg, og)
+        return self.z_d, self.z_g
+
+
+@contextlib.contextmanager
+def private_depth_rng(gen):
+    """Run forward-only side work (sample grids, the reconstruction test) without touching the training run's
+    LIS-depth draws: ``GeneratorLearnedInputSpace.lis_depth`` consumes one ``rng.random()`` per module even when
+    the depth is forced (as the reference does, common/model.py:286-294), and rank 0 alone draws sample grids — on
+    the shared stream that would shift rank 0's later depths against the other ranks'."""
+    saved, gen.rng = gen.rng, random.Random(0)
+    try:
+        yield
+    finally:
+        gen.rng = saved
+
+
 class SyntheticData(object):
     """U[0,1) image batches from the device Philox generator (the benchmark's data source)."""
 
-    def __init__(self, opt, device, seed):
+    def __init__(self, opt, device, seed, out=None):
         from glis_b200 import ops
         self.ops, self.seed, self.calls = ops, seed, 0
-        self.buf = torch.empty(opt.batch_size, 3, opt.height, opt.width, device=device).contiguous(
-            memory_format=torch.channels_last)
+        self.buf = out if out is not None else torch.empty(
+            opt.batch_size, 3, opt.height, opt.width, device=device).contiguous(memory_format=torch.channels_last)
         self.test = torch.rand(min(64, opt.vis_row * opt.vis_col), 3, opt.height, opt.width,
                                generator=torch.Generator().manual_seed(seed)).to(device)
 
     def next_batch(self):
         self.calls += 1
         return self.ops.uniform_(self.buf, self.seed, self.calls * (1 << 24))
+
+    def position(self):
+        return {"index_shuffle": torch.zeros(0, dtype=torch.long), "current_sample": self.calls}
+
+    def restore(self, state):
+        self.calls = int(state.get("current_sample", 0))
 
 
 class DatasetData(object):
@@ -161,6 +209,15 @@ class DatasetData(object):
                 self.current, self.shuffle = 0, torch.randperm(self.train_index.size(0))
         return self.host.to(self.device, non_blocking=True)
 
+    def position(self):
+        """``index_shuffle`` / ``current_sample`` of the reference's state file (g_lis/main.py:350-357)."""
+        return {"index_shuffle": self.shuffle.clone(), "current_sample": self.current}
+
+    def restore(self, state):
+        sh = state.get("index_shuffle")
+        if sh is not None and sh.numel() == self.train_index.size(0):
+            self.shuffle, self.current = sh.clone(), int(state.get("current_sample", 0))
+
 
 def reconstruction_test(gen, targets, opt):
     """Latent-reconstruction error of held-out images (g_lis/main.py:398-453): 50 RMSprop steps on
@@ -169,6 +226,16 @@ def reconstruction_test(gen, targets, opt):
     gen.eval()
     for p in gen.parameters():
         p.requires_grad_(False)
+    total = 0.0
+    with private_depth_rng(gen):
+        total = _reconstruction_loop(gen, targets, opt)
+    for p in gen.parameters():
+        p.requires_grad_(True)
+    gen.train(was_training)
+    return total / max(1, targets.size(0))
+
+
+def _reconstruction_loop(gen, targets, opt):
     total = 0.0
     for i in range(0, targets.size(0), opt.batch_size):
         tgt = targets[i:i + opt.batch_size]
@@ -183,10 +250,46 @@ def reconstruction_test(gen, targets, opt):
         with torch.no_grad():
             out, _ = gen(code)
             total += torch.nn.functional.mse_loss(out, tgt).item() * tgt.size(0)
-    for p in gen.parameters():
-        p.requires_grad_(True)
-    gen.train(was_training)
-    return total / max(1, targets.size(0))
+    return total
+
+
+def new_history(r_iterations):
+    """The loss-history groups of g_lis/main.py:316-319."""
+    from common.plotting import History
+    h = History()
+    h.add_group("loss-r-mix", ["train-r%d" % i for i in range(r_iterations)], increasing=False)
+    h.add_group("loss-g-mix", ["train-g%d" % i for i in range(1 + r_iterations)], increasing=False)
+    h.add_group("loss-d-mix", ["train-d-real"] + ["train-d-fake%d" % i for i in range(1 + r_iterations)], increasing=False)
+    return h
+
+
+def state_for_saving(state, history, data):
+    """The reference's ``*_state.pt`` (g_lis/main.py:350-357): index_shuffle, current_iter, best_iter, min_loss,
+    current_sample and the PICKLED history."""
+    out = {k: state[k] for k in ("current_iter", "best_iter", "min_loss")}
+    out.update(data.position())
+    out["history"] = history.to_string()
+    return out
+
+
+def history_from_state(state, r_iterations):
+    """History of a loaded state file: the reference's pickled string (python-2 pickles included), a History
+    object, or the plain list round-1 checkpoints of this repository carried."""
+    from common.plotting import History
+    h = state.get("history")
+    if isinstance(h, (bytes, str)):
+        return History.from_string(h)
+    if isinstance(h, History):
+        return h
+    hist = new_history(r_iterations)
+    for rec in (h or []):
+        it, d_real, d_fake, g, r = rec
+        hist.add_value("loss-d-mix", "train-d-real", it, d_real)
+        hist.add_value("loss-d-mix", "train-d-fake0", it, d_fake)
+        hist.add_value("loss-g-mix", "train-g0", it, g)
+        for i, v in enumerate(r):
+            hist.add_value("loss-r-mix", "train-r%d" % i, it, min(max(v, 0.0), 1.0))
+    return hist
 
 
 def save_state(path, prefix, trainer, state):
@@ -241,22 +344,33 @@ def main(argv=None):
     gen = GeneratorLearnedInputSpace(opt.width, opt.height, opt.nfeature, opt.nlayer, opt.code_size, opt.norm,
                                      n_lis_layers=opt.r_iterations, upscaling=opt.g_upscaling).to(device)
     dis = build_discriminator(opt.width, opt.height, opt.nfeature, opt.nlayer, opt.norm, opt.d_dropout).to(device)
+    # the stochastic LIS depth must agree across ranks: its draws come from a generator seeded identically
+    # everywhere that nothing but the training loop touches (private_depth_rng shields it from sample grids / tests)
+    gen.rng = random.Random(opt.seed)
     if rank == 0:
         print(gen)
         print(dis)
-    if opt.ls:
-        raise NotImplementedError("--ls (LSGAN loss) is not part of the accelerated path yet")
     sync = dp.OverlappedGradSync(world) if world > 1 else None
-    trainer = GLISTrainer(gen, dis, lr=opt.lr, lambda_r=opt.lambda_r, grad_sync=sync)
+    trainer = GLISTrainer(gen, dis, lr=opt.lr, lambda_r=opt.lambda_r, grad_sync=sync, ls=opt.ls)
 
     if rank == 0:
         for sub in ("", "samples", "net_archive", "log", "running_test"):
             os.makedirs(os.path.join(opt.save_path, sub), exist_ok=True)
-    data = SyntheticData(opt, device, data_seed) if opt.synthetic else DatasetData(opt, device, rank, world)
+    use_graph = not opt.no_graph
+    graphed = GraphedStep(trainer, opt.batch_size, opt.height, opt.width, opt.code_size, device) if use_graph else None
+    # synthetic images are generated straight into the step's static input (the first half of D's 2B batch)
+    data = SyntheticData(opt, device, data_seed, out=graphed.real if graphed is not None else None) if opt.synthetic \
+        else DatasetData(opt, device, rank, world)
+    noise = NoiseSource(opt.batch_size, opt.code_size, device, data_seed)
 
-    state = {"current_iter": 0, "best_iter": 0, "min_loss": 1e100, "history": []}
+    state = {"current_iter": 0, "best_iter": 0, "min_loss": 1e100}
+    history = new_history(opt.r_iterations)
     if opt.load_path is not None:
-        state = load_state(opt.load_path, opt.net if opt.final_test else "last", trainer, opt.load_tolerant)
+        loaded = load_state(opt.load_path, opt.net if opt.final_test else "last", trainer, opt.load_tolerant)
+        state.update({k: loaded[k] for k in ("current_iter", "best_iter", "min_loss") if k in loaded})
+        history = history_from_state(loaded, opt.r_iterations)
+        data.restore(loaded)
+        gen.rng = random.Random(opt.seed * 1000003 + int(state["current_iter"]))   # same on every rank
         vis_code = torch.load(os.path.join(opt.load_path, "samples", "vis_code.pt")).to(device)
     else:
         vis_code = torch.randn(opt.vis_row * opt.vis_col, opt.code_size).to(device)
@@ -266,31 +380,33 @@ def main(argv=None):
         print("loss = {0}".format(reconstruction_test(gen, data.test, opt)))
         return
 
-    use_graph = not opt.no_graph and opt.d_dropout == 0
-    graphed = GraphedStep(trainer, opt.batch_size, opt.height, opt.width, opt.code_size, device) if use_graph else None
     forced = opt.r_iterations if opt.always_train_all else None   # the reference's `opr` typo, fixed (App. D)
 
     def visualize(it):
         import torchvision
         was = gen.training
         gen.eval()
-        with torch.no_grad():
+        with torch.no_grad(), private_depth_rng(gen):
             img, _ = gen(vis_code, n_execute_lis_layers="all")
         gen.train(was)
         torchvision.utils.save_image(img * 2 - 1 if opt.output_scale else img,
                                      os.path.join(opt.save_path, "samples", "sample_{0}.jpg".format(it)),
                                      nrow=opt.vis_row)
 
+    def checkpoint(prefix, it):
+        state["current_iter"] = it
+        save_state(opt.save_path, prefix, trainer, state_for_saving(state, history, data))
+
     it = state["current_iter"]
     while it < opt.niter:
         t0 = time.time()
         it += 1
         real = data.next_batch()
-        z_d = torch.randn(opt.batch_size, opt.code_size).to(device, non_blocking=True)
-        z_g = torch.randn(opt.batch_size, opt.code_size).to(device, non_blocking=True)
+        z_d, z_g = noise.draw(it)
         depth_d, depth_g = gen.lis_depth(forced), gen.lis_depth(forced)
         if graphed is not None:
-            out = graphed.step(real, z_d, z_g, depth_d, depth_g)
+            in_place = real.data_ptr() == graphed.real.data_ptr()
+            out = graphed.step(None if in_place else real, z_d, z_g, depth_d, depth_g)
         else:
             out = trainer.step(real, z_d, z_g, depth_d, depth_g)
         if rank == 0 and it % opt.log_interval == 0:
@@ -301,24 +417,26 @@ def main(argv=None):
             msg += ["r%d: %.4f" % (i, v) for i, v in enumerate(r)]
             msg.append("t:%.4fs" % (time.time() - t0))
             print(" ".join(msg))
-            state["history"].append((it, vals["d_real"], vals["d_fake"], vals["g"], r))
+            # the reference's history lines (g_lis/main.py:597-613): the index of a fake / g line is the LIS depth
+            history.add_value("loss-d-mix", "train-d-real", it, vals["d_real"])
+            history.add_value("loss-d-mix", "train-d-fake%d" % depth_d, it, vals["d_fake"])
+            history.add_value("loss-g-mix", "train-g%d" % depth_g, it, vals["g"])
+            for i, v in enumerate(r):
+                history.add_value("loss-r-mix", "train-r%d" % i, it, min(max(v, 0.0), 1.0))
         if rank == 0 and it % opt.vis_interval == 0:
             visualize(it)
         if it % opt.test_interval == 0:
             loss = reconstruction_test(gen, data.test, opt)
             if rank == 0:
                 print("Testing ... loss = {0}".format(loss))
-                state["current_iter"] = it
                 if loss < state["min_loss"]:
                     state["min_loss"], state["best_iter"] = loss, it
-                    save_state(opt.save_path, "best", trainer, state)
-                save_state(opt.save_path, "last", trainer, state)
+                    checkpoint("best", it)
+                checkpoint("last", it)
         if rank == 0 and it % opt.save_interval == 0:
-            state["current_iter"] = it
-            save_state(opt.save_path, it, trainer, state)
+            checkpoint(it, it)
     if rank == 0:
-        state["current_iter"] = it
-        save_state(opt.save_path, "last", trainer, state)
+        checkpoint("last", it)
 
 
 if __name__ == "__main__":

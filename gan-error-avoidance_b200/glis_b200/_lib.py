@@ -57,6 +57,9 @@ SIGNATURES = {
     "glis_channel_sum": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "glis_bce_logits": [_vp, _f, _i, _f, _vp, _vp, _vp, _vp],
     "glis_mse_scaled": [_vp, _vp, _i64, _f, _vp, _vp, _i, _vp],
+    "glis_lsq_logits": [_vp, _f, _i, _f, _vp, _vp, _vp, _vp],
+    "glis_dropout": [_vp, _vp, _i64, _i, _i, _i64, _i, _f, _u64, _vp, _u64, _vp],
+    "glis_counter_add": [_vp, _u64, _vp],
     "glis_rmsprop": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "glis_randn": [_vp, _i64, _u64, _u64, _vp],
     "glis_uniform": [_vp, _i64, _u64, _u64, _vp],

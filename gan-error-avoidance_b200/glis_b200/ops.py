@@ -361,6 +361,15 @@ def refresh_packs(flat, part="all", side=True):
         pw.pending = (done, kinds)
 
 
+def forget_pending(flat):
+    """Drop the 'rebuild in flight on the side stream' marks of ``flat``'s packs — after the caller has joined the
+    side stream itself (their events were recorded inside a CUDA-graph capture, or the join made them moot)."""
+    for p in flat.params:
+        cached = getattr(p, "_glis_packed", None)
+        if cached is not None:
+            cached[1].pending = None
+
+
 def wn_prepare(weight, scale, spec, want_io=True, want_oi=True):
     """(norm [Cout], pack_io [T][Cin][Cout], pack_oi [T][Cout][Cin]) of the effective weights (uncached)."""
     pw = PackedWeights(weight, scale, spec)
@@ -400,11 +409,22 @@ def tc_supported(g):
     return bool(L.load().glis_conv_tc_supported(C.byref(g)))
 
 
-def _launch_geom(spec, relation, in_shape, out_shape_nchw, like):
+def _usable_out(buf, shape, like):
+    """``buf`` if the caller's output buffer can take an NHWC result of NCHW ``shape`` on ``like``'s device."""
+    if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != torch.float32 or buf.device != like.device:
+        return None
+    if not buf.is_contiguous(memory_format=torch.channels_last if buf.dim() == 4 else torch.contiguous_format):
+        return None
+    return buf
+
+
+def _launch_geom(spec, relation, in_shape, out_shape_nchw, like, out=None):
     if len(in_shape) == 4:
         n, ci, hi, wi = in_shape
         _, co, ho, wo = out_shape_nchw
-        out = _empty_nhwc(n, co, ho, wo, like)
+        out = _usable_out(out, (n, co, ho, wo), like)
+        if out is None:
+            out = _empty_nhwc(n, co, ho, wo, like)
     else:
         n, ci = in_shape
         hi = wi = ho = wo = 1
@@ -500,7 +520,7 @@ def unfolded_planes(x, lo=True):
 
 
 def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
-                       want_preact, want_planes, want_f32=True):
+                       want_preact, want_planes, want_f32=True, out_buf=None):
     """The two image-side launches as 1x1 tensor-core products (see image_side_mode)."""
     prec = spec.precision
     lo = prec == L.PREC_BF16X3
@@ -539,20 +559,23 @@ def _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bia
     with L.timed("image_side fold M=%d N=%d K=%d tc" % (n * hi * wi, j, ci)):
         L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xp[0]), L.ptr16(xp[1]), L.ptr16(wp[0]), L.ptr16(wp[1]),
                C.byref(ep), L.ptr(cols), None, None, prec, L.stream())
-    out = _empty_nhwc(n, co, ho, wo, xp[0])
+    out = _usable_out(out_buf, (n, co, ho, wo), xp[0])
+    if out is None:
+        out = _empty_nhwc(n, co, ho, wo, xp[0])
     L.call("glis_fold4x4s2", L.ptr(cols), n, hi, wi, co, L.ptr(bias), act, L.ptr(out), L.stream())
     return out, None, None
 
 
 def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_NONE, act_a=None, act_b=None,
-           want_preact=False, want_planes=False, want_f32=True):
+           want_preact=False, want_planes=False, want_f32=True, out_buf=None):
     """One gather-GEMM launch (tensor cores when the geometry tiles, FFMA otherwise).
 
     ``x``: fp32 NHWC-dense (or 2-D) input; ``forward_pack`` selects the layer's forward
     ([T][Cout][Cin] K-major / [T][Cin][Cout] fp32) or data-gradient packs.
     Returns (out_fp32, preact or None, (hi, lo) planes of out or None).  ``want_f32=False`` (the caller
     knows that every consumer of the output reads its planes): a tensor-core launch that writes planes
-    leaves the fp32 buffer unwritten and marks it ``_glis_f32_invalid``.
+    leaves the fp32 buffer unwritten and marks it ``_glis_f32_invalid``.  ``out_buf``: write the fp32 result into
+    this caller-owned NHWC buffer (ignored when its shape / layout does not fit).
     """
     in_shape = tuple(x.shape)
     prec = spec.precision
@@ -564,9 +587,9 @@ def launch(spec, relation, x, out_shape, pw, forward_pack, bias=None, act=L.ACT_
         mode = None
     if mode is not None:
         return _launch_image_side(mode, spec, relation, x, out_shape, pw, forward_pack, bias, act, act_a, act_b,
-                                  want_preact, want_planes, want_f32)
+                                  want_preact, want_planes, want_f32, out_buf)
     like = x._glis_planes_only[0] if isinstance(x, PlanesOnly) else x
-    g, out = _launch_geom(spec, relation, in_shape, out_shape, like)
+    g, out = _launch_geom(spec, relation, in_shape, out_shape, like, out_buf)
     preact = torch.empty_like(out) if want_preact else None
     use_tc = _use_tc(spec, relation, in_shape, out_shape)
     planes = None
@@ -663,8 +686,14 @@ def _take_scratch(weight):
     (zeroed once per backward with the gradients) or a fresh zeros tensor."""
     sc = getattr(weight, "_glis_scratch", None)
     if sc is not None:
-        return sc
-    return torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        # the weight-gradient kernels ADD into this buffer; the owner zero-fills it once per zero_grad.  A second
+        # backward through the same layer before the next zero_grad (the reference's own D pattern of two
+        # `.backward()` calls, gradient accumulation) must not see the first one's sums: clear it here
+        # (the caller clears it on the stream the weight gradient runs on, behind the previous projection)
+        dirty = getattr(weight, "_glis_scratch_dirty", False)
+        weight._glis_scratch_dirty = True
+        return sc, dirty
+    return torch.zeros_like(weight, memory_format=torch.contiguous_format), False
 
 
 def _touch_hooks(*params):
@@ -842,7 +871,7 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
 
     dw = dscale = dbias = None
     if need_dw or need_dscale:
-        graw = _take_scratch(weight)
+        graw, graw_stale = _take_scratch(weight)
         if spec.transposed:   # small = x (Cin), big = dy (Cout)
             g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin)
             small, big = xc, dyc
@@ -877,6 +906,8 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
             acc = 0
 
         def weight_gradient():
+            if graw_stale:
+                graw.zero_()
             if isw is not None:
                 n_, hs, ws, ca, c_img = isw
                 g1 = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
@@ -983,13 +1014,13 @@ class WNContractionSigmoid(torch.autograd.Function):
     kernel).  Backward: ``dy = dout * s * (1 - s)`` from the saved output, then the layer's backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, bias, spec):
+    def forward(ctx, x, weight, scale, bias, spec, out_buf=None):
         xc = _nhwc(x)
         shape = _layer_shapes(xc, weight, spec)
         pw = packed_weights(weight, scale, spec)
         b = None if bias is None else bias.detach().reshape(-1).contiguous()
         rel_f = L.TCONV if spec.transposed else L.CONV
-        out, _, _ = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_SIGMOID)
+        out, _, _ = launch(spec, rel_f, xc, shape, pw, forward_pack=True, bias=b, act=L.ACT_SIGMOID, out_buf=out_buf)
         ctx.spec, ctx.pw, ctx.bias_param = spec, pw, bias
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.x_planes = getattr(xc, "_glis_planes", None)
@@ -1014,10 +1045,13 @@ class WNContractionSigmoid(torch.autograd.Function):
         dx, dw, dscale, dbias = _layer_backward(ctx.spec, ctx.pw, xc, dy, None, ni[0], ni[1],
                                                 ctx.pw.scale is not None and ni[2],
                                                 ctx.bias_shape is not None and ni[3], ctx.bias_shape, ctx.bias_param)
-        return dx, dw, dscale, dbias, None
+        return dx, dw, dscale, dbias, None, None
 
 
-def wn_contraction_sigmoid(x, weight, scale, bias, spec):
+def wn_contraction_sigmoid(x, weight, scale, bias, spec, out=None):
+    """``out``: (under no_grad) a caller-owned NHWC buffer the images are written into."""
+    if out is not None and not torch.is_grad_enabled():
+        return WNContractionSigmoid.apply(x, weight, scale, bias, spec, out)
     return WNContractionSigmoid.apply(x, weight, scale, bias, spec)
 
 
@@ -1416,9 +1450,106 @@ def bce_logits(logit, target, gscale=1.0, want_grad=True, want_prob=False):
     return loss, dl, pr
 
 
-def mse_scaled(u, z, lam, du=None, accumulate=False):
+def mse_scaled(u, z, lam, du=None, accumulate=False, unscaled_loss=False):
+    """loss[1] = lam * mean((u - z)^2) (or the plain mean with ``unscaled_loss``); du (+)= 2 lam (u - z) / numel."""
     uc, zc = u.detach().contiguous(), z.detach().contiguous()
     loss = torch.empty(1, device=uc.device, dtype=torch.float32)
     L.call("glis_mse_scaled", L.ptr(uc), L.ptr(zc), uc.numel(), float(lam), L.ptr(loss), L.ptr(du),
-           1 if accumulate else 0, L.stream())
+           (1 if accumulate else 0) | (2 if unscaled_loss else 0), L.stream())
     return loss
+
+
+def lsq_logits(logit, target, gscale=1.0, want_grad=True, want_prob=False):
+    """(loss[1], dlogit or None, prob or None) for --ls: mean((sigmoid(logit) - target)^2) (g_lis/main.py:308-311)."""
+    lg = logit.detach().reshape(-1).contiguous()
+    loss = torch.empty(1, device=lg.device, dtype=torch.float32)
+    dl = torch.empty_like(lg) if want_grad else None
+    pr = torch.empty_like(lg) if want_prob else None
+    L.call("glis_lsq_logits", L.ptr(lg), float(target), lg.numel(), float(gscale), L.ptr(loss), L.ptr(dl),
+           L.ptr(pr), L.stream())
+    return loss, dl, pr
+
+
+# ---------------------------------------------------------------------------- dropout
+class DropoutClock(object):
+    """Where the dropout masks come from: ``keep = Philox(seed, stream = counter + call, element) >= p``.
+
+    ``counter`` is a device uint64 advanced by ``tick()`` — once per training iteration, inside the captured
+    graph — and ``call`` numbers the dropout calls since the last tick (a Python count, frozen per call site by a
+    capture).  So eager calls never repeat a mask, a CUDA-graph replay draws fresh masks without any host work,
+    and backward regenerates the mask of its forward from (counter, call) instead of storing it.  ``seed`` differs
+    per data-parallel rank (dp.seed_everything)."""
+
+    TICK = 1 << 20           # > dropout calls per iteration
+    seed = None
+    _counter = {}
+    calls = 0
+
+    @classmethod
+    def counter(cls, device):
+        c = cls._counter.get(device)
+        if c is None:
+            c = cls._counter[device] = torch.zeros(1, device=device, dtype=torch.int64)
+        return c
+
+    @classmethod
+    def get_seed(cls):
+        if cls.seed is None:
+            cls.seed = torch.initial_seed() & 0x7fffffffffffffff
+        return cls.seed
+
+    @classmethod
+    def tick(cls, device):
+        L.call("glis_counter_add", C.c_void_p(cls.counter(device).data_ptr()), cls.TICK, L.stream())
+        cls.calls = 0
+
+    @classmethod
+    def next_call(cls):
+        if cls.calls >= cls.TICK:
+            raise RuntimeError("glis_b200: %d dropout calls without a DropoutClock.tick()" % cls.calls)
+        cls.calls += 1
+        return cls.calls - 1
+
+
+class DropoutFunction(torch.autograd.Function):
+    """``nn.Dropout(p)`` (common/model.py:52-53) / ``nn.Dropout2d(p)`` (:344-346) in training mode on the
+    counter-based generator of ``glis_dropout``; backward = the same call on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, p, channel_mode):
+        xc = _nhwc(x)
+        out = torch.empty_like(xc)
+        ctx.args = DropoutFunction._args(xc, p, channel_mode, DropoutClock.next_call())
+        DropoutFunction._run(xc, out, ctx.args)
+        return out
+
+    @staticmethod
+    def _args(xc, p, channel_mode, call):
+        if channel_mode and xc.dim() != 4:
+            raise RuntimeError("glis_b200: Dropout2d expects a 4-D tensor")
+        c = xc.shape[1]
+        per_image = xc.numel() // max(1, xc.shape[0])
+        return (c, per_image, 1 if channel_mode else 0, float(p), DropoutClock.get_seed(),
+                DropoutClock.counter(xc.device), call)
+
+    @staticmethod
+    def _run(src, dst, args):
+        c, per_image, mode, p, seed, counter, call = args
+        L.call("glis_dropout", L.ptr(src), L.ptr(dst), src.numel(), c, 1, per_image, mode, p, seed,
+               C.c_void_p(counter.data_ptr()), call, L.stream())
+
+    @staticmethod
+    def backward(ctx, dout):
+        dc = _nhwc(dout)
+        dx = torch.empty_like(dc)
+        DropoutFunction._run(dc, dx, ctx.args)
+        return dx, None, None
+
+
+def dropout(x, p, channel_mode=False):
+    """Training-mode dropout of a CUDA fp32 tensor (2-D, or 4-D handled in NHWC storage order)."""
+    if p <= 0:
+        return x
+    if p >= 1:
+        raise RuntimeError("glis_b200: dropout probability must be < 1")
+    return DropoutFunction.apply(x, p, channel_mode)

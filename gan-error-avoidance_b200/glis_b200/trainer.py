@@ -48,12 +48,18 @@ class FlatParams(object):
             p._glis_direct_grad = True                      # kernels may add into .grad in place
             p._glis_scratch = self.scratch[o:o + n].view(p.shape) if p.dim() >= 2 else None
 
+    def _scratch_clean(self):
+        for p in self.params:
+            p._glis_scratch_dirty = False
+
     def zero_grad(self):
         self.gs.zero_()
+        self._scratch_clean()
 
     def zero_grad_async(self):
         """Clear the gradients on the side stream (they are not touched before the next backward); returns the
         event the stream that runs that backward has to wait for, or None when done in place."""
+        self._scratch_clean()
         if not (ops.Overlap.enabled and torch.cuda.is_available()):
             self.gs.zero_()
             return None
@@ -80,7 +86,8 @@ class FlatParams(object):
 
     def optimizer_state_dict(self, lr, alpha=0.9, eps=1e-6):
         """RMSprop state in ``torch.optim.RMSprop.state_dict()`` form — what the reference saves as
-        ``*_opt.pt`` (g_lis/main.py:345-349) — so checkpoints move both ways."""
+        ``*_opt.pt`` (g_lis/main.py:345-349): loads into a stock ``torch.optim.RMSprop`` over the same
+        parameters; ``load_optimizer_state_dict`` reads it back, and also the 2017 format (below)."""
         state = {}
         for i, (p, o) in enumerate(zip(self.params, self.offsets)):
             state[i] = {"step": torch.tensor(0.0),
@@ -91,13 +98,28 @@ class FlatParams(object):
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
-        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
-            entry = sd["state"].get(i)
+        """Accepts both ``Optimizer.state_dict()`` formats: today's (state keyed by the parameter's index in
+        ``param_groups[*]['params']``) and the reference era's (mid-2017: ``'params'`` lists ``id(p)`` of the
+        saving process and ``state`` is keyed by those ids).  Either way the i-th entry of the concatenated
+        ``params`` lists is the key of the i-th parameter."""
+        keys = [k for group in sd["param_groups"] for k in group["params"]]
+        if len(keys) != len(self.params):
+            raise ValueError("optimizer state has %d parameters, the network has %d" % (len(keys), len(self.params)))
+        matched = 0
+        for key, p, o in zip(keys, self.params, self.offsets):
+            entry = sd["state"].get(key)
             seg = self.v[o:o + p.numel()]
             if entry is None:          # never stepped in the saved run: legacy "skip" == zero state
                 seg.zero_()
-            else:
-                seg.copy_(entry["square_avg"].reshape(-1).to(seg.device, dtype=torch.float32))
+                continue
+            sq = entry["square_avg"]
+            if sq.numel() != p.numel():
+                raise ValueError("optimizer state entry %r has %d elements, its parameter %d"
+                                 % (key, sq.numel(), p.numel()))
+            seg.copy_(sq.reshape(-1).to(seg.device, dtype=torch.float32))
+            matched += 1
+        if sd["state"] and not matched:
+            raise ValueError("optimizer state is not empty but none of its entries matched a parameter")
 
     def rmsprop_step(self, lr, alpha=0.9, eps=1e-6, gscale=1.0):
         ops.rmsprop_(self.p, self.g, self.v, lr, alpha, eps, gscale, params=self.params)
@@ -112,18 +134,13 @@ def _split_head(dis):
     return None
 
 
-def dis_bce(dis, x, targets):
-    """[mean BCE(dis(x)[chunk_i], targets[i])] for equal batch chunks of ``x`` — nn.Sigmoid +
-    nn.BCELoss (g_lis/main.py:311,555,564,578) fused into one kernel per chunk when D has the standard head."""
-    from common.model import run_layers
+def dis_bce(dis, x, targets, ls=False):
+    """[mean loss(dis(x)[chunk_i], targets[i])] for equal batch chunks of ``x``, through autograd — the path for a
+    discriminator WITHOUT the standard Sigmoid + View(1) head (``bce_on_logits`` serves the standard one)."""
     n = x.shape[0] // len(targets)
-    body = _split_head(dis)
-    if body is None:
-        p = dis(x)
-        return [F.binary_cross_entropy(p[i * n:(i + 1) * n], torch.full_like(p[i * n:(i + 1) * n], t))
-                for i, t in enumerate(targets)]
-    logits = run_layers(body, x).reshape(x.shape[0], -1)
-    return [ops.bce_with_logits_const(logits[i * n:(i + 1) * n], t) for i, t in enumerate(targets)]
+    p = dis(x)
+    lossfunc = F.mse_loss if ls else F.binary_cross_entropy
+    return [lossfunc(p[i * n:(i + 1) * n], torch.full_like(p[i * n:(i + 1) * n], t)) for i, t in enumerate(targets)]
 
 
 def dis_logits(dis, x):
@@ -136,26 +153,52 @@ def dis_logits(dis, x):
     return run_layers(body, x).reshape(-1)
 
 
-def bce_on_logits(logits, targets):
-    """([mean BCE of chunk i against targets[i]], d(sum of those means)/d(logits)): one fused kernel
-    per chunk (sigmoid + BCE + gradient, g_lis/main.py:311,555,564,578); nothing for autograd to trace —
-    the caller starts backward from the logits with the returned gradient."""
+def bce_on_logits(logits, targets, ls=False, gscale=1.0):
+    """([mean loss of chunk i against targets[i]], gscale * d(sum of those means)/d(logits)): one fused kernel
+    per chunk — sigmoid + BCE (g_lis/main.py:311,555,564,578) or, with ``ls``, sigmoid + squared error (--ls,
+    :308-311) — that also leaves the gradient; nothing for autograd to trace: the caller starts backward from
+    the logits with the returned gradient."""
     lg = logits.detach()
     n = lg.numel() // len(targets)
     dl = torch.empty_like(lg)
     losses = torch.empty(len(targets), device=lg.device, dtype=torch.float32)
+    entry = "glis_lsq_logits" if ls else "glis_bce_logits"
     for i, t in enumerate(targets):
-        ops.L.call("glis_bce_logits", ops.L.ptr(lg[i * n:(i + 1) * n]), float(t), n, 1.0, ops.L.ptr(losses[i:i + 1]),
+        ops.L.call(entry, ops.L.ptr(lg[i * n:(i + 1) * n]), float(t), n, float(gscale), ops.L.ptr(losses[i:i + 1]),
                    ops.L.ptr(dl[i * n:(i + 1) * n]), None, ops.L.stream())
     return [losses[i] for i in range(len(targets))], dl
+
+
+def _has_dropout(*nets):
+    return any(isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)) and m.p > 0 for net in nets for m in net.modules())
+
+
+class PairedBatch(object):
+    """The 2B-image batch of a D update, real images in the first half and generated ones in the second, as ONE
+    persistent NHWC buffer: the generator's last kernel writes its images straight into the second half and a
+    caller that fills ``real_view`` in place (GraphedStep's static input is that view) costs no copy at all."""
+
+    def __init__(self):
+        self.buf = None
+
+    def views(self, real):
+        B = real.shape[0]
+        shape = (2 * B,) + tuple(real.shape[1:])
+        if self.buf is None or tuple(self.buf.shape) != shape or self.buf.device != real.device:
+            self.buf = torch.empty(shape, device=real.device, dtype=torch.float32).contiguous(
+                memory_format=torch.channels_last)
+        return self.buf, self.buf[:B], self.buf[B:]
 
 
 class GLISTrainer(object):
     """One object per (G-LIS, D) pair; ``step`` = one reference training iteration."""
 
-    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6, grad_sync=None):
+    def __init__(self, gen, dis, lr, lambda_r=0.9, alpha=0.9, eps=1e-6, grad_sync=None, ls=False):
         self.gen, self.dis = gen, dis
         self.lr, self.lambda_r, self.alpha, self.eps = lr, lambda_r, alpha, eps
+        self.ls = bool(ls)                      # --ls: squared error on D's sigmoid output instead of BCE
+        self.paired = PairedBatch()
+        self.dropout = _has_dropout(gen, dis)
         self.gen_flat = FlatParams(gen)
         self.dis_flat = FlatParams(dis)
         # data parallelism: either a callable (flat_grad_tensor, tag) -> gscale run after backward
@@ -186,6 +229,8 @@ class GLISTrainer(object):
     def step(self, real, z_d, z_g, depth_d=None, depth_g=None):
         gen, dis = self.gen, self.dis
         B = real.shape[0]
+        if self.dropout:
+            ops.DropoutClock.tick(real.device)     # fresh dropout masks for this iteration (also under graph replay)
 
         # G's data-gradient packs are not needed before the G update's backward: rebuilt on the side stream
         ops.refresh_packs(self.gen_flat, part="backward", side=True)
@@ -198,19 +243,25 @@ class GLISTrainer(object):
         # side stream, under G's forward
         zeroed_d = self.dis_flat.zero_grad_async()
         zeroed_g = self.gen_flat.zero_grad_async()
+        both, real_half, fake_half = self.paired.views(real)
+        if real.data_ptr() != real_half.data_ptr():
+            real_half.copy_(real)                   # (a caller that fills `paired` in place skips this)
         with torch.no_grad():
-            fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d)
-        both = torch.cat([real.contiguous(memory_format=torch.channels_last), fake], dim=0)
+            fake, lis_d = gen(z_d, n_execute_lis_layers=depth_d, out=fake_half)
+        if fake.data_ptr() != fake_half.data_ptr():
+            fake_half.copy_(fake)                   # generator tail off the fused path: one copy
+        for attr in ("_glis_unfolded", "_glis_planes"):
+            both.__dict__.pop(attr, None)           # planes cached for the buffer's previous contents
         logits = dis_logits(dis, both)
         self._sync_begin("dis")
         if zeroed_d is not None:
             torch.cuda.current_stream().wait_event(zeroed_d)
         ops.Overlap.begin()
         if logits is not None:     # losses and d(loss)/d(logits) from one kernel per half; backward starts at the logits
-            (loss_d_real, loss_d_fake), dl = bce_on_logits(logits, [1.0, 0.0])
+            (loss_d_real, loss_d_fake), dl = bce_on_logits(logits, [1.0, 0.0], self.ls)
             logits.backward(dl)
         else:
-            loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
+            loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0], self.ls)
             (loss_d_real + loss_d_fake).backward()
         ops.Overlap.join()
         self.dis_flat.rebind_grads()
@@ -230,7 +281,7 @@ class GLISTrainer(object):
         ops.Overlap.begin()
         if logits is not None:
             # roots of backward: the logits and every LIS output, each with its kernel-computed gradient
-            (loss_g,), dl = bce_on_logits(logits, [1.0])
+            (loss_g,), dl = bce_on_logits(logits, [1.0], self.ls)
             roots, grads = [logits], [dl]
             if self.lambda_r > 0:
                 zc = z_g.detach().contiguous()
@@ -242,7 +293,7 @@ class GLISTrainer(object):
                     grads.append(du)
             torch.autograd.backward(roots, grads)
         else:
-            (loss_g,) = dis_bce(dis, fake, [1.0])
+            (loss_g,) = dis_bce(dis, fake, [1.0], self.ls)
             total = loss_g
             if self.lambda_r > 0:
                 for i, u in enumerate(lis_g):
@@ -273,8 +324,10 @@ class GraphedStep(object):
 
     def __init__(self, trainer, batch, height, width, code, device, warmup=2):
         self.tr = trainer
-        self.real = torch.zeros(batch, 3, height, width, device=device).contiguous(
-            memory_format=torch.channels_last)
+        # the static image input IS the first half of the trainer's 2B buffer: filling it in place costs no copy
+        _, self.real, _ = trainer.paired.views(torch.empty(batch, 3, height, width, device=device).contiguous(
+            memory_format=torch.channels_last))
+        self.real.zero_()
         self.z_d = torch.zeros(batch, code, device=device)
         self.z_g = torch.zeros(batch, code, device=device)
         self.warmup = warmup
@@ -353,18 +406,30 @@ class RIterTrainer(object):
     kernels: plain generator, reverser R and discriminator, three flat RMSprop states.
 
     Per hop r of the chain: G update, (r > 0) R update on
-    ``λ^r·MSE(code, first_code) + (1-λ^r)·BCE(dis(gen(code)), 1)``, D update.  The stochastic
-    ``do_train`` schedule (:445-451) is drawn from ``self.rng`` unless ``train_flags`` is given.
-    During the R update the generator's parameter gradients are not needed (the reference lets
-    them pile up and zero-fills them before the next G step), so they are not computed.
+    ``λ^r·MSE(code, first_code) + (1-λ^r)·loss(dis(gen(code)), 1)``, D update on a fresh real batch and the hop's
+    (pre-update) generated images as one 2B batch.  The stochastic ``do_train`` schedule (:445-451) is drawn from
+    ``self.rng`` unless ``train_flags`` is given.  Losses and their gradients come from the fused loss kernels and
+    every backward starts at the logits / the code (no autograd loss glue); weight gradients fork onto the side
+    stream; under data parallelism each of the three networks has its own bucket set.  During the R
+    update the generator's parameter gradients are not needed (the reference lets them pile up and zero-fills
+    them before the next G step), so they are not computed.
     """
 
-    def __init__(self, gen, rev, dis, lr, lambda_r=0.9, r_iterations=3, alpha=0.9, eps=1e-6, rng=None):
+    def __init__(self, gen, rev, dis, lr, lambda_r=0.9, r_iterations=3, alpha=0.9, eps=1e-6, rng=None,
+                 grad_sync=None, ls=False):
         import random as _random
         self.gen, self.rev, self.dis = gen, rev, dis
         self.lr, self.lambda_r, self.r_iterations, self.alpha, self.eps = lr, lambda_r, r_iterations, alpha, eps
+        self.ls = bool(ls)
         self.gen_flat, self.rev_flat, self.dis_flat = FlatParams(gen), FlatParams(rev), FlatParams(dis)
         self.rng = rng if rng is not None else _random
+        self.paired = PairedBatch()
+        self.dropout = _has_dropout(gen, rev, dis)
+        self.grad_sync = grad_sync
+        self._overlapped = hasattr(grad_sync, "register")
+        if self._overlapped:
+            for tag, flat in (("gen", self.gen_flat), ("rev", self.rev_flat), ("dis", self.dis_flat)):
+                grad_sync.register(tag, flat)
 
     def draw_train_flags(self, always_train_all=False):
         hops = 1 + self.r_iterations
@@ -382,13 +447,42 @@ class RIterTrainer(object):
         for p in flat.params:
             p.requires_grad_(flag)
 
+    def _backward_and_update(self, tag, flat, roots, grads):
+        """Backward from ``roots`` (weight gradients on the side stream, gradient exchange overlapped), RMSprop on
+        ``flat``, its weight packs rebuilt on the side stream under whatever runs next."""
+        if self._overlapped:
+            self.grad_sync.begin(tag)
+        ops.Overlap.begin()
+        torch.autograd.backward(roots, grads)
+        ops.Overlap.join()
+        flat.rebind_grads()
+        if self.grad_sync is None:
+            gs = 1.0
+        elif self._overlapped:
+            gs = self.grad_sync.finish(tag)
+        else:
+            gs = self.grad_sync(flat.g, tag)
+        flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+        ops.refresh_packs(flat, part="all", side=True)
+
+    def _adv(self, x, targets, gscale=1.0):
+        """(losses, logits, d(sum of losses)/d(logits) * gscale) of ``dis`` on ``x`` — or (losses, None, None) with
+        the losses differentiable through autograd when D has no standard head."""
+        logits = dis_logits(self.dis, x)
+        if logits is None:
+            return dis_bce(self.dis, x, targets, self.ls), None, None
+        losses, dl = bce_on_logits(logits, targets, self.ls, gscale)
+        return losses, logits, dl
+
     def step(self, first_code, reals, train_flags=None):
-        gen, rev, dis = self.gen, self.rev, self.dis
-        B = first_code.shape[0]
+        gen, rev = self.gen, self.rev
         hops = 1 + self.r_iterations
         if train_flags is None:
             train_flags = [True] * hops
         reals = list(reals)
+        if self.dropout:
+            ops.DropoutClock.tick(first_code.device)
+        first = first_code.detach()
         out, last_images, last_code = [], None, None
         for r_idx in range(hops):
             code = first_code if last_images is None else rev(last_images.detach())
@@ -399,39 +493,114 @@ class RIterTrainer(object):
                 out.append(None)
                 continue
             rec = {}
-            # ---- G
+            # ---- G (:475-485)
             self.gen_flat.zero_grad()
             self._requires_grad(self.dis_flat, False)
             generated = gen(code.detach())
-            (loss_g,) = dis_bce(dis, generated, [1.0])
-            loss_g.backward()
-            self.gen_flat.rebind_grads()
-            self.gen_flat.rmsprop_step(self.lr, self.alpha, self.eps)
+            (loss_g,), logits, dl = self._adv(generated, [1.0])
+            if logits is not None:
+                self._backward_and_update("gen", self.gen_flat, [logits], [dl])
+            else:
+                self._backward_and_update("gen", self.gen_flat, [loss_g], [None])
             rec["g"] = loss_g.detach()
-            # ---- R (through the updated G and the frozen D)
+            # ---- R (:487-497), through the updated G and the frozen D
             if last_code is not None:
                 self.rev_flat.zero_grad()
                 self._requires_grad(self.gen_flat, False)
-                (loss_g2,) = dis_bce(dis, gen(code), [1.0])
-                loss_r = F.mse_loss(code, first_code.detach())
                 lar = self.lambda_r ** r_idx
-                (lar * loss_r + (1 - lar) * loss_g2).backward()
+                (loss_g2,), logits, dl = self._adv(gen(code), [1.0], gscale=1.0 - lar)
+                if logits is not None:
+                    du = torch.empty_like(code, memory_format=torch.contiguous_format)
+                    loss_r = ops.mse_scaled(code, first, lar, du, unscaled_loss=True).reshape(())
+                    self._backward_and_update("rev", self.rev_flat, [logits, code], [dl, du])
+                else:
+                    loss_r = F.mse_loss(code, first)
+                    self._backward_and_update("rev", self.rev_flat, [lar * loss_r + (1 - lar) * loss_g2], [None])
                 self._requires_grad(self.gen_flat, True)
-                self.rev_flat.rebind_grads()
-                self.rev_flat.rmsprop_step(self.lr, self.alpha, self.eps)
                 rec["r"] = loss_r.detach()
-            # ---- D (real and the hop's pre-update generated batch as one 2B batch)
+            # ---- D (:502-526): the real batch and the hop's pre-update generated batch as one 2B batch
             self.dis_flat.zero_grad()
             self._requires_grad(self.dis_flat, True)
-            both = torch.cat([reals.pop(0).contiguous(memory_format=torch.channels_last), generated.detach()], dim=0)
-            loss_d_real, loss_d_fake = dis_bce(dis, both, [1.0, 0.0])
-            (loss_d_real + loss_d_fake).backward()
-            self.dis_flat.rebind_grads()
-            self.dis_flat.rmsprop_step(self.lr, self.alpha, self.eps)
+            real = reals.pop(0)
+            both, real_half, fake_half = self.paired.views(real)
+            if real.data_ptr() != real_half.data_ptr():
+                real_half.copy_(real)
+            fake_half.copy_(generated.detach())
+            for attr in ("_glis_unfolded", "_glis_planes"):
+                both.__dict__.pop(attr, None)
+            (loss_d_real, loss_d_fake), logits, dl = self._adv(both, [1.0, 0.0])
+            if logits is not None:
+                self._backward_and_update("dis", self.dis_flat, [logits], [dl])
+            else:
+                self._backward_and_update("dis", self.dis_flat, [loss_d_real + loss_d_fake], [None])
             rec["d_real"], rec["d_fake"] = loss_d_real.detach(), loss_d_fake.detach()
             last_images, last_code = generated, code
             out.append(rec)
+        if ops.Overlap.enabled and torch.cuda.is_available():
+            # the last pack rebuild runs on the side stream: join it (a captured iteration must end on ONE stream)
+            torch.cuda.current_stream().wait_stream(ops.Overlap.stream())
+            for flat in (self.gen_flat, self.rev_flat, self.dis_flat):
+                ops.forget_pending(flat)
         return out
+
+
+class GraphedRIter(object):
+    """CUDA-graph replay of ``RIterTrainer.step``: one captured graph per ``do_train`` schedule (the sticky rule
+    leaves ``1 + r_iterations`` distinct ones), replayed from static inputs ``first_code`` and ``reals[hop]``."""
+
+    def __init__(self, trainer, batch, height, width, code, device, warmup=1):
+        self.tr = trainer
+        hops = 1 + trainer.r_iterations
+        self.first_code = torch.zeros(batch, code, device=device)
+        self.reals = [torch.zeros(batch, 3, height, width, device=device).contiguous(memory_format=torch.channels_last)
+                      for _ in range(hops)]
+        self.warmup, self.graphs, self.pool = warmup, {}, None
+
+    def _capture(self, flags):
+        tr = self.tr
+        flats = [tr.gen_flat, tr.rev_flat, tr.dis_flat]
+        run = lambda: tr.step(self.first_code, self.reals[:sum(flags)], list(flags))
+        graph, out, self.pool = capture_step(flats, run, self.warmup, self.pool)
+        self.graphs[flags] = (graph, out)
+        return self.graphs[flags]
+
+    def step(self, first_code=None, reals=None, train_flags=None):
+        flags = tuple(bool(f) for f in (train_flags if train_flags is not None else self.tr.draw_train_flags()))
+        if first_code is not None:
+            self.first_code.copy_(first_code, non_blocking=True)
+        for dst, src in zip(self.reals, reals or ()):
+            dst.copy_(src, non_blocking=True)
+        entry = self.graphs.get(flags) or self._capture(flags)
+        entry[0].replay()
+        ops.bump_param_epoch()
+        return entry[1]
+
+
+def capture_step(flats, run, warmup, pool):
+    """Capture ``run()`` (one training iteration over the FlatParams ``flats``) into a CUDA graph.  The warm-up
+    iterations (lazy CUDA init, allocator) must not count as training: parameters, gradients and optimizer state
+    are snapshotted and restored, and the weight packs — which live in persistent buffers and are rebuilt INSIDE
+    the graph after each optimizer step — are rebuilt eagerly for the restored parameters before the capture.
+    Returns (graph, outputs of the captured run, memory pool)."""
+    saved = [(f.p.clone(), f.g.clone(), f.v.clone()) for f in flats]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for f, (p, g, v) in zip(flats, saved):
+        f.p.copy_(p); f.g.copy_(g); f.v.copy_(v)
+    ops.bump_param_epoch()
+    for f in flats:
+        ops.refresh_packs(f, part="all", side=False)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, pool=pool):
+        out = run()
+    ops.bump_param_epoch()
+    return graph, out, (pool if pool is not None else graph.pool())
 
 
 class HostFedStepper(object):

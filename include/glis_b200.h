@@ -246,7 +246,30 @@ int glis_channel_sum(const float* x, float* out, int64_t numel, int C, int inner
 int glis_bce_logits(const float* logit, float target, int B, float gscale, float* loss,
                     float* dlogit, float* prob, void* stream);
 
-/* lambda * mean((u - z)^2) (nn.MSELoss, g_lis/main.py:312,584-585); du (+)= 2*lambda*(u-z)/numel. */
+/* --ls (LSGAN): nn.MSELoss() on D's sigmoid output against a constant target (g_lis/main.py:308-311,
+ * r_iterative/main.py:208-211).  loss[0] = mean((p - t)^2), p = sigmoid(logit); dlogit[i] = gscale * 2 (p_i - t)
+ * p_i (1 - p_i) / B (may be NULL); prob (may be NULL) receives p. */
+int glis_lsq_logits(const float* logit, float target, int B, float gscale, float* loss,
+                    float* dlogit, float* prob, void* stream);
+
+/* nn.Dropout(p) before D's final convolution (common/model.py:52-53) and nn.Dropout2d(p) in R (:344-346):
+ * out = keep ? x / (1 - p) : 0.  The mask is a pure function of (seed, *counter + call, element):
+ * keep(e) = u01(Philox4x32-10(key = seed, counter = {e / 4, *counter + call})[e % 4]) >= p, u01(r) = (r >> 8) / 2^24.
+ * `counter` (device uint64, may be NULL = 0) is advanced once per training iteration with glis_counter_add, `call`
+ * numbers the dropout calls inside an iteration: a CUDA-graph replay draws a fresh mask each time, the backward
+ * pass is the same call on the gradient (nothing is stored), and a host can reproduce every mask.
+ * channel_mode == 0: mask element e = element index in storage order.
+ * channel_mode != 0 (Dropout2d): e = (i / per_image) * C + (i / inner) % C, one mask element per (image, channel);
+ *   NHWC: inner = 1, per_image = H*W*C;  NCHW: inner = H*W, per_image = C*H*W. */
+int glis_dropout(const float* x, float* out, int64_t numel, int C, int inner, int64_t per_image, int channel_mode,
+                 float p, uint64_t seed, const void* counter, uint64_t call, void* stream);
+/* *counter += inc (one thread; stream-ordered, capturable). */
+int glis_counter_add(void* counter, uint64_t inc, void* stream);
+
+/* lambda * mean((u - z)^2) (nn.MSELoss, g_lis/main.py:312,584-585); du (+)= 2*lambda*(u-z)/numel.
+ * accumulate: bit 0 = add into du instead of overwriting; bit 1 = report the UNSCALED mean in loss[0] while du keeps
+ * the factor lambda (the R-iterative trainer logs MSE(code, first_code) but back-propagates lambda^r times it,
+ * r_iterative/main.py:489-497). */
 int glis_mse_scaled(const float* u, const float* z, int64_t numel, float lambda, float* loss,
                     float* du, int accumulate, void* stream);
 

@@ -81,3 +81,29 @@ class FlipAwarePair(object):
 
     def remove(self):
         self.fa.remove()
+
+
+def _philox4x32_10(seed, quad, stream):
+    """Philox4x32-10 (Salmon et al., SC'11), vectorised over ``quad``: key = seed (64 bit), counter =
+    {quad lo, quad hi, stream lo, stream hi} — the host restatement of csrc/pointwise.cu::philox4_stream."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    quad = np.asarray(quad, dtype=np.uint64)
+    c = [quad & mask, quad >> np.uint64(32), np.full_like(quad, np.uint64(stream & 0xFFFFFFFF)),
+         np.full_like(quad, np.uint64((stream >> 32) & 0xFFFFFFFF))]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def philox_keep_mask(seed, stream, numel, p):
+    """Keep mask (bool tensor of ``numel`` elements) of one glis_dropout draw: element e is kept iff
+    u01(Philox(seed, {e // 4, stream})[e % 4]) >= p with u01(r) = (r >> 8) / 2^24 compared in fp32."""
+    quads = np.arange((numel + 3) // 4, dtype=np.uint64)
+    words = np.stack(_philox4x32_10(int(seed), quads, int(stream)), axis=1).reshape(-1)[:numel]
+    u = (words >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.from_numpy(u >= np.float32(p))
