@@ -31,11 +31,39 @@ for p in (ROOT, os.path.join(ROOT, "gan-error-avoidance_b200")):
 
 import torch  # noqa: E402
 
-CFG = dict(W=80, H=80, B=64, nfeature=64, nlayer=4, code=256, n_lis=1, lr=2e-5, lambda_r=0.9)
-WORKLOAD = "G-LIS 1 LIS module, 80x80 CelebA-shaped synthetic, batch 64/GPU (BASELINE configs[1])"
-# F_step = 8 F_D + 4 F_G + 4 F_LIS = 250.9 GFLOP at config 2 (B = 64)
-GFLOP_PER_STEP = 250.9
+# BASELINE.json `configs`, with the algorithmic GFLOP per step of SURVEY.md §8d (F_step = 8 F_D + 4 F_G + 4 F_LIS;
+# config 5a: 21 F_G + 38 F_D + 9 F_R per outer iteration).  The driver's line is config 2 (the default); the others
+# are reachable with --config for the configs table of DESIGN.md.
+CONFIGS = {
+    "1": dict(W=32, H=32, B=32, nfeature=64, nlayer=3, code=256, n_lis=1, gflop=13.79,
+              workload="G-LIS 1 LIS module, 32x32 CIFAR-shaped synthetic, batch 32 (BASELINE configs[0])"),
+    "2": dict(W=80, H=80, B=64, nfeature=64, nlayer=4, code=256, n_lis=1, gflop=250.9,
+              workload="G-LIS 1 LIS module, 80x80 CelebA-shaped synthetic, batch 64/GPU (BASELINE configs[1])"),
+    "3": dict(W=80, H=80, B=64, nfeature=64, nlayer=4, code=256, n_lis=3, gflop=251.0,
+              workload="G-LIS 3 LIS modules, 80x80 synthetic, batch 64/GPU (BASELINE configs[2])"),
+    "4": dict(W=160, H=160, B=32, nfeature=64, nlayer=5, code=256, n_lis=1, gflop=661.1,
+              workload="G-LIS 1 LIS module at 160x160 (extra G/D layer), batch 32/GPU (BASELINE configs[3])"),
+    "5a": dict(W=80, H=80, B=64, nfeature=64, nlayer=4, code=256, n_lis=0, gflop=1283.7, riter=3,
+               workload="R-iterative 3 iterations (--always_train_all), 80x80 synthetic, batch 64/GPU (BASELINE configs[4], first half)"),
+    "5b": dict(W=64, H=64, B=64, nfeature=64, nlayer=3, code=256, n_lis=1, gflop=153.1, upscaling="nearest", d_dropout=0.2,
+               workload="G-LIS 64x64 3-layer NN-upsampling G/D with dropout 0.2 in D, batch 64/GPU (BASELINE configs[4], second half)"),
+}
+for _c in CONFIGS.values():
+    _c.setdefault("upscaling", "fractional")
+    _c.setdefault("d_dropout", 0)
+    _c.setdefault("riter", 0)
+    _c.update(lr=2e-5, lambda_r=0.9)
+CFG = dict(CONFIGS["2"])
+WORKLOAD = CFG["workload"]
+GFLOP_PER_STEP = CFG["gflop"]
 SEED = 1234
+
+
+def select_config(name):
+    global WORKLOAD, GFLOP_PER_STEP
+    CFG.clear()
+    CFG.update(CONFIGS[name])
+    WORKLOAD, GFLOP_PER_STEP = CFG["workload"], CFG["gflop"]
 
 
 def measured_peaks():
@@ -99,9 +127,18 @@ def build_oracle_pair():
     import oracle
     torch.manual_seed(SEED)
     g = oracle.GeneratorLearnedInputSpace(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight",
-                                          CFG["n_lis"], "fractional")
-    d = oracle.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", 0)
+                                          CFG["n_lis"], CFG["upscaling"])
+    d = oracle.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", CFG["d_dropout"])
     return g, d
+
+
+def build_oracle_riter():
+    import oracle
+    torch.manual_seed(SEED)
+    g = oracle.build_generator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight")
+    r = oracle.build_reverser(CFG["W"], CFG["H"], CFG["nfeature"] // 2, CFG["nlayer"], CFG["code"], "weight", 0)
+    d = oracle.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", 0)
+    return g, r, d
 
 
 def time_cpu_oracle(steps, warmup, budget_s=150.0):
@@ -110,19 +147,30 @@ def time_cpu_oracle(steps, warmup, budget_s=150.0):
     A step is one full config-2 iteration at batch 64; if `steps + warmup` of those would not fit
     `budget_s`, the per-step batch is cut (never below 8) so that the run stays bounded — images/s
     is then per-step images over per-step time, which is what the metric means."""
-    from oracle.step import GLISOracleTrainer
+    from oracle.step import GLISOracleTrainer, riter_iteration
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g, d = build_oracle_pair()
-    tr = GLISOracleTrainer(g, d, lr=CFG["lr"], lambda_r=CFG["lambda_r"])
     gen = torch.Generator().manual_seed(SEED + 1)
+    if CFG["riter"]:
+        g, r, d = build_oracle_riter()
+        states = ({}, {}, {})
 
-    def one(B):
-        real = torch.rand(B, 3, CFG["H"], CFG["W"], generator=gen)
-        zd, zg = torch.randn(B, CFG["code"], generator=gen), torch.randn(B, CFG["code"], generator=gen)
-        t0 = time.perf_counter()
-        tr.step(real, zd, zg, CFG["n_lis"], CFG["n_lis"])
-        return time.perf_counter() - t0
+        def one(B):
+            z = torch.randn(B, CFG["code"], generator=gen)
+            reals = [torch.rand(B, 3, CFG["H"], CFG["W"], generator=gen) for _ in range(1 + CFG["riter"])]
+            t0 = time.perf_counter()
+            riter_iteration(g, r, d, states[0], states[1], states[2], z, reals, CFG["lr"], CFG["lambda_r"], CFG["riter"])
+            return time.perf_counter() - t0
+    else:
+        g, d = build_oracle_pair()
+        tr = GLISOracleTrainer(g, d, lr=CFG["lr"], lambda_r=CFG["lambda_r"])
+
+        def one(B):
+            real = torch.rand(B, 3, CFG["H"], CFG["W"], generator=gen)
+            zd, zg = torch.randn(B, CFG["code"], generator=gen), torch.randn(B, CFG["code"], generator=gen)
+            t0 = time.perf_counter()
+            tr.step(real, zd, zg, CFG["n_lis"], CFG["n_lis"])
+            return time.perf_counter() - t0
 
     B = CFG["B"]
     t_first = one(B)                      # doubles as the first warm-up step
@@ -148,26 +196,39 @@ def cpu_model():
     return "unknown"
 
 
+def bench_config():
+    """The `config` object of BOTH arms' JSON lines (identical by construction: the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": CFG["B"], "lis_depth": "all" if not CFG["riter"] else "n/a",
+            "gflop_per_step": GFLOP_PER_STEP,
+            "l2": "inputs larger than L2: every step touches > 200 MB of activations and all weights (126 MB L2)"}
+
+
+def metric_name():
+    if CFG["workload"] == CONFIGS["2"]["workload"]:
+        return "G-LIS train images/sec at 80x80 bs64/GPU"
+    return "train images/sec, " + CFG["workload"]
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     sec, cores, b_step = time_cpu_oracle(args.steps, args.warmup)
     ips = b_step / sec
-    sample = "%d full config-2 iterations (batch %d per step) after %d warm-up, oracle port on torch %s CPU, %s" % (
+    sample = "%d full iterations of the workload (batch %d per step) after %d warm-up, oracle port on torch %s CPU, %s" % (
         args.steps, b_step, args.warmup, torch.__version__, cpu_model())
     print(json.dumps({
-        "impl": "reference", "metric": "G-LIS train images/sec at 80x80 bs64/GPU", "value": ips, "unit": "images/s",
+        "impl": "reference", "metric": metric_name(), "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": b_step,
-                   "note": "python2.7/PyTorch@065c5986 pin not installable offline; nearest installable "
-                           "PyTorch CPU build used (oracle port of the reference step)"},
+        "config": bench_config(),
+        "note": "python2.7/PyTorch@065c5986 pin not installable offline; nearest installable PyTorch CPU build used "
+                "(oracle port of the reference step); batch per timed step: %d" % b_step,
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def probe_dominant_kernel(dev, precision_name):
+def probe_dominant_kernel(dev):
     """Time the dominant kernel alone: `tc_conv_kernel` on the discriminator's level-1 convolution
     of the 2B-image D pass (64 -> 128 channels, 40x40 -> 20x20, 128 images: M=51200, N=128, K=1024).
     20 launches replayed as one CUDA graph, CUDA events on the launching stream."""
@@ -201,12 +262,14 @@ def probe_dominant_kernel(dev, precision_name):
     ms = e0.elapsed_time(e1) / reps
     flop = 2.0 * n * ho * ho * co * ci * 16
     passes = 3 if L.default_precision == L.PREC_BF16X3 else 1
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("tc_conv_kernel_d1_2B_dram_bytes")
+            tj = json.load(fh)
+        traffic, traffic_src = tj.get("tc_conv_kernel_d1_2B_dram_bytes"), tj.get("captured_at")
     return {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "traffic": traffic,
+            "traffic_source": traffic_src,
             "kernel": "tc_conv_kernel  D level-1 conv 64->128, 40x40->20x20, 128 images (M=51200 N=128 K=1024)",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flop / 1e9,
             "mma_passes": passes, "mma_pipe_tflops": passes * flop / (ms * 1e-3) / 1e12,
@@ -214,11 +277,233 @@ def probe_dominant_kernel(dev, precision_name):
                     "`achieved` counts algorithmic FLOPs only"}
 
 
+def time_gpu_library(dev, steps=10):
+    """Secondary yardstick: the ORACLE's modules — stock PyTorch ops, i.e. cuDNN / cuBLAS / ATen
+    kernels — running the same iteration on this GPU, fp32 (TF32 off) and with TF32 allowed, launched eagerly and
+    as one captured CUDA graph.  Not the target and not the reference arm: it tells how the hand-written path
+    compares with the vendor libraries at the same fidelity."""
+    import oracle
+    from oracle.step import rmsprop_update
+    import torch.nn.functional as F
+    if CFG["riter"]:
+        return None
+    out = {}
+    B, H, W, code, depth = CFG["B"], CFG["H"], CFG["W"], CFG["code"], CFG["n_lis"]
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        g, d = build_oracle_pair()
+        g, d = g.to(dev), d.to(dev)
+        if CFG["d_dropout"]:
+            d.eval()         # (graph-safe: stock dropout inside a captured graph needs the philox plumbing of torch's RNG)
+        gs, ds = {}, {}
+        real = torch.rand(B, 3, H, W, device=dev)
+        zd, zg = torch.randn(B, code, device=dev), torch.randn(B, code, device=dev)
+        ones, zeros = torch.ones(B, 1, device=dev), torch.zeros(B, 1, device=dev)
+
+        def step():
+            for p in d.parameters():
+                p.requires_grad_(True)
+                if p.grad is not None:
+                    p.grad.zero_()
+            F.binary_cross_entropy(d(real), ones).backward()
+            with torch.no_grad():
+                fake, _ = g(zd, n_execute_lis_layers=depth)
+            F.binary_cross_entropy(d(fake), zeros).backward()
+            rmsprop_update(list(d.parameters()), ds, CFG["lr"])
+            for p in d.parameters():
+                p.requires_grad_(False)
+            for p in g.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            fake, lis = g(zg, n_execute_lis_layers=depth)
+            total = F.binary_cross_entropy(d(fake), ones)
+            for i, u in enumerate(lis):
+                total = total + F.mse_loss(u, zg) * (CFG["lambda_r"] ** (i + 1))
+            total.backward()
+            rmsprop_update(list(g.parameters()), gs, CFG["lr"])
+
+        def timed(fn, n):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        key = "tf32" if tf32 else "fp32"
+        try:
+            for _ in range(3):
+                step()
+            out[key + "_eager_ms"] = timed(step, steps)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            graph.replay()
+            out[key + "_graph_ms"] = timed(graph.replay, steps)
+            del graph
+        except Exception as exc:           # a yardstick must never take the bench line down
+            out[key + "_error"] = repr(exc)[:200]
+        del g, d
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    best = min([v for k, v in out.items() if k.endswith("_ms") and k.startswith("fp32")] or [float("nan")])
+    out.update({"images_per_s_fp32": B / (best * 1e-3) if best == best else None, "unit": "ms per step",
+                "what": "oracle modules on torch %s + cuDNN %s on this GPU, same iteration, batch %d" % (
+                    torch.__version__, torch.backends.cudnn.version(), B)})
+    return out
+
+
+class GlisWorkload(object):
+    """G-LIS iteration (configs 1-4, 5b): inputs from the device Philox generator into the graph's static buffers."""
+
+    def __init__(self, dev, world, data_seed, use_graph):
+        import common.model as pm
+        from glis_b200 import dp, ops
+        from glis_b200.trainer import GLISTrainer, GraphedStep
+        self.ops, self.seed = ops, data_seed
+        gen = pm.GeneratorLearnedInputSpace(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight",
+                                            CFG["n_lis"], CFG["upscaling"]).to(dev)
+        dis = pm.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", CFG["d_dropout"]).to(dev)
+        sync = dp.OverlappedGradSync(world) if world > 1 else None
+        self.tr = GLISTrainer(gen, dis, lr=CFG["lr"], lambda_r=CFG["lambda_r"], grad_sync=sync)
+        B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
+        self.depth = CFG["n_lis"]   # LIS depth forced to "all": fixed work per step
+        self.graphed = GraphedStep(self.tr, B, H, W, code, dev) if use_graph else None
+        if self.graphed is not None:
+            self.real, self.zd, self.zg = self.graphed.real, self.graphed.z_d, self.graphed.z_g
+        else:
+            self.real = torch.empty(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+            self.zd, self.zg = torch.empty(B, code, device=dev), torch.empty(B, code, device=dev)
+        self.counter = 0
+        self.h2d = 4 * (self.real.numel() + self.zd.numel() + self.zg.numel())
+        self.d2h = 4 * (3 + CFG["n_lis"])
+
+    def fill(self):
+        off = self.counter * (1 << 22)
+        self.counter += 1
+        self.ops.uniform_(self.real, self.seed, off)
+        self.ops.randn_(self.zd, self.seed + 7, off)
+        self.ops.randn_(self.zg, self.seed + 13, off)
+
+    def device_step(self):
+        self.fill()
+        if self.graphed is not None:
+            return self.graphed.step(None, None, None, self.depth, self.depth)
+        return self.tr.step(self.real, self.zd, self.zg, self.depth, self.depth)
+
+    def eager_step(self):
+        self.fill()
+        return self.tr.step(self.real, self.zd, self.zg, self.depth, self.depth)
+
+    def make_e2e(self):
+        """(step(), drain() -> last losses): pinned host batches -> H2D -> iteration -> D2H of the losses, through
+        trainer.HostFedStepper (copy of iteration i+1 overlaps iteration i; losses read one iteration late)."""
+        B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
+        h_real = torch.rand(B, 3, H, W).pin_memory()
+        h_zd, h_zg = torch.randn(B, code).pin_memory(), torch.randn(B, code).pin_memory()
+        last = [None]
+        if self.graphed is not None:
+            from glis_b200.trainer import HostFedStepper
+            feeder = HostFedStepper(self.graphed)
+
+            def step():
+                last[0] = feeder.submit(h_real, h_zd, h_zg, self.depth, self.depth)
+
+            def drain():
+                last[0] = feeder.flush()
+                return last[0]
+            return step, drain, "glis_b200.trainer.HostFedStepper.submit(pinned real, z_d, z_g) -> losses"
+        h_loss = torch.empty(3).pin_memory()
+
+        def step():
+            self.real.copy_(h_real, non_blocking=True)
+            self.zd.copy_(h_zd, non_blocking=True)
+            self.zg.copy_(h_zg, non_blocking=True)
+            out = self.tr.step(self.real, self.zd, self.zg, self.depth, self.depth)
+            h_loss.copy_(torch.stack([out["d_real"], out["d_fake"], out["g"]]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            last[0] = h_loss.tolist()
+        return step, (lambda: last[0]), "glis_b200.trainer.GLISTrainer.step(real, z_d, z_g) from pinned host batches"
+
+
+class RIterWorkload(object):
+    """R-iterative outer iteration (config 5a): 1 + R hops, every hop trained (--always_train_all)."""
+
+    def __init__(self, dev, world, data_seed, use_graph):
+        import common.model as pm
+        from glis_b200 import dp, ops
+        from glis_b200.trainer import GraphedRIter, RIterTrainer
+        self.ops, self.seed = ops, data_seed
+        gen = pm.build_generator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight").to(dev)
+        rev = pm.build_reverser(CFG["W"], CFG["H"], CFG["nfeature"] // 2, CFG["nlayer"], CFG["code"], "weight", 0).to(dev)
+        dis = pm.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight").to(dev)
+        sync = dp.OverlappedGradSync(world) if world > 1 else None
+        self.tr = RIterTrainer(gen, rev, dis, lr=CFG["lr"], lambda_r=CFG["lambda_r"], r_iterations=CFG["riter"],
+                               grad_sync=sync)
+        B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
+        self.hops = 1 + CFG["riter"]
+        self.flags = [True] * self.hops
+        self.graphed = GraphedRIter(self.tr, B, H, W, code, dev) if use_graph else None
+        if self.graphed is not None:
+            self.first, self.reals = self.graphed.first_code, self.graphed.reals
+        else:
+            self.first = torch.empty(B, code, device=dev)
+            self.reals = [torch.empty(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+                          for _ in range(self.hops)]
+        self.counter = 0
+        self.h2d = 4 * (self.first.numel() + sum(r.numel() for r in self.reals))
+        self.d2h = 4 * (4 * self.hops - 1)
+
+    def fill(self):
+        off = self.counter * (1 << 24)
+        self.counter += 1
+        self.ops.randn_(self.first, self.seed + 7, off)
+        for i, r in enumerate(self.reals):
+            self.ops.uniform_(r, self.seed, off + (i << 21))
+
+    def device_step(self):
+        self.fill()
+        if self.graphed is not None:
+            return self.graphed.step(None, None, self.flags)
+        return self.tr.step(self.first, self.reals, self.flags)
+
+    def eager_step(self):
+        self.fill()
+        return self.tr.step(self.first, self.reals, self.flags)
+
+    def make_e2e(self):
+        B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
+        h_first = torch.randn(B, code).pin_memory()
+        h_reals = [torch.rand(B, 3, H, W).pin_memory() for _ in range(self.hops)]
+        h_loss = torch.empty(4 * self.hops).pin_memory()
+        last = [None]
+
+        def step():
+            if self.graphed is not None:
+                out = self.graphed.step(h_first, h_reals, self.flags)
+            else:
+                self.first.copy_(h_first, non_blocking=True)
+                for d_, s_ in zip(self.reals, h_reals):
+                    d_.copy_(s_, non_blocking=True)
+                out = self.tr.step(self.first, self.reals, self.flags)
+            vals = [v.reshape(()) for rec in out for v in rec.values()]
+            h_loss[:len(vals)].copy_(torch.stack(vals), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            last[0] = h_loss[:len(vals)].tolist()
+        return step, (lambda: last[0]), "glis_b200.trainer.GraphedRIter.step(pinned first_code, reals) -> losses"
+
+
 def run_ours(args, rank, world, local):
     import torch.distributed as dist
-    import common.model as pm
-    from glis_b200 import _lib, dp, ops
-    from glis_b200.trainer import GLISTrainer, GraphedStep
+    from glis_b200 import _lib, dp
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: the product path needs a CUDA device (there is no CPU fallback)")
@@ -228,33 +513,8 @@ def run_ours(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     data_seed = dp.seed_everything(SEED, rank)
-    gen = pm.GeneratorLearnedInputSpace(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], CFG["code"], "weight",
-                                        CFG["n_lis"], "fractional").to(dev)
-    dis = pm.build_discriminator(CFG["W"], CFG["H"], CFG["nfeature"], CFG["nlayer"], "weight", 0).to(dev)
-    sync = dp.OverlappedGradSync(world) if world > 1 else None
-    tr = GLISTrainer(gen, dis, lr=CFG["lr"], lambda_r=CFG["lambda_r"], grad_sync=sync)
-    B, H, W, code = CFG["B"], CFG["H"], CFG["W"], CFG["code"]
-    depth = CFG["n_lis"]  # LIS depth forced to "all": fixed work per step (the stochastic schedule halves LIS work)
-
-    # ---- device-resident inputs (value): Philox on the device, a fresh batch every step
-    real = torch.empty(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
-    zd, zg = torch.empty(B, code, device=dev), torch.empty(B, code, device=dev)
-    counter = [0]
-
-    graphed = None
-    if not args.no_graph:
-        graphed = GraphedStep(tr, B, H, W, code, dev)
-        real, zd, zg = graphed.real, graphed.z_d, graphed.z_g   # fill the static buffers in place
-
-    def device_step():
-        off = counter[0] * (1 << 22)
-        counter[0] += 1
-        ops.uniform_(real, data_seed, off)
-        ops.randn_(zd, data_seed + 7, off)
-        ops.randn_(zg, data_seed + 13, off)
-        if graphed is not None:
-            return graphed.step(None, None, None, depth, depth)
-        return tr.step(real, zd, zg, depth, depth)
+    wl = (RIterWorkload if CFG["riter"] else GlisWorkload)(dev, world, data_seed, not args.no_graph)
+    B = CFG["B"]
 
     def barrier():
         if world > 1:
@@ -280,75 +540,38 @@ def run_ours(args, rank, world, local):
     if rank == 0:
         sampler.start()          # nvidia-smi needs ~0.2 s to produce its first sample: start it before the warm-up
     for _ in range(args.warmup):
-        device_step()
-    launches0 = _lib.launch_count
-    ms_total = timed_region(device_step, args.steps)
-    launches = _lib.launch_count - launches0
-    if graphed is not None:
-        # a replayed graph launches the kernels captured once: count them from an eager step
-        l0 = _lib.launch_count
-        tr.step(real, zd, zg, depth, depth)
-        launches = args.steps * (_lib.launch_count - l0 + 3)
+        wl.device_step()
+    ms_total = timed_region(wl.device_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step * 1e-3)
 
-    # ---- per-kernel timing for the roofline (separate short pass; events serialise nothing)
-    _lib.timed.enabled = True
-    for _ in range(min(args.steps, 5)):
-        ops.uniform_(real, data_seed, 1 << 40)
-        tr.step(real, zd, zg, depth, depth)      # eager: the event brackets cannot live inside a graph
+    # ---- kernels per iteration: a replayed graph launches what was captured once, so count one eager iteration
+    # through the C ABI (every launch of the library goes through _lib.call) and tally the tensor-core launches by tag
+    _lib.launch_tags.clear()
+    l0 = _lib.launch_count
+    wl.eager_step()
     torch.cuda.synchronize()
-    _lib.timed.enabled = False
-    per_kernel = _lib.timer_summary()
+    per_step = _lib.launch_count - l0
+    tags = dict(_lib.launch_tags)
+    launches = args.steps * (per_step + 3)       # + the three input generators
     if args.kernel_table and rank == 0:
         with open(args.kernel_table, "w") as fh:
-            json.dump({k: {"launches": c, "ms": m} for k, (c, m) in sorted(per_kernel.items())}, fh, indent=1)
+            json.dump({"launches_per_iteration": per_step, "tagged": tags}, fh, indent=1, sort_keys=True)
 
-    probe = probe_dominant_kernel(dev, prec_name) if rank == 0 else None
+    probe = probe_dominant_kernel(dev) if rank == 0 else None
 
-    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses, through the public
-    # host-fed API (trainer.HostFedStepper): every iteration's image + noise batches cross PCIe from
-    # pinned memory and every iteration's losses are read back on the host; the copy of iteration
-    # i+1 overlaps the compute of iteration i and the host reads losses one iteration late.
-    h_real = torch.rand(B, 3, H, W).pin_memory()
-    h_zd, h_zg = torch.randn(B, code).pin_memory(), torch.randn(B, code).pin_memory()
-    if graphed is not None:
-        from glis_b200.trainer import HostFedStepper
-        feeder = HostFedStepper(graphed)
-        h2d, d2h = feeder.h2d_bytes, 4 * (3 + CFG["n_lis"])
-        last = [None]
-
-        def e2e_step():
-            last[0] = feeder.submit(h_real, h_zd, h_zg, depth, depth)
-
-        def e2e_drain():
-            last[0] = feeder.flush()
-    else:
-        d_real = torch.empty(B, 3, H, W, device=dev)
-        h_loss = torch.empty(3).pin_memory()
-        h2d = h_real.numel() * 4 + h_zd.numel() * 4 + h_zg.numel() * 4
-        d2h = h_loss.numel() * 4
-
-        def e2e_step():
-            d_real.copy_(h_real, non_blocking=True)
-            zd.copy_(h_zd, non_blocking=True)
-            zg.copy_(h_zg, non_blocking=True)
-            out = tr.step(d_real, zd, zg, depth, depth)
-            h_loss.copy_(torch.stack([out["d_real"], out["d_fake"], out["g"]]), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        def e2e_drain():
-            pass
-
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses, through the public host-fed API
+    e2e_step, e2e_drain, e2e_api = wl.make_e2e()
     for _ in range(max(3, args.warmup // 2)):
         e2e_step()
     e2e_drain()
+    e2e_losses = [None]
 
     def e2e_region():
         for _ in range(args.steps):
             e2e_step()
-        e2e_drain()          # the last iteration's losses are read inside the timed region too
+        e2e_losses[0] = e2e_drain()   # the last iteration's losses are read inside the timed region too
 
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -364,49 +587,45 @@ def run_ours(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = t.item()
     e2e_value = B * world / (ms_e2e * 1e-3)
-    e2e_losses = last[0] if graphed is not None else None
 
     if rank != 0:
         return
     peaks = measured_peaks()
-    fam = {k: v for k, v in per_kernel.items() if "conv" in k}
     roofline = probe
-    if roofline is not None and fam:
+    if roofline is not None:
         def flops(tag):
             dims = dict(kv.split("=") for kv in tag.split() if "=" in kv)
             return 2.0 * int(dims["M"]) * int(dims["N"]) * int(dims["K"])
-        n = min(args.steps, 5)
-        tc = {t: v for t, v in fam.items() if t.endswith(" tc")}
+        tc = {t: c for t, c in tags.items() if t.endswith(" tc") or " tc " in t}
         roofline["peak"] = peaks["tf_burst"]
         roofline["frac"] = roofline["achieved"] / peaks["tf_burst"]
         roofline["frac_mma_pipe"] = roofline["mma_pipe_tflops"] / peaks["tf_burst"]
         roofline["peak_source"] = peaks["source"] + " bf16 dense cuBLAS, burst (kernel timed alone)"
-        roofline["tensor_core_launches_per_step"] = sum(c for c, _ in tc.values()) / n
-        roofline["tensor_core_gflop_per_step"] = sum(flops(t) * c for t, (c, m) in tc.items()) / n / 1e9
-    cpu = None
+        roofline["tensor_core_launches_per_step"] = sum(tc.values())
+        roofline["tensor_core_gflop_per_step"] = sum(flops(t) * c for t, c in tc.items()) / 1e9
+    cpu = lib = None
     if world == 1 and not args.no_cpu_baseline:
         sec, cores, b_step = time_cpu_oracle(3, 1)
         cpu = {"value": b_step / sec, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "3 full config-2 iterations (B=64) after 1 warm-up; oracle port, torch %s CPU, %s; "
-                         "reference pin (py2.7/PyTorch@065c5986) not installable offline" % (torch.__version__,
-                                                                                           cpu_model())}
-    act_mb = 4 * (13.52e6 + 12.29e6) * 2 / 1e6
+               "sample": "3 full iterations of the workload (batch %d) after 1 warm-up; oracle port, torch %s CPU, %s; "
+                         "reference pin (py2.7/PyTorch@065c5986) not installable offline" % (
+                             b_step, torch.__version__, cpu_model())}
+        lib = time_gpu_library(dev)
     print(json.dumps({
-        "metric": "G-LIS train images/sec at 80x80 bs64/GPU", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": metric_name(), "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32-faithful) + f32", "bf16": "bf16"}[prec_name],
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "lis_depth": "all", "precision": prec_name, "cuda_graph": graphed is not None,
-                   "l2": "inputs larger than L2: ~%.0f MB of activations + 36 MB of weights touched per step"
-                         % act_mb,
-                   "gflop_per_step": GFLOP_PER_STEP,
-                   "step_tflops": GFLOP_PER_STEP * world / ms_step},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "host_wall_ms_per_step": wall_ms / args.steps, "last_losses": e2e_losses,
-                "api": "glis_b200.trainer.HostFedStepper.submit(pinned real, z_d, z_g) -> losses"},
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32-faithful) + f32", "bf16": "bf16",
+                  "tf32": "tf32 gradients + bf16x3 forward"}.get(prec_name, prec_name),
+        "data": "synthetic", "config": bench_config(),
+        "details": {"global_batch": B * world, "parallelism": "dp%d" % world, "precision": prec_name,
+                    "cuda_graph": wl.graphed is not None, "step_tflops": GFLOP_PER_STEP * world / ms_step,
+                    "launches_per_iteration": per_step},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h,
+                "ms_per_step": ms_e2e, "host_wall_ms_per_step": wall_ms / args.steps, "last_losses": e2e_losses[0],
+                "api": e2e_api},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_library_baseline": lib,
     }))
 
 
@@ -416,11 +635,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: 1, 2 (default, the driver's line), 3, 4, 5a (R-iterative), 5b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python (no CUDA graph)")
-    ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (JSON) here")
+    ap.add_argument("--kernel-table", default=None, help="write the per-iteration launch tally (JSON) here")
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
+    select_config(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

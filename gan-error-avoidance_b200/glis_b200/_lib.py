@@ -120,7 +120,6 @@ def ptr(t):
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 
 launch_count = 0     # kernels this process enqueued through the C ABI
-_timers = {}         # tag -> list of (start_event, end_event); see `timed`
 
 
 def ptr16(t):
@@ -149,32 +148,20 @@ def call(name, *args, kernels=None):
     launch_count += KERNELS_PER_CALL[name] if kernels is None else kernels
 
 
-class timed(object):
-    """``with timed(tag):`` brackets the enclosed launches with CUDA events on the current
-    stream when profiling is on (bench.py's per-kernel roofline); free otherwise."""
+launch_tags = {}     # tag -> launches (GEMM-shaped launches tag themselves with their M / N / K: bench.py's tally)
 
-    enabled = False
+
+class timed(object):
+    """``with timed(tag):`` tallies the enclosed launch under ``tag`` (kernel family + GEMM shape).  Counting only:
+    per-kernel TIMES come from the ncu launch lists under profiles/ — CUDA events recorded around an asynchronous
+    launch bracket its enqueue, not its execution."""
 
     def __init__(self, tag):
         self.tag = tag
 
     def __enter__(self):
-        if timed.enabled:
-            self.start = torch.cuda.Event(enable_timing=True)
-            self.end = torch.cuda.Event(enable_timing=True)
-            self.start.record()
+        launch_tags[self.tag] = launch_tags.get(self.tag, 0) + 1
         return self
 
     def __exit__(self, *exc):
-        if timed.enabled:
-            self.end.record()
-            _timers.setdefault(self.tag, []).append((self.start, self.end))
         return False
-
-
-def timer_summary(reset=True):
-    """tag -> (launches, mean milliseconds). Call after a device synchronize."""
-    out = {k: (len(v), sum(s.elapsed_time(e) for s, e in v) / len(v)) for k, v in _timers.items() if v}
-    if reset:
-        _timers.clear()
-    return out
