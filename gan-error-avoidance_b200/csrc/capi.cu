@@ -26,6 +26,7 @@ int tc_conv_plan_describe(const glis_geom_t* g, int plain_out, int out[15]);
 int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
+int tc_conv_halo_describe(const glis_geom_t* g, int plain_out, int out[20]);
 int tc_pm_supported(const glis_geom_t* g);
 int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                   const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
@@ -94,6 +95,15 @@ extern "C" int glis_conv_tc_plan(const glis_geom_t* g, int plain_out, int* out15
   GLIS_REQUIRE(out15 != nullptr, GLIS_E_BADARG, "glis_conv_tc_plan: NULL output");
   GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_tc_plan: geometry not tileable for tcgen05");
   return tc_conv_plan_describe(g, plain_out, out15);
+}
+
+extern "C" int glis_conv_tc_halo_plan(const glis_geom_t* g, int plain_out, int* out20) {
+  int rc = validate_geom(g, "glis_conv_tc_halo_plan");
+  if (rc != GLIS_OK) return rc;
+  GLIS_REQUIRE(out20 != nullptr, GLIS_E_BADARG, "glis_conv_tc_halo_plan: NULL output");
+  rc = tc_conv_halo_describe(g, plain_out, out20);
+  if (rc != GLIS_OK) set_error("glis_conv_tc_halo_plan: the halo kernel does not apply to this geometry");
+  return rc;
 }
 
 extern "C" int glis_conv_forward_bf16(const glis_geom_t* g, const void* x_hi, const void* x_lo, const void* w_hi,

@@ -357,6 +357,131 @@ static int launch_linear_wgrad(const float* small, const float* big, float* G, i
   return GLIS_OK;
 }
 
+// ---------------------------------------------------------------------------- weight gradient + projection
+// Weight gradient of a weight-normalised LINEAR layer with the weight-norm projection in the same
+// kernel: for master row o
+//     G_o = sum_m dy[m][a(o)] x[m][:],   dw_o (+)= (s_o / n_o) (G_o - w_o <G_o, w_o> / n_o^2),   ds_o (+)= <G_o, w_o> / n_o
+// The batch is small (64-256 rows) and a row short (<= 1024 inputs), so a WARP owns a whole row: x is staged in
+// shared memory once per block, the row's 8 (16, 32) outputs per lane stay in registers through the dot product
+// with w_o, and the raw gradient never exists in memory.  Replaces two launches (linear_wgrad_kernel +
+// wn_project_warp_kernel: 51 + 26 us for G's 12800 x 256 initial linear) by one (~10 us), at the END of G's
+// backward, where nothing else is left to overlap with.
+constexpr int LP_NT = 256;
+constexpr int LP_ROWS = 4;   // rows a warp carries at once: every x value read from shared memory feeds 4 FMAs
+template <int PER>   // outputs per lane: Cb <= 32 * PER
+__global__ void __launch_bounds__(LP_NT)
+linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                            const float* __restrict__ scale, const float* __restrict__ norm, float* __restrict__ dw,
+                            float* __restrict__ dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
+                            int rows_per_block) {
+  extern __shared__ __align__(16) float lp_xs[];        // [M][Cb]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  {
+    // stage x: batches of 8 independent loads per thread (a plain load -> store loop serialises on the load latency)
+    const int total = M * Cb;
+    for (int i0 = tid; i0 < total; i0 += 8 * LP_NT) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (i0 + u * LP_NT < total) ? __ldg(x + i0 + u * LP_NT) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * LP_NT < total) lp_xs[i0 + u * LP_NT] = v[u];
+    }
+  }
+  __syncthreads();
+  const int a_beg = blockIdx.x * rows_per_block, a_end = min(Ca, a_beg + rows_per_block);
+  for (int a0 = a_beg + wid * LP_ROWS; a0 < a_end; a0 += (LP_NT / 32) * LP_ROWS) {
+    float acc[LP_ROWS][PER];
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r)
+#pragma unroll
+      for (int u = 0; u < PER; ++u) acc[r][u] = 0.f;
+    // dy[m][a0 .. a0 + 3]: lanes fetch 32 batch rows at a time, then broadcast
+    for (int m0 = 0; m0 < M; m0 += 32) {
+      float dmine[LP_ROWS];
+#pragma unroll
+      for (int r = 0; r < LP_ROWS; ++r)
+        dmine[r] = (m0 + lane < M && a0 + r < a_end) ? __ldg(dy + (size_t)(m0 + lane) * Ca + a0 + r) : 0.f;
+      const int mc = min(32, M - m0);
+      for (int mm = 0; mm < mc; ++mm) {
+        float d[LP_ROWS];
+#pragma unroll
+        for (int r = 0; r < LP_ROWS; ++r) d[r] = __shfl_sync(0xffffffffu, dmine[r], mm);
+        const float* xr = lp_xs + (size_t)(m0 + mm) * Cb;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int j = lane + 32 * u;
+          const float xv = j < Cb ? xr[j] : 0.f;
+#pragma unroll
+          for (int r = 0; r < LP_ROWS; ++r) acc[r][u] = fmaf(d[r], xv, acc[r][u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+      const int a = a0 + r;
+      if (a >= a_end) break;                                             // (uniform across the warp)
+      const int o = perm_c ? (a % perm_c) * perm_p + a / perm_c : a;     // master row of pack row a
+      float wv[PER], dot = 0.f;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int j = lane + 32 * u;
+        wv[u] = j < Cb ? __ldg(w + (size_t)o * Cb + j) : 0.f;
+        dot = fmaf(acc[r][u], wv[u], dot);
+      }
+      dot = warp_sum(dot);
+      const float n = __ldg(norm + o), sc = scale ? __ldg(scale + o) : 1.f;
+      const float k1 = sc / n, k2 = dot / (n * n);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int j = lane + 32 * u;
+        if (j < Cb) {
+          const float v = k1 * (acc[r][u] - k2 * wv[u]);
+          float* dst = dw + (size_t)o * Cb + j;
+          *dst = accumulate ? *dst + v : v;
+        }
+      }
+      if (dscale && lane == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
+    }
+  }
+}
+
+int linear_wgrad_project_supported(int M, int Ca, int Cb) {
+  return M >= 1 && M <= 512 && Cb >= 1 && Cb <= 1024 && (size_t)M * Cb * sizeof(float) <= 200 * 1024 && Ca >= 1;
+}
+
+int linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale, const float* norm,
+                         float* dw, float* dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
+                         cudaStream_t st) {
+  GLIS_REQUIRE(linear_wgrad_project_supported(M, Ca, Cb), GLIS_E_UNSUPPORTED,
+               "glis_linear_wgrad_project: batch %d x %d inputs does not fit the fused kernel", M, Cb);
+  const size_t smem = (size_t)M * Cb * sizeof(float);
+  // enough blocks to give every SM a few, each with >= 8 rows (one per warp) so that staging x pays
+  int rows_per_block = (Ca + 148 * 2 - 1) / (148 * 2);
+  rows_per_block = (rows_per_block + 31) / 32 * 32;       // 8 warps x LP_ROWS rows per pass
+  if (rows_per_block < 32) rows_per_block = 32;
+  const int blocks = (Ca + rows_per_block - 1) / rows_per_block;
+#define LP_LAUNCH(PER)                                                                                              \
+  do {                                                                                                              \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      cudaError_t e = cudaFuncSetAttribute(linear_wgrad_project_kernel<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           200 * 1024);                                                             \
+      GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(linear_wgrad_project): %s", cudaGetErrorString(e)); \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    linear_wgrad_project_kernel<PER><<<blocks, LP_NT, smem, st>>>(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
+                                                                  perm_p, accumulate, rows_per_block);             \
+  } while (0)
+  if (Cb <= 128) LP_LAUNCH(4);
+  else if (Cb <= 256) LP_LAUNCH(8);
+  else if (Cb <= 512) LP_LAUNCH(16);
+  else LP_LAUNCH(32);
+#undef LP_LAUNCH
+  GLIS_CHECK_LAUNCH("glis_linear_wgrad_project");
+  return GLIS_OK;
+}
+
 int simt_linear_wgrad(const glis_geom_t* g, const float* small, const float* big, float* G, cudaStream_t st) {
   return launch_linear_wgrad(small, big, G, g->N, g->Co, g->Ci, g->KH * g->KW, 0, 0, st);
 }
@@ -370,4 +495,20 @@ extern "C" int glis_linear_wgrad(const float* dy, const float* x, float* G, int 
   GLIS_REQUIRE((perm_c == 0 && perm_p == 0) || (perm_c > 0 && perm_p > 0 && (int64_t)perm_c * perm_p == Ca), GLIS_E_BADARG,
                "glis_linear_wgrad: bad row permutation (C=%d P=%d for %d rows)", perm_c, perm_p, Ca);
   return launch_linear_wgrad(dy, x, G, M, Ca, Cb, 1, perm_c, perm_p, (cudaStream_t)stream);
+}
+
+extern "C" int glis_linear_wgrad_project_supported(int M, int Ca, int Cb) {
+  return glis::linear_wgrad_project_supported(M, Ca, Cb);
+}
+
+extern "C" int glis_linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale,
+                                         const float* norm, float* dw, float* dscale, int M, int Ca, int Cb, int perm_c,
+                                         int perm_p, int accumulate, void* stream) {
+  using namespace glis;
+  GLIS_REQUIRE(dy && x && w && norm && dw && M > 0 && Ca > 0 && Cb > 0, GLIS_E_BADARG,
+               "glis_linear_wgrad_project: bad arguments");
+  GLIS_REQUIRE((perm_c == 0 && perm_p == 0) || (perm_c > 0 && perm_p > 0 && (int64_t)perm_c * perm_p == Ca), GLIS_E_BADARG,
+               "glis_linear_wgrad_project: bad row permutation (C=%d P=%d for %d rows)", perm_c, perm_p, Ca);
+  return linear_wgrad_project(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, perm_p, accumulate,
+                              (cudaStream_t)stream);
 }

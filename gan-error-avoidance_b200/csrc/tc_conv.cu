@@ -442,8 +442,17 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first;
 // strides in bytes for dims 1..rank-1.
+int make_bf16_map_swz(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, int swizzle_bytes);
+
 int make_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                   const uint32_t* box) {
+  return make_bf16_map_swz(m, ptr, rank, dims, strides, box, 128);
+}
+
+// swizzle_bytes: 128 (64 bf16 per shared-memory row) or 64 (32 per row)
+int make_bf16_map_swz(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   GLIS_REQUIRE(enc != nullptr, GLIS_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t d[5], s[4];
@@ -451,8 +460,9 @@ int make_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dim
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GLIS_REQUIRE(r == CUDA_SUCCESS, GLIS_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return GLIS_OK;
 }
@@ -586,8 +596,15 @@ static int tc_plan(const glis_geom_t* g, bool plain_out, TcConvParams& P) {
 
 // The K split a plain-output launch of this geometry would use (1 = none): lets the host decide to run a
 // fused-epilogue layer as split-K sums + one pointwise pass when its tiles alone cannot fill the machine.
+int tc_conv_halo_applies(const glis_geom_t* g, int plain_out);
+int tc_conv_halo_ksplit(const glis_geom_t* g);
+int tc_conv_halo_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                         __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
+
 int tc_conv_plan_ksplit(const glis_geom_t* g) {
   if (!tc_conv_supported(g)) return 1;
+  if (tc_conv_halo_applies(g, 1)) return tc_conv_halo_ksplit(g);   // the kernel that would run
   TcConvParams P;
   if (tc_plan(g, true, P) != GLIS_OK) return 1;
   return P.ksplit;
@@ -615,6 +632,12 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st) {
   GLIS_REQUIRE(tc_conv_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: geometry not tileable for tcgen05");
+  {
+    // layers whose taps share pixel boxes (4x4 stride 2, 3x3 stride 1) run on the halo kernel (tc_conv2.cu)
+    const bool plain = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
+    if (tc_conv_halo_applies(g, plain))
+      return tc_conv_halo_forward(g, x_hi, x_lo, w_hi, w_lo, ep, out_f32, out_hi, out_lo, precision, st);
+  }
   const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
   GLIS_REQUIRE(x_hi && w_hi && (passes == 1 || (x_lo && w_lo)), GLIS_E_BADARG,
                "glis_conv_forward_bf16: missing hi/lo operand planes");

@@ -232,15 +232,6 @@ wn_project_warp_kernel(const float* __restrict__ G, const float* __restrict__ w,
   if (dscale && lane == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
 }
 
-}  // namespace glis
-
-using namespace glis;
-
-extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
-                               float c, float* norm, float* pack_io, float* pack_oi, void* stream) {
-  return glis_wn_prepare_perm(w, scale, out_axis, Cout, Cin, T, c, norm, pack_io, pack_oi, 0, 0, stream);
-}
-
 static int check_perm(int out_axis, int Cout, int T, int perm_c, int perm_p, const char* who) {
   GLIS_REQUIRE((perm_c == 0 && perm_p == 0) ||
                    (perm_c > 0 && perm_p > 0 && T == 1 && out_axis == 0 && (int64_t)perm_c * perm_p == Cout),
@@ -248,6 +239,241 @@ static int check_perm(int out_axis, int Cout, int T, int perm_c, int perm_p, con
                out_axis);
   return GLIS_OK;
 }
+
+// ---------------------------------------------------------------------------- multi-tensor prepare
+// All layers of a network in TWO launches (norms, then packs) instead of a launch pair per layer: the descriptors
+// travel as a kernel parameter (captured by value into a CUDA graph), a block finds its layer by scanning the
+// block-offset prefix.  ~30 launches of 3-20 us become 2 per network and update.
+constexpr int WN_MULTI_MAX = 24;
+struct WnMultiParams {
+  int n;
+  int norm_block_begin[WN_MULTI_MAX + 1];   // norm kernel: blocks of layer l = [begin[l], begin[l+1])
+  int pack_block_begin[WN_MULTI_MAX + 1];   // pack kernel
+  glis_wn_layer_t L[WN_MULTI_MAX];
+};
+
+__global__ void __launch_bounds__(WN_NT)
+wn_norm_multi_kernel(const __grid_constant__ WnMultiParams P) {
+  __shared__ float red[33];
+  int l = 0;
+  while (l + 1 < P.n && (int)blockIdx.x >= P.norm_block_begin[l + 1]) ++l;
+  const glis_wn_layer_t& Y = P.L[l];
+  const int b = blockIdx.x - P.norm_block_begin[l];
+  const int R = Y.Cin * Y.T;
+  const float* __restrict__ w = Y.w;
+  if (R <= 512) {                      // one warp per output channel, 8 channels per block
+    const int o = b * (WN_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= Y.Cout) return;
+    float ss = 0.f;
+#pragma unroll 8
+    for (int r = lane; r < R; r += 32) {
+      const int i = r / Y.T, t = r - i * Y.T;
+      const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) Y.norm[o] = sqrtf(ss * Y.c + 1e-6f);
+    return;
+  }
+  const int o = b;                     // one block per output channel
+  float ss = 0.f;
+#pragma unroll 8
+  for (int r = threadIdx.x; r < R; r += WN_NT) {
+    const int i = r / Y.T, t = r - i * Y.T;
+    const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
+    ss = fmaf(v, v, ss);
+  }
+  ss = block_sum<WN_NT>(ss, red);
+  if (threadIdx.x == 0) Y.norm[o] = sqrtf(ss * Y.c + 1e-6f);
+}
+
+constexpr int WN_PACK_PER_BLOCK = WN_NT * 8;   // packed elements per block of the multi-tensor pack kernel
+
+__global__ void __launch_bounds__(WN_NT)
+wn_pack_multi_kernel(const __grid_constant__ WnMultiParams P) {
+  int l = 0;
+  while (l + 1 < P.n && (int)blockIdx.x >= P.pack_block_begin[l + 1]) ++l;
+  const glis_wn_layer_t& Y = P.L[l];
+  const uint32_t Cout = (uint32_t)Y.Cout, Cin = (uint32_t)Y.Cin, T = (uint32_t)Y.T;
+  const uint32_t total = T * Cin * Cout;
+  const uint32_t e0 = (uint32_t)(blockIdx.x - P.pack_block_begin[l]) * WN_PACK_PER_BLOCK;
+  const float* __restrict__ w = Y.w;
+  const float* __restrict__ scale = Y.scale;
+  const float* __restrict__ norm = Y.norm;
+  __nv_bfloat16* fwd_hi = (__nv_bfloat16*)Y.fwd_hi; __nv_bfloat16* fwd_lo = (__nv_bfloat16*)Y.fwd_lo;
+  __nv_bfloat16* bwd_hi = (__nv_bfloat16*)Y.bwd_hi; __nv_bfloat16* bwd_lo = (__nv_bfloat16*)Y.bwd_lo;
+  __nv_bfloat16* e_hi = (__nv_bfloat16*)Y.mat_hi; __nv_bfloat16* e_lo = (__nv_bfloat16*)Y.mat_lo;
+  __nv_bfloat16* et_hi = (__nv_bfloat16*)Y.matt_hi; __nv_bfloat16* et_lo = (__nv_bfloat16*)Y.matt_lo;
+#pragma unroll 2
+  for (uint32_t e = e0 + threadIdx.x; e < total && e < e0 + WN_PACK_PER_BLOCK; e += WN_NT) {
+    if (Y.pack_oi || fwd_hi) {   // [t][o][i]
+      const int i = (int)(e % Cin); const uint32_t r = e / Cin;
+      const int o = master_channel((int)(r % Cout), Y.perm_c, Y.perm_p);
+      const int t = (int)(r / Cout);
+      const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t)) *
+                      ((scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o));
+      if (Y.pack_oi) Y.pack_oi[e] = v;
+      if (fwd_hi) {
+        __nv_bfloat16 h, lo_;
+        sm100::split_bf16(v, h, lo_);
+        fwd_hi[e] = h;
+        if (fwd_lo) fwd_lo[e] = lo_;
+      }
+    }
+    if (Y.pack_io || bwd_hi) {   // [t][i][o]
+      const int o = master_channel((int)(e % Cout), Y.perm_c, Y.perm_p);
+      const uint32_t r = e / Cout; const int i = (int)(r % Cin); const int t = (int)(r / Cin);
+      const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t)) *
+                      ((scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o));
+      if (Y.pack_io) Y.pack_io[e] = v;
+      if (bwd_hi) {
+        __nv_bfloat16 h, lo_;
+        sm100::split_bf16(v, h, lo_);
+        bwd_hi[e] = h;
+        if (bwd_lo) bwd_lo[e] = lo_;
+      }
+    }
+    if (e_hi || et_hi) {         // E[a][j] over the master order (image-side layers), E^T[j][a]
+      const uint32_t J = total / (uint32_t)Y.mat_rows;
+      const uint32_t a = e / J, j = e - a * J;
+      const int o = Y.out_axis == 0 ? (int)a : (int)(j / T);
+      const float v = __ldg(w + e) * ((scale ? __ldg(scale + o) : 1.f) / __ldg(norm + o));
+      __nv_bfloat16 h, lo_;
+      sm100::split_bf16(v, h, lo_);
+      if (e_hi) { e_hi[e] = h; if (e_lo) e_lo[e] = lo_; }
+      if (et_hi) { et_hi[(size_t)j * Y.mat_rows + a] = h; if (et_lo) et_lo[(size_t)j * Y.mat_rows + a] = lo_; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- multi-tensor projection
+struct WnProjMultiParams {
+  int n;
+  int block_begin[WN_MULTI_MAX + 1];
+  glis_wn_proj_t L[WN_MULTI_MAX];
+};
+
+// Two passes over a row (the second one hits L1 / L2): dot = <G_o, w_o>, then dw_o (+)= (s/n)(G_o - c w_o dot / n^2).
+// Rows of <= 512 elements: one warp per output channel, 8 per block; longer rows: one block per channel.
+__global__ void __launch_bounds__(WN_NT)
+wn_project_multi_kernel(const __grid_constant__ WnProjMultiParams P) {
+  __shared__ float red[33];
+  int l = 0;
+  while (l + 1 < P.n && (int)blockIdx.x >= P.block_begin[l + 1]) ++l;
+  const glis_wn_proj_t& Y = P.L[l];
+  const int b = blockIdx.x - P.block_begin[l];
+  const int R = Y.Cin * Y.T;
+  const float* __restrict__ G = Y.G;
+  const float* __restrict__ w = Y.w;
+  float* __restrict__ dw = Y.dw;
+  const bool warp_rows = R <= 512;
+  const int o = warp_rows ? b * (WN_NT / 32) + (threadIdx.x >> 5) : b;
+  const int r0 = warp_rows ? (threadIdx.x & 31) : threadIdx.x, rs = warp_rows ? 32 : WN_NT;
+  if (o >= Y.Cout) return;             // (whole warps: the block-wide sum below is only reached by full blocks)
+  float dot = 0.f;
+#pragma unroll 4
+  for (int r = r0; r < R; r += rs) {
+    const int i = r / Y.T, t = r - i * Y.T;
+    const int64_t idx = master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t);
+    dot = fmaf(__ldg(G + idx), __ldg(w + idx), dot);
+  }
+  dot = warp_rows ? warp_sum(dot) : block_sum<WN_NT>(dot, red, true);
+  const float n = __ldg(Y.norm + o), sc = Y.scale ? __ldg(Y.scale + o) : 1.f;
+  const float a = sc / n, k = Y.c * dot / (n * n);
+#pragma unroll 4
+  for (int r = r0; r < R; r += rs) {
+    const int i = r / Y.T, t = r - i * Y.T;
+    const int64_t idx = master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t);
+    const float v = a * (__ldg(G + idx) - k * __ldg(w + idx));
+    dw[idx] = Y.accumulate ? dw[idx] + v : v;
+  }
+  if (Y.dscale && r0 == 0) Y.dscale[o] = Y.accumulate ? Y.dscale[o] + dot / n : dot / n;
+}
+
+}  // namespace glis
+
+using namespace glis;
+
+extern "C" int glis_wn_project_multi(const glis_wn_proj_t* items, int n, void* stream) {
+  GLIS_REQUIRE(items && n >= 0, GLIS_E_BADARG, "glis_wn_project_multi: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n; base += WN_MULTI_MAX) {
+    WnProjMultiParams P;
+    P.n = n - base < WN_MULTI_MAX ? n - base : WN_MULTI_MAX;
+    int nb = 0;
+    for (int l = 0; l < P.n; ++l) {
+      const glis_wn_proj_t& Y = items[base + l];
+      GLIS_REQUIRE(Y.G && Y.w && Y.norm && Y.dw && Y.Cout > 0 && Y.Cin > 0 && Y.T > 0 && (Y.out_axis == 0 || Y.out_axis == 1),
+                   GLIS_E_BADARG, "glis_wn_project_multi: item %d: bad descriptor", base + l);
+      P.L[l] = Y;
+      P.block_begin[l] = nb;
+      nb += (int64_t)Y.Cin * Y.T <= 512 ? (Y.Cout + WN_NT / 32 - 1) / (WN_NT / 32) : Y.Cout;
+    }
+    P.block_begin[P.n] = nb;
+    if (nb > 0) {
+      wn_project_multi_kernel<<<nb, WN_NT, 0, st>>>(P);
+      GLIS_CHECK_LAUNCH("glis_wn_project_multi");
+    }
+  }
+  return GLIS_OK;
+}
+
+
+extern "C" int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void* stream) {
+  GLIS_REQUIRE(layers && n >= 0, GLIS_E_BADARG, "glis_wn_prepare_multi: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n; base += WN_MULTI_MAX) {
+    WnMultiParams P;
+    P.n = n - base < WN_MULTI_MAX ? n - base : WN_MULTI_MAX;
+    int nb = 0, pb = 0;
+    bool any_pack = false, any_norm = false;
+    for (int l = 0; l < P.n; ++l) {
+      const glis_wn_layer_t& Y = layers[base + l];
+      GLIS_REQUIRE(Y.w && Y.norm && Y.Cout > 0 && Y.Cin > 0 && Y.T > 0 && (Y.out_axis == 0 || Y.out_axis == 1), GLIS_E_BADARG,
+                   "glis_wn_prepare_multi: layer %d: bad descriptor", base + l);
+      GLIS_REQUIRE((int64_t)Y.T * Y.Cin * Y.Cout < ((int64_t)1 << 31), GLIS_E_UNSUPPORTED,
+                   "glis_wn_prepare_multi: layer %d has 2^31 or more weights", base + l);
+      if (int rc = check_perm(Y.out_axis, Y.Cout, Y.T, Y.perm_c, Y.perm_p, "glis_wn_prepare_multi")) return rc;
+      GLIS_REQUIRE((Y.fwd_hi || !Y.fwd_lo) && (Y.bwd_hi || !Y.bwd_lo) && (Y.mat_hi || !Y.mat_lo) && (Y.matt_hi || !Y.matt_lo),
+                   GLIS_E_BADARG, "glis_wn_prepare_multi: layer %d: lo plane without hi", base + l);
+      const bool mats = Y.mat_hi || Y.matt_hi;
+      GLIS_REQUIRE(!mats || (Y.mat_rows > 0 && ((int64_t)Y.T * Y.Cin * Y.Cout) % Y.mat_rows == 0 && Y.perm_c == 0), GLIS_E_BADARG,
+                   "glis_wn_prepare_multi: layer %d: bad matrix pack shape", base + l);
+      P.L[l] = Y;
+      P.norm_block_begin[l] = nb;
+      if (Y.need_norm) {
+        const int64_t R = (int64_t)Y.Cin * Y.T;
+        nb += R <= 512 ? (Y.Cout + WN_NT / 32 - 1) / (WN_NT / 32) : Y.Cout;
+        any_norm = true;
+      }
+      P.pack_block_begin[l] = pb;
+      if (Y.pack_io || Y.pack_oi || Y.fwd_hi || Y.bwd_hi || mats) {
+        const int64_t total = (int64_t)Y.T * Y.Cin * Y.Cout;
+        pb += (int)((total + WN_PACK_PER_BLOCK - 1) / WN_PACK_PER_BLOCK);
+        any_pack = true;
+      }
+    }
+    P.norm_block_begin[P.n] = nb;
+    P.pack_block_begin[P.n] = pb;
+    // (a layer without work owns an empty block range: the prefix scan skips it)
+    if (any_norm && nb > 0) {
+      wn_norm_multi_kernel<<<nb, WN_NT, 0, st>>>(P);
+      GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(norm)");
+    }
+    if (any_pack && pb > 0) {
+      wn_pack_multi_kernel<<<pb, WN_NT, 0, st>>>(P);
+      GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(pack)");
+    }
+  }
+  return GLIS_OK;
+}
+
+
+extern "C" int glis_wn_prepare(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
+                               float c, float* norm, float* pack_io, float* pack_oi, void* stream) {
+  return glis_wn_prepare_perm(w, scale, out_axis, Cout, Cin, T, c, norm, pack_io, pack_oi, 0, 0, stream);
+}
+
 
 extern "C" int glis_wn_prepare_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T,
                                     float c, float* norm, float* pack_io, float* pack_oi, int perm_c, int perm_p,

@@ -29,12 +29,28 @@ class Epilogue(C.Structure):
                 ("act_channels", C.c_int32), ("split_slabs", C.c_int32)]
 
 
+class WnLayer(C.Structure):
+    """glis_wn_layer_t: one layer of a glis_wn_prepare_multi call."""
+    _fields_ = ([(n, C.c_void_p) for n in ("w", "scale", "norm", "pack_io", "pack_oi", "fwd_hi", "fwd_lo", "bwd_hi",
+                                            "bwd_lo", "mat_hi", "mat_lo", "matt_hi", "matt_lo")]
+                + [(n, C.c_int32) for n in ("out_axis", "Cout", "Cin", "T", "perm_c", "perm_p", "mat_rows", "need_norm")]
+                + [("c", C.c_float), ("reserved", C.c_int32)])
+
+
+class WnProj(C.Structure):
+    """glis_wn_proj_t: one layer of a glis_wn_project_multi call."""
+    _fields_ = ([(n, C.c_void_p) for n in ("G", "w", "scale", "norm", "dw", "dscale")]
+                + [(n, C.c_int32) for n in ("out_axis", "Cout", "Cin", "T", "accumulate")] + [("c", C.c_float)])
+
+
 _vp, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
 # name -> argtypes; every symbol include/glis_b200.h declares
 SIGNATURES = {
     "glis_wn_prepare": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "glis_wn_project": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
+    "glis_wn_prepare_multi": [C.POINTER(WnLayer), _i, _vp],
+    "glis_wn_project_multi": [C.POINTER(WnProj), _i, _vp],
     "glis_conv_forward": [C.POINTER(Geom), _vp, _vp, C.POINTER(Epilogue), _vp, _i, _vp],
     "glis_conv_wgrad": [C.POINTER(Geom), _vp, _vp, _vp, _i, _vp],
     "glis_split_bf16": [_vp, _vp, _vp, _i64, _vp],
@@ -42,6 +58,7 @@ SIGNATURES = {
     "glis_conv_tc_supported": [C.POINTER(Geom)],
     "glis_conv_tc_ksplit": [C.POINTER(Geom)],
     "glis_conv_tc_plan": [C.POINTER(Geom), _i, C.POINTER(C.c_int)],
+    "glis_conv_tc_halo_plan": [C.POINTER(Geom), _i, C.POINTER(C.c_int)],
     "glis_tprelu_forward_planes_sum": [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_lis_supported": [_i],
     "glis_lis_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
@@ -66,6 +83,8 @@ SIGNATURES = {
     "glis_wn_prepare_perm": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp],
     "glis_wn_prepare_bf16_perm": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "glis_linear_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "glis_linear_wgrad_project_supported": [_i, _i, _i],
+    "glis_linear_wgrad_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "glis_unfold4x4s2_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "glis_fold4x4s2": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "glis_wn_pack_matrix_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -240,6 +240,88 @@ class PackedWeights(object):
             _need_matrix(self, lo)
 
 
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def _describe(pw, part):
+    """glis_wn_layer_t for the kinds ``PackedWeights.refresh(part)`` would rebuild (buffers allocated, kinds marked
+    fresh), or None when there is nothing to do."""
+    wanted = pw.wanted()
+    lo = pw.spec.precision == L.PREC_BF16X3
+    f, b = part in ("all", "forward"), part in ("all", "backward")
+    fwd = f and "fwd" in wanted and "fwd" not in pw.fresh
+    bwd = b and "bwd" in wanted and "bwd" not in pw.fresh
+    io = f and "io" in wanted and "io" not in pw.fresh
+    oi = b and "oi" in wanted and "oi" not in pw.fresh
+    mat = f and "mat" in wanted and "mat" not in pw.fresh
+    norm = "norm" not in pw.fresh and (f or fwd or bwd or io or oi or mat)
+    if not (fwd or bwd or io or oi or mat or norm):
+        return None
+    w, sc = pw._w()
+    dev = w.device
+    mk16 = lambda shape: torch.empty(shape, device=dev, dtype=torch.bfloat16)
+    if pw.norm is None:
+        pw.norm = torch.empty(pw.cout, device=dev, dtype=torch.float32)
+    if io and pw.io is None:
+        pw.io = torch.empty(pw.t, pw.cin, pw.cout, device=dev, dtype=torch.float32)
+    if oi and pw.oi is None:
+        pw.oi = torch.empty(pw.t, pw.cout, pw.cin, device=dev, dtype=torch.float32)
+    for kind, want, shape in (("fwd", fwd, (pw.t, pw.cout, pw.cin)), ("bwd", bwd, (pw.t, pw.cin, pw.cout))):
+        if not want:
+            continue
+        cur = getattr(pw, kind)
+        hi = cur[0] if cur is not None else mk16(shape)
+        lo_t = cur[1] if cur is not None else None
+        if lo and lo_t is None:
+            lo_t = mk16(shape)
+        setattr(pw, kind, (hi, lo_t))
+    a = w.shape[0]
+    j = w.numel() // a
+    if mat:
+        if pw.mat is None:
+            pw.mat, pw.mat_t = (mk16((a, j)), mk16((a, j)) if lo else None), (mk16((j, a)), mk16((j, a)) if lo else None)
+        elif lo and pw.mat[1] is None:
+            pw.mat, pw.mat_t = (pw.mat[0], torch.empty_like(pw.mat[0])), (pw.mat_t[0], torch.empty_like(pw.mat_t[0]))
+    d = L.WnLayer()
+    d.w, d.scale, d.norm = w.data_ptr(), _dp(sc), pw.norm.data_ptr()
+    d.pack_io, d.pack_oi = _dp(pw.io) if io else None, _dp(pw.oi) if oi else None
+    if fwd:
+        d.fwd_hi, d.fwd_lo = pw.fwd[0].data_ptr(), _dp(pw.fwd[1]) if lo else None
+    if bwd:
+        d.bwd_hi, d.bwd_lo = pw.bwd[0].data_ptr(), _dp(pw.bwd[1]) if lo else None
+    if mat:
+        d.mat_hi, d.mat_lo = pw.mat[0].data_ptr(), _dp(pw.mat[1]) if lo else None
+        d.matt_hi, d.matt_lo = pw.mat_t[0].data_ptr(), _dp(pw.mat_t[1]) if lo else None
+        d.mat_rows = a
+    d.out_axis, d.Cout, d.Cin, d.T = pw.out_axis, pw.cout, pw.cin, pw.t
+    d.perm_c, d.perm_p = pw.spec.perm or (0, 0)
+    d.need_norm, d.c = int(norm), pw.spec.norm_factor
+    pw.fresh.add("norm")
+    for kind, want in (("fwd", fwd), ("bwd", bwd), ("io", io), ("oi", oi), ("mat", mat)):
+        if want:
+            pw.fresh.add(kind)
+    d._keep = (w, sc)               # the contiguous copies the pointers refer to stay alive until the call
+    return d
+
+
+MULTI_PREPARE = os.environ.get("GLIS_MULTI_PREPARE", "1") != "0"
+
+
+def refresh_many(pws, part):
+    """``pw.refresh(part)`` for every pack set in ``pws`` as ONE glis_wn_prepare_multi call (two launches: all
+    norms, then all packs) on the current stream."""
+    if not MULTI_PREPARE:
+        for pw in pws:
+            pw.refresh(part)
+        return
+    descs = [d for d in (_describe(pw, part) for pw in pws) if d is not None]
+    if not descs:
+        return
+    arr = (L.WnLayer * len(descs))(*descs)
+    L.call("glis_wn_prepare_multi", arr, len(descs), L.stream(), kernels=2 * ((len(descs) + 23) // 24))
+
+
 def _need_matrix(pw, lo):
     """E / E^T packs of an image-side layer (csrc/image_side.cu): one norm + one pack launch."""
     pw.wanted().add("mat")
@@ -310,10 +392,10 @@ def refresh_packs(flat, part="all", side=True):
     use_side = side and Overlap.enabled and torch.cuda.is_available()
     if not use_side:
         all_kinds = PackedWeights.FORWARD_KINDS + PackedWeights.BACKWARD_KINDS
-        if not (Overlap.enabled and torch.cuda.is_available() and len(todo) > 2):
+        if MULTI_PREPARE or not (Overlap.enabled and torch.cuda.is_available() and len(todo) > 2):
             for pw in todo:
                 pw._wait(all_kinds)
-                pw.refresh(part)
+            refresh_many(todo, part)
             return
         # Needed by the very next kernel (G's forward packs at the end of an iteration): the layers are
         # independent and each is a pair of short launches, so build them on three streams at once — the
@@ -351,8 +433,7 @@ def refresh_packs(flat, part="all", side=True):
     s.wait_event(ready)
     launches = L.launch_count
     with torch.cuda.stream(s):
-        for pw in todo:
-            pw.refresh(part)
+        refresh_many(todo, part)
         if L.launch_count == launches:
             return              # everything was fresh: nothing enqueued, nothing to wait for
         done = torch.cuda.Event()
@@ -718,6 +799,11 @@ class Overlap(object):
     reads are kept alive until the join."""
 
     enabled = os.environ.get("GLIS_OVERLAP_WGRAD", "1") != "0"
+    # one glis_wn_project_multi launch per backward pass instead of one launch per layer: measured SLOWER inside the
+    # step (1.95 vs 1.90 ms at config 2) — the per-layer projections are short kernels that run beside the main
+    # stream's data-gradient kernels for free, the batched one sits at the end of backward, in front of the optimizer
+    defer_projections = os.environ.get("GLIS_MULTI_PROJECT", "0") != "0"
+    _projections = []
     _on = False
     _side = None
     _main = None
@@ -770,10 +856,31 @@ class Overlap(object):
         cls._dirty = True
 
     @classmethod
+    def queue_projection(cls, graw, w, scale, norm, out_axis, cout, cin, t, c, dw, dscale, acc):
+        d = L.WnProj()
+        d.G, d.w, d.scale, d.norm = graw.data_ptr(), w.data_ptr(), _dp(scale), norm.data_ptr()
+        d.dw, d.dscale = dw.data_ptr(), _dp(dscale)
+        d.out_axis, d.Cout, d.Cin, d.T, d.accumulate, d.c = out_axis, cout, cin, t, int(acc), c
+        cls._projections.append((d, (graw, w, scale, norm, dw, dscale)))
+
+    @classmethod
+    def flush_projections(cls):
+        """The deferred weight-norm projections of this backward pass as one launch (on the side stream, behind
+        the weight gradients they read)."""
+        if not cls._projections:
+            return
+        items, cls._projections = cls._projections, []
+        arr = (L.WnProj * len(items))(*[d for d, _ in items])
+        with torch.cuda.stream(cls._side):
+            L.call("glis_wn_project_multi", arr, len(items), L.stream(), kernels=(len(items) + 23) // 24)
+        cls._keep.append(items)
+
+    @classmethod
     def join(cls):
         """The main stream waits for the side stream; call before anything reads a parameter gradient."""
         if not cls._on:
             return
+        cls.flush_projections()
         if cls._dirty:
             cls._main.wait_stream(cls._side)
         cls._keep = []
@@ -870,8 +977,12 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
         n, h, w, ho, wo = xc.shape[0], 1, 1, 1, 1
 
     dw = dscale = dbias = None
+    # batch-sized linear layers: weight gradient + weight-norm projection as ONE kernel (no raw gradient in memory)
+    fused_lin = ((need_dw or need_dscale) and xc.dim() == 2 and t == 1 and not spec.transposed
+                 and not isinstance(dyc, PlanesOnly) and FUSED_LINEAR_WGRAD
+                 and bool(L.load().glis_linear_wgrad_project_supported(n, cout, cin)))
     if need_dw or need_dscale:
-        graw, graw_stale = _take_scratch(weight)
+        graw, graw_stale = (None, False) if fused_lin else _take_scratch(weight)
         if spec.transposed:   # small = x (Cin), big = dy (Cout)
             g = spec.geom(L.CONV, n, ho, wo, cout, h, w, cin)
             small, big = xc, dyc
@@ -901,11 +1012,21 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
         if in_place:
             dw_buf, ds_buf, acc = direct_w, direct_s, 1
         else:
-            dw_buf = torch.empty_like(graw)
+            dw_buf = torch.empty_like(weight, memory_format=torch.contiguous_format)
             ds_buf = torch.empty(cout, device=dw_buf.device, dtype=torch.float32) if scale is not None else None
             acc = 0
 
         def weight_gradient():
+            if fused_lin:
+                _require_f32(small, "an fp32 weight gradient")
+                _require_f32(big, "an fp32 weight gradient")
+                pc, pp = spec.perm or (0, 0)
+                with L.timed(tag + " fp32 (fused projection)"):
+                    L.call("glis_linear_wgrad_project", L.ptr(small), L.ptr(big), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm),
+                           L.ptr(dw_buf), L.ptr(ds_buf), n, cout, cin, pc, pp, acc, L.stream())
+                if acc:
+                    _touch_hooks(weight, scale)
+                return
             if graw_stale:
                 graw.zero_()
             if isw is not None:
@@ -929,6 +1050,15 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                 with L.timed(tag + " fp32"):
                     L.call("glis_conv_wgrad", C.byref(g), L.ptr(small), L.ptr(big), L.ptr(graw), L.PREC_FP32,
                            L.stream())
+            hooked = getattr(weight, "_glis_grad_hooks", None) or (scale is not None and
+                                                                   getattr(scale, "_glis_grad_hooks", None))
+            if fork and acc and not hooked and Overlap.defer_projections:
+                # nobody waits for this gradient before the join: its projection joins the network's other ones in
+                # ONE glis_wn_project_multi launch at Overlap.join() (a gradient exchange that fires per parameter
+                # — data parallelism — keeps the per-layer launch so that buckets leave as early as they can)
+                Overlap.queue_projection(graw, wc, sc, pw.norm, pw.out_axis, cout, cin, t, spec.norm_factor, dw_buf,
+                                         ds_buf, acc)
+                return
             L.call("glis_wn_project", L.ptr(graw), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm), pw.out_axis, cout, cin, t,
                    spec.norm_factor, L.ptr(dw_buf), L.ptr(ds_buf), acc, L.stream())
             if acc:
@@ -1328,6 +1458,7 @@ class LISModuleFunction(torch.autograd.Function):
 
 
 LIS_FUSED = os.environ.get("GLIS_LIS_FUSED", "1") != "0"
+FUSED_LINEAR_WGRAD = os.environ.get("GLIS_FUSED_LINEAR_WGRAD", "1") != "0"
 
 
 def lis_supported(code):

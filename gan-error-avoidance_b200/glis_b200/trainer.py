@@ -544,6 +544,56 @@ class RIterTrainer(object):
         return out
 
 
+class RSeparateTrainer(object):
+    """The R-separate trainer's iteration (g_lis/train_r.py:406-436): a reverser trained alone on
+    ``MSE(rev(gen(z)), z)`` against a FROZEN G-LIS, with the frozen D scoring the generated images before and after
+    the round trip through R (two forward-only passes).  One flat RMSprop state (R's)."""
+
+    def __init__(self, gen, rev, dis, lr, r_iterations, alpha=0.9, eps=1e-6, grad_sync=None, ls=False):
+        self.gen, self.rev, self.dis = gen, rev, dis
+        self.lr, self.depth, self.alpha, self.eps, self.ls = lr, r_iterations, alpha, eps, bool(ls)
+        for net in (gen, dis):
+            for p in net.parameters():
+                p.requires_grad_(False)
+        self.rev_flat = FlatParams(rev)
+        self.dropout = _has_dropout(rev)
+        self.grad_sync = grad_sync
+        self._overlapped = hasattr(grad_sync, "register")
+        if self._overlapped:
+            grad_sync.register("rev", self.rev_flat)
+
+    def _score(self, images):
+        logits = dis_logits(self.dis, images)
+        if logits is None:
+            return dis_bce(self.dis, images, [0.0], self.ls)[0]
+        return bce_on_logits(logits, [0.0], self.ls)[0][0]
+
+    def step(self, z):
+        if self.dropout:
+            ops.DropoutClock.tick(z.device)
+        with torch.no_grad():
+            generated, _ = self.gen(z, n_execute_lis_layers=self.depth)
+            stage1 = self._score(generated)
+        self.rev_flat.zero_grad()
+        code_fixed = self.rev(generated)
+        du = torch.empty_like(code_fixed, memory_format=torch.contiguous_format)
+        loss_r = ops.mse_scaled(code_fixed, z, 1.0, du).reshape(())
+        if self._overlapped:
+            self.grad_sync.begin("rev")
+        ops.Overlap.begin()
+        code_fixed.backward(du)
+        ops.Overlap.join()
+        self.rev_flat.rebind_grads()
+        gs = 1.0 if self.grad_sync is None else (self.grad_sync.finish("rev") if self._overlapped
+                                                 else self.grad_sync(self.rev_flat.g, "rev"))
+        self.rev_flat.rmsprop_step(self.lr, self.alpha, self.eps, gs)
+        ops.refresh_packs(self.rev_flat, part="all", side=False)
+        with torch.no_grad():
+            fixed, _ = self.gen(code_fixed.detach(), n_execute_lis_layers=self.depth)
+            stage2 = self._score(fixed)
+        return {"stage1": stage1.detach(), "r": loss_r.detach(), "stage2": stage2.detach()}
+
+
 class GraphedRIter(object):
     """CUDA-graph replay of ``RIterTrainer.step``: one captured graph per ``do_train`` schedule (the sticky rule
     leaves ``1 + r_iterations`` distinct ones), replayed from static inputs ``first_code`` and ``reals[hop]``."""

@@ -106,10 +106,44 @@ int glis_wn_prepare_perm(const float* w, const float* scale, int out_axis, int C
 int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int out_axis, int Cout, int Cin, int T, float c,
                               float* norm, void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo, int perm_c,
                               int perm_p, void* stream);
+/* Everything glis_wn_prepare* / glis_wn_pack_matrix_bf16 do, for a LIST of layers in two launches (all norms, then
+ * all packs): one call per network and parameter update.  Per layer: any subset of the pack pointers may be NULL;
+ * need_norm = 0 reuses the norm already stored in `norm`.  mat_* / matt_* are the E [A][J] / E^T [J][A] matrix packs
+ * of the image-side layers (A = mat_rows, J = T*Cin*Cout / A, in master element order). */
+typedef struct glis_wn_layer {
+  const float* w; const float* scale; float* norm;
+  float* pack_io; float* pack_oi;
+  void* fwd_hi; void* fwd_lo; void* bwd_hi; void* bwd_lo;
+  void* mat_hi; void* mat_lo; void* matt_hi; void* matt_lo;
+  int32_t out_axis, Cout, Cin, T, perm_c, perm_p, mat_rows, need_norm;
+  float c;
+  int32_t reserved;
+} glis_wn_layer_t;
+int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void* stream);
+
 /* Weight gradient of a linear layer, G[row(a)][b] += sum_m dy[m][a] * x[m][b] with dy in the permuted
  * feature order of glis_wn_prepare_perm: row(a) = (a % perm_c)*perm_p + a / perm_c (identity if perm_c == 0). */
 int glis_linear_wgrad(const float* dy, const float* x, float* G, int M, int Ca, int Cb, int perm_c, int perm_p,
                       void* stream);
+
+/* glis_wn_project (below) for a LIST of layers in one launch: the projections of a whole network once all its raw
+ * weight gradients are in. */
+typedef struct glis_wn_proj {
+  const float* G; const float* w; const float* scale; const float* norm;
+  float* dw; float* dscale;
+  int32_t out_axis, Cout, Cin, T, accumulate;
+  float c;
+} glis_wn_proj_t;
+int glis_wn_project_multi(const glis_wn_proj_t* items, int n, void* stream);
+
+/* Weight gradient of a weight-normalised LINEAR layer and the projection below in ONE kernel (the raw gradient
+ * never exists in memory): with G[row(a)][:] = sum_m dy[m][a] x[m][:] (row(a) as in glis_linear_wgrad),
+ * dw[o] (+)= (s/n)(G[o] - w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n  (c = 1).  For batch-sized M and rows of
+ * at most 1024 inputs (glis_linear_wgrad_project_supported): G's initial linear, the LIS linears. */
+int glis_linear_wgrad_project_supported(int M, int Ca, int Cb);
+int glis_linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale, const float* norm,
+                              float* dw, float* dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
+                              void* stream);
 
 /* Backward of the normalisation: given the raw gradient G w.r.t. w_hat
  * (master layout), dw[o] (+)= (s/n)(G[o] - c w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n.
@@ -151,6 +185,13 @@ int glis_conv_tc_ksplit(const glis_geom_t* g);
  * tile rows, tile images, UMMA N, TMEM columns, 64-channel blocks, K split, staged weight rows, pipeline stages,
  * row tiles per image, pixel tiles, channel tiles, tiles, work items, dynamic shared memory bytes}. */
 int glis_conv_tc_plan(const glis_geom_t* g, int plain_out, int* out15);
+/* The plan of the HALO kernel (csrc/tc_conv2.cu: the taps of a stride-parity class share one pixel box with a halo;
+ * 4x4 stride-2 and 3x3 stride-1 layers) when a launch of this geometry takes it, GLIS_E_UNSUPPORTED otherwise
+ * (1x1 products, GLIS_TC_HALO=0): out20 = {tw, th, tn, n_mma, tmem_cols, kblocks, ksplit, a_rows, weight slots,
+ * tiles_h, tiles_x, tiles_co, total_tiles, n_groups, dynamic shared memory bytes, hx, hy, box rows, pixel-slot rows,
+ * tap classes + 1000 * channels per stage (64: 128-byte rows / SWIZZLE_128B, 32: 64-byte rows / SWIZZLE_64B)}.  glis_conv_forward_bf16 uses this kernel whenever it applies; glis_conv_tc_plan keeps describing the
+ * one-box-per-tap kernel of csrc/tc_conv.cu. */
+int glis_conv_tc_halo_plan(const glis_geom_t* g, int plain_out, int* out20);
 
 /* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
  * TMEM, epilogue fused.  x planes [N,Hi,Wi,Ci] bf16, w packs [KH*KW][Co][Ci] bf16.  Outputs

@@ -23,11 +23,11 @@ from .modules import (TPReLU, View, WeightNormalizedConv2d,
                       WeightNormalizedConvTranspose2d, WeightNormalizedLinear)
 from .model import (GeneratorLearnedInputSpace, build_discriminator,
                     build_generator, build_reverser)
-from .step import GLISOracleTrainer, glis_iteration, riter_iteration, rmsprop_update
+from .step import GLISOracleTrainer, glis_iteration, riter_iteration, rmsprop_update, rsep_iteration
 
 __all__ = [
     "TPReLU", "View", "WeightNormalizedConv2d", "WeightNormalizedConvTranspose2d",
     "WeightNormalizedLinear", "GeneratorLearnedInputSpace", "build_discriminator",
     "build_generator", "build_reverser", "GLISOracleTrainer", "glis_iteration",
-    "rmsprop_update", "riter_iteration",
+    "rmsprop_update", "riter_iteration", "rsep_iteration",
 ]

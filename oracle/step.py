@@ -166,3 +166,30 @@ def riter_iteration(gen, rev, dis, gen_state, rev_state, dis_state, first_code, 
         last_images, last_code = generated, code
         out.append(rec)
     return out
+
+
+def rsep_iteration(gen, rev, dis, rev_state, z, lr, depth, alpha=0.9, eps=1e-6, ls=False):
+    """One iteration of the R-separate trainer, restated from ``g_lis/train_r.py:406-436``: a reverser R is trained
+    ALONE to recover the latent code of images a frozen G-LIS generates, and the frozen D scores the images before
+    and after the round trip.
+
+    ``generated = gen(z)`` with ``depth`` LIS modules (:410); stage-1 loss = lossfunc(dis(generated), zeros) without
+    gradients (:413-417); R update on ``MSE(r(generated), z)`` (:420-427 — the reference forgets to keep the
+    result of ``generated.detach()`` (:418), so its backward also walks the frozen generator; no parameter but R's
+    is ever stepped, which is what is restated); stage-2 loss = lossfunc(dis(gen(r(generated))), zeros) (:430-435).
+    Returns {"stage1", "r", "stage2"} as floats."""
+    B = z.size(0)
+    zeros = torch.zeros(B, 1, dtype=z.dtype)
+    lossfunc = adversarial_loss(ls)
+    with torch.no_grad():
+        generated, _ = gen(z, n_execute_lis_layers=depth)
+        stage1 = lossfunc(dis(generated), zeros).item()
+    _zero_fill(rev)
+    code_fixed = rev(generated)
+    loss_r = F.mse_loss(code_fixed, z)
+    loss_r.backward()
+    rmsprop_update(list(rev.parameters()), rev_state, lr, alpha, eps)
+    with torch.no_grad():
+        fixed, _ = gen(code_fixed.detach(), n_execute_lis_layers=depth)
+        stage2 = lossfunc(dis(fixed), zeros).item()
+    return {"stage1": stage1, "r": loss_r.item(), "stage2": stage2}

@@ -27,6 +27,8 @@ What is written (all float64, tiny shapes, ``.npz``):
                       (including a skipped module, exercising the zero-fill rule);
 * ``glis_steps_ls.npz`` – two such iterations with ``--ls`` (``lossfunc = nn.MSELoss()`` on D's sigmoid
                       output, g_lis/main.py:308-311);
+* ``rsep_steps.npz``  – two iterations of the R-separate trainer (g_lis/train_r.py:406-436): reverser trained alone
+                      against reference-built frozen G-LIS + D;
 * ``riter_steps.npz`` – two outer iterations of the R-iterative trainer (r_iterative/main.py:428-535) on
                       reference-built plain G + reverser R + D with three stock RMSprops: all hops trained,
                       then the schedule [skip, train, train].
@@ -410,7 +412,42 @@ def main():
                 for k, v in undot(net.state_dict()).items():
                     put(steps, pre + "/" + tag, **{k: v})
         np.savez_compressed(os.path.join(OUT, "riter_steps.npz"), **steps)
-    for f in ("modules.npz", "models.npz", "glis_steps.npz", "glis_steps_ls.npz", "riter_steps.npz"):
+
+        # ---- R-separate iterations (g_lis/train_r.py:406-436; nets :205-222)
+        steps = {}
+        torch.manual_seed(10)
+        g = ref.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis_layers=n_lis, upscaling="fractional").double()
+        rv = ref.build_reverser(W, H, nf // 2, nl, code, "weight", 0).double()
+        d = ref.build_discriminator(W, H, nf, nl, "weight", 0).double()
+        for net in (g, rv, d):
+            net.train()
+        for p in list(g.parameters()) + list(d.parameters()):
+            p.requires_grad = False
+        r_opt = torch.optim.RMSprop(rv.parameters(), lr=lr, eps=1e-6, alpha=0.9)
+        lossfunc, lossfunc_r = nn.BCELoss(), nn.MSELoss()
+        for tag, net in (("g", g), ("r", rv), ("d", d)):
+            for k, v in undot(net.state_dict()).items():
+                put(steps, "init/" + tag, **{k: v})
+        put(steps, "cfg", W=W, H=H, B=B, code=code, nf=nf, nl=nl, n_lis=n_lis, lr=lr, iters=2)
+        for it in range(2):
+            pre = "it%d" % it
+            z = torch.randn(B, code, dtype=torch.float64, generator=gen)
+            generated, _ = g(z, n_execute_lis_layers=n_lis)
+            with torch.no_grad():
+                l1 = lossfunc(d(generated.detach()), zeros)
+            rv.zero_grad(set_to_none=False)
+            code_fixed = rv(generated.detach())
+            loss_r = lossfunc_r(code_fixed, z)
+            loss_r.backward()
+            r_opt.step()
+            with torch.no_grad():
+                fixed, _ = g(code_fixed.detach(), n_execute_lis_layers=n_lis)
+                l2 = lossfunc(d(fixed), zeros)
+            put(steps, pre, z=z, stage1=l1.item(), r=loss_r.item(), stage2=l2.item())
+            for k, v in undot(rv.state_dict()).items():
+                put(steps, pre + "/r", **{k: v})
+        np.savez_compressed(os.path.join(OUT, "rsep_steps.npz"), **steps)
+    for f in ("modules.npz", "models.npz", "glis_steps.npz", "glis_steps_ls.npz", "riter_steps.npz", "rsep_steps.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

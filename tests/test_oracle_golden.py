@@ -178,3 +178,24 @@ def test_r_iterative_iterations_match_reference(golden_dir):
         for tag, net in (("g", gen), ("r", rev), ("d", dis)):
             for k, v in net.state_dict().items():
                 np.testing.assert_allclose(v.numpy(), g[tag + "/" + k], err_msg="it%d %s %s" % (it, tag, k), **TOL)
+
+
+def test_r_separate_iterations_match_reference(golden_dir):
+    """oracle.rsep_iteration against two iterations of g_lis/train_r.py:406-436 run on the reference's builders."""
+    from oracle.step import rsep_iteration
+    s = _load(golden_dir, "rsep_steps.npz")
+    cfg = _group(s, "cfg")
+    W, H, B, code, nf, nl, n_lis = (int(cfg[k]) for k in ("W", "H", "B", "code", "nf", "nl", "n_lis"))
+    gen = oracle.GeneratorLearnedInputSpace(W, H, nf, nl, code, "weight", n_lis, "fractional").double()
+    rev = oracle.build_reverser(W, H, nf // 2, nl, code, "weight", 0).double()
+    dis = oracle.build_discriminator(W, H, nf, nl, "weight", 0).double()
+    for tag, net in (("g", gen), ("r", rev), ("d", dis)):
+        net.load_state_dict({k: _t(v) for k, v in _group(s, "init/" + tag).items()})
+    state = {}
+    for it in range(int(cfg["iters"])):
+        g = _group(s, "it%d" % it)
+        out = rsep_iteration(gen, rev, dis, state, _t(g["z"]), float(cfg["lr"]), n_lis)
+        for k in ("stage1", "r", "stage2"):
+            np.testing.assert_allclose(out[k], g[k], err_msg="it%d %s" % (it, k), **TOL)
+        for k, v in rev.state_dict().items():
+            np.testing.assert_allclose(v.numpy(), g["r/" + k], err_msg="it%d %s" % (it, k), **TOL)

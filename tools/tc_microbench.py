@@ -43,7 +43,34 @@ def main():
         for cl in (sys.argv[1:] or ["1", "2", "4"]):
             dbg = "0"
             os.environ["GLIS_TC_DEBUG"] = dbg
-            if cl.startswith("k"):      # "k1", "k8": upper bound on the K split, no cluster
+            os.environ.pop("GLIS_TC_HALO", None)
+            os.environ.pop("GLIS_T2_DEBUG", None)
+            os.environ.pop("GLIS_TC_HALO_BK", None)
+            os.environ.pop("GLIS_TC_HALO_MINW", None)
+            if cl.startswith("b"):      # "b32" / "b64": halo kernel on every map width with that many channels per stage
+                os.environ["GLIS_TC_HALO_BK"] = cl[1:]
+                os.environ["GLIS_TC_HALO_MINW"] = "1"
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ.pop("GLIS_TC_KSPLIT", None)
+                cl = "x"
+            if cl.startswith("c"):      # "c2d6": tc_conv.cu, cluster 2 (weight multicast), debug bits 6 (weight loads only)
+                os.environ["GLIS_TC_HALO"] = "0"
+                os.environ["GLIS_TC_CLUSTER"], os.environ["GLIS_TC_DEBUG"] = cl[1:].split("d")
+                os.environ["GLIS_TC_KSPLIT"] = "1"
+            elif cl.startswith("t"):      # "t1" ...: halo kernel with GLIS_T2_DEBUG bits
+                os.environ["GLIS_T2_DEBUG"] = cl[1:]
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ.pop("GLIS_TC_KSPLIT", None)
+            elif cl.startswith("d"):      # "d1" / "d2" / "d4" / "d6": tc_conv.cu with debug bits (1 no stores, 2 no MMA, 4 no pixel loads)
+                os.environ["GLIS_TC_HALO"] = "0"
+                os.environ["GLIS_TC_DEBUG"] = cl[1:]
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ.pop("GLIS_TC_KSPLIT", None)
+            elif cl.startswith("h"):      # "h0" / "h1": one box per tap (tc_conv.cu) / halo kernel (tc_conv2.cu)
+                os.environ["GLIS_TC_HALO"] = cl[1:]
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ.pop("GLIS_TC_KSPLIT", None)
+            elif cl.startswith("k"):      # "k1", "k8": upper bound on the K split, no cluster
                 os.environ["GLIS_TC_CLUSTER"] = "1"
                 os.environ["GLIS_TC_KSPLIT"] = cl[1:]
             else:

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-k-step timeline of CTA 0 of the tcgen05 conv kernel (GLIS_TC_TRACE)."""
+"""Timeline of CTA 0 of the halo kernel (csrc/tc_conv2.cu, GLIS_TC_TRACE): when each weight tile / pixel box was
+requested and when the MMA warp saw it."""
 import ctypes as C
 import os
 import sys
@@ -11,9 +12,8 @@ from glis_b200 import _lib as L, ops
 
 dev = "cuda"
 spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
-for name, rel, n, hi, wi, ci, ho, wo, co in [("D1 2B", L.CONV, 128, 40, 40, 64, 20, 20, 128), ("D1", L.CONV, 64, 40, 40, 64, 20, 20, 128),
-                                              ("G1", L.TCONV, 64, 20, 20, 128, 40, 40, 64),
-                                              ("D3", L.CONV, 64, 10, 10, 256, 5, 5, 512)]:
+for name, rel, n, hi, wi, ci, ho, wo, co in [("D1 2B", L.CONV, 128, 40, 40, 64, 20, 20, 128),
+                                              ("D2 2B", L.CONV, 128, 20, 20, 128, 10, 10, 256)]:
     g = spec.geom(rel, n, hi, wi, ci, ho, wo, co)
     x = torch.randn(n, hi, wi, ci, device=dev)
     xh, xl = ops.split_bf16(x)
@@ -21,7 +21,7 @@ for name, rel, n, hi, wi, ci, ho, wo, co in [("D1 2B", L.CONV, 128, 40, 40, 64, 
     wh, wl = ops.split_bf16(w)
     out = torch.empty(n, ho, wo, co, device=dev)
     ep = L.Epilogue(None, 0, None, None, None)
-    trace = torch.zeros(1088, dtype=torch.int64, device=dev)
+    trace = torch.zeros(1280, dtype=torch.int64, device=dev)
     def run():
         L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xh), L.ptr16(xl), L.ptr16(wh), L.ptr16(wl),
                C.byref(ep), L.ptr(out), None, None, L.PREC_BF16X3, L.stream())
@@ -33,11 +33,11 @@ for name, rel, n, hi, wi, ci, ho, wo, co in [("D1 2B", L.CONV, 128, 40, 40, 64, 
     torch.cuda.synchronize()
     del os.environ["GLIS_TC_TRACE"]
     t = trace.cpu().tolist()
-    t0 = t[1087]
-    prod = [v - t0 for v in t[:512] if v]
-    mma = [v - t0 for v in t[512:1024] if v]
-    epi = [v - t0 for v in t[1024:1087] if v]
-    print(name, "k-steps", len(prod))
-    print("  producer issue (ns):", prod[:40])
-    print("  mma full-seen  (ns):", mma[:40])
-    print("  epilogue start/end (ns):", epi)
+    t0 = t[1216]
+    rel_ = lambda a: [v - t0 for v in a if v]
+    print(name)
+    print("  W issue  :", rel_(t[0:512])[:40])
+    print("  W seen   :", rel_(t[512:1024])[:40])
+    print("  X issue  :", rel_(t[1024:1088])[:12])
+    print("  X seen   :", rel_(t[1088:1152])[:12])
+    print("  epilogue :", rel_(t[1152:1216]))
