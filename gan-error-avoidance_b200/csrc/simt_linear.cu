@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(LP_NT)
 linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ scale, const float* __restrict__ norm, float* __restrict__ dw,
                             float* __restrict__ dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
-                            int rows_per_block) {
+                            int rows_per_block, int row_begin, int row_count) {
   extern __shared__ __align__(16) float lp_xs[];        // [M][Cb]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   {
@@ -389,7 +389,9 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
     }
   }
   __syncthreads();
-  const int a_beg = blockIdx.x * rows_per_block, a_end = min(Ca, a_beg + rows_per_block);
+  // rows are MASTER rows o in [row_begin, row_begin + row_count): dw is written contiguously; the matching column of
+  // dy is a(o) = (o % P) * C + o / P under the NHWC row permutation of glis_wn_prepare_perm
+  const int a_beg = row_begin + blockIdx.x * rows_per_block, a_end = min(row_begin + row_count, a_beg + rows_per_block);
   for (int a0 = a_beg + wid * LP_ROWS; a0 < a_end; a0 += (LP_NT / 32) * LP_ROWS) {
     float acc[LP_ROWS][PER];
 #pragma unroll
@@ -400,8 +402,11 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
     for (int m0 = 0; m0 < M; m0 += 32) {
       float dmine[LP_ROWS];
 #pragma unroll
-      for (int r = 0; r < LP_ROWS; ++r)
-        dmine[r] = (m0 + lane < M && a0 + r < a_end) ? __ldg(dy + (size_t)(m0 + lane) * Ca + a0 + r) : 0.f;
+      for (int r = 0; r < LP_ROWS; ++r) {
+        const int o = a0 + r;
+        const int a = perm_c ? (o % perm_p) * perm_c + o / perm_p : o;
+        dmine[r] = (m0 + lane < M && o < a_end) ? __ldg(dy + (size_t)(m0 + lane) * Ca + a) : 0.f;
+      }
       const int mc = min(32, M - m0);
       for (int mm = 0; mm < mc; ++mm) {
         float d[LP_ROWS];
@@ -419,9 +424,8 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
     }
 #pragma unroll
     for (int r = 0; r < LP_ROWS; ++r) {
-      const int a = a0 + r;
-      if (a >= a_end) break;                                             // (uniform across the warp)
-      const int o = perm_c ? (a % perm_c) * perm_p + a / perm_c : a;     // master row of pack row a
+      const int o = a0 + r;
+      if (o >= a_end) break;                                             // (uniform across the warp)
       float wv[PER], dot = 0.f;
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
@@ -452,15 +456,18 @@ int linear_wgrad_project_supported(int M, int Ca, int Cb) {
 
 int linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale, const float* norm,
                          float* dw, float* dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
-                         cudaStream_t st) {
+                         int row_begin, int row_count, cudaStream_t st) {
   GLIS_REQUIRE(linear_wgrad_project_supported(M, Ca, Cb), GLIS_E_UNSUPPORTED,
                "glis_linear_wgrad_project: batch %d x %d inputs does not fit the fused kernel", M, Cb);
   const size_t smem = (size_t)M * Cb * sizeof(float);
   // enough blocks to give every SM a few, each with >= 8 rows (one per warp) so that staging x pays
-  int rows_per_block = (Ca + 148 * 2 - 1) / (148 * 2);
+  GLIS_REQUIRE(row_begin >= 0 && row_count >= 0 && row_begin + row_count <= Ca, GLIS_E_BADARG,
+               "glis_linear_wgrad_project: rows [%d, %d) of %d", row_begin, row_begin + row_count, Ca);
+  if (row_count == 0) return GLIS_OK;
+  int rows_per_block = (row_count + 148 * 2 - 1) / (148 * 2);
   rows_per_block = (rows_per_block + 31) / 32 * 32;       // 8 warps x LP_ROWS rows per pass
   if (rows_per_block < 32) rows_per_block = 32;
-  const int blocks = (Ca + rows_per_block - 1) / rows_per_block;
+  const int blocks = (row_count + rows_per_block - 1) / rows_per_block;
 #define LP_LAUNCH(PER)                                                                                              \
   do {                                                                                                              \
     static bool attr_set = false;                                                                                   \
@@ -471,7 +478,8 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
       attr_set = true;                                                                                              \
     }                                                                                                               \
     linear_wgrad_project_kernel<PER><<<blocks, LP_NT, smem, st>>>(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
-                                                                  perm_p, accumulate, rows_per_block);             \
+                                                                  perm_p, accumulate, rows_per_block, row_begin,   \
+                                                                  row_count);                                      \
   } while (0)
   if (Cb <= 128) LP_LAUNCH(4);
   else if (Cb <= 256) LP_LAUNCH(8);
@@ -503,12 +511,12 @@ extern "C" int glis_linear_wgrad_project_supported(int M, int Ca, int Cb) {
 
 extern "C" int glis_linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale,
                                          const float* norm, float* dw, float* dscale, int M, int Ca, int Cb, int perm_c,
-                                         int perm_p, int accumulate, void* stream) {
+                                         int perm_p, int accumulate, int row_begin, int row_count, void* stream) {
   using namespace glis;
   GLIS_REQUIRE(dy && x && w && norm && dw && M > 0 && Ca > 0 && Cb > 0, GLIS_E_BADARG,
                "glis_linear_wgrad_project: bad arguments");
   GLIS_REQUIRE((perm_c == 0 && perm_p == 0) || (perm_c > 0 && perm_p > 0 && (int64_t)perm_c * perm_p == Ca), GLIS_E_BADARG,
                "glis_linear_wgrad_project: bad row permutation (C=%d P=%d for %d rows)", perm_c, perm_p, Ca);
-  return linear_wgrad_project(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, perm_p, accumulate,
-                              (cudaStream_t)stream);
+  return linear_wgrad_project(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, perm_p, accumulate, row_begin,
+                              row_count, (cudaStream_t)stream);
 }

@@ -84,7 +84,7 @@ SIGNATURES = {
     "glis_wn_prepare_bf16_perm": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "glis_linear_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "glis_linear_wgrad_project_supported": [_i, _i, _i],
-    "glis_linear_wgrad_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "glis_linear_wgrad_project": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "glis_unfold4x4s2_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "glis_fold4x4s2": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "glis_wn_pack_matrix_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -84,37 +84,103 @@ def plan_param_buckets(offsets, sizes, total, bucket_elems):
     return buckets
 
 
+def plan_unit_buckets(units, total, bucket_elems):
+    """As plan_param_buckets over UNITS — (start, length) pieces of the flat buffer in ascending order, a whole
+    parameter or one row chunk of a large one: walk them from the last (first ready) to the first, closing a bucket
+    once it holds at least ``bucket_elems`` elements.  Returns [(offset, length, [unit indices])]; the buckets tile
+    [0, total)."""
+    buckets, members, end = [], [], total
+    for u in range(len(units) - 1, -1, -1):
+        members.append(u)
+        if end - units[u][0] >= bucket_elems or u == 0:
+            start = units[u][0] if u > 0 else 0
+            buckets.append((start, end - start, members))
+            members, end = [], start
+    return buckets
+
+
+def split_rows(rows, row_elems, chunk_elems, max_parts=8):
+    """[(row_begin, row_count)] cutting a (rows x row_elems) matrix into at most ``max_parts`` chunks of about
+    ``chunk_elems`` elements (whole rows, multiples of 32 rows: the fused linear weight-gradient kernel works in
+    32-row blocks)."""
+    parts = max(1, min(max_parts, (rows * row_elems) // max(1, chunk_elems)))
+    per = -(-rows // parts)
+    per = -(-per // 32) * 32
+    out, r = [], 0
+    while r < rows:
+        n = min(per, rows - r)
+        out.append((r, n))
+        r += n
+    return out
+
+
 class OverlappedGradSync(object):
     """Bucketed gradient all-reduce launched from a side stream WHILE backward is still running.
 
     One instance serves several flat buffers (``register(tag, flat)``).  Every parameter gets a
     post-accumulate-grad hook; when the last parameter of a bucket has its gradient, the main
     stream records an event, the side stream waits for it and issues that bucket's all-reduce, so
-    the exchange of the late layers overlaps the backward of the early ones.  ``finish(tag)``
+    the exchange of the late layers overlaps the backward of the early ones.  A LARGE 2-D parameter
+    (a linear weight of ``split_mb`` or more: the generator's initial linear, 13 MB at config 2, whose gradient
+    is the LAST one backward produces) is cut into row chunks that are buckets of their own: the operator
+    that makes the gradient produces it chunk by chunk (``_glis_grad_parts``, ops._layer_backward) and the
+    all-reduce of chunk i runs under the kernel of chunk i+1.  ``finish(tag)``
     flushes the buckets that never completed (a LIS module skipped by the stochastic depth keeps
     its zero-filled gradient — identically on every rank, so the flush order is the same
     everywhere), makes the main stream wait for the side stream and returns 1/world for the
     fused RMSprop.  Everything is stream-ordered, so the whole thing can sit inside a CUDA graph.
     """
 
-    def __init__(self, world, bucket_mb=None, group=None):
+    def __init__(self, world, bucket_mb=None, group=None, split_mb=None):
         self.world, self.group = world, group
         if bucket_mb is None:
             bucket_mb = float(os.environ.get("GLIS_DP_BUCKET_MB", "2"))
+        if split_mb is None:
+            # 0 = off (default).  Measured on 8 B200 at config 2 (tools/dp_bench.sh): cutting the 13 MB gradient of
+            # G's initial linear into 4-6 chunks is SLOWER (2.19 vs 2.12 ms): its kernel takes ~10 us, the exchange
+            # ~100 us, so there is nothing to pipeline with — what is exposed is the all-reduce of the LAST gradient
+            # of backward itself, and the optimizer needs it whole.
+            split_mb = float(os.environ.get("GLIS_DP_SPLIT_MB", "0"))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.split_elems = int(split_mb * (1 << 20) / 4)
         self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
         self.sets = {}
         self.bytes_reduced = 0
 
     def register(self, tag, flat):
-        plan = plan_param_buckets(flat.offsets, [p.numel() for p in flat.params], flat.numel, self.bucket_elems)
+        # units: whole parameters, or the row chunks of a large linear weight
+        units, unit_of = [], []          # (start, length); per parameter: its unit indices, in part order
+        for idx, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+            parts = None
+            if self.split_elems > 0 and p.dim() == 2 and p.numel() >= self.split_elems and self.world > 1:
+                parts = split_rows(p.shape[0], p.shape[1], max(self.split_elems // 4, self.bucket_elems))
+                if len(parts) < 2:
+                    parts = None
+            if parts is None:
+                nxt = flat.offsets[idx + 1] if idx + 1 < len(flat.offsets) else flat.numel
+                unit_of.append([len(units)])
+                units.append((off, nxt - off))
+            else:
+                p._glis_grad_parts = parts
+                mine = []
+                for k, (r0, rc) in enumerate(parts):
+                    start = off + r0 * p.shape[1]
+                    length = rc * p.shape[1]
+                    if k == len(parts) - 1:      # alignment padding rides along with the last chunk
+                        nxt = flat.offsets[idx + 1] if idx + 1 < len(flat.offsets) else flat.numel
+                        length = nxt - start
+                    mine.append(len(units))
+                    units.append((start, length))
+                unit_of.append(mine)
+        plan = plan_unit_buckets(units, flat.numel, self.bucket_elems)
         buckets = [(o, n) for o, n, _ in plan]
-        owner = [None] * len(flat.params)
+        owner = [None] * len(units)
         for b, (_, _, members) in enumerate(plan):
-            for i in members:
-                owner[i] = b
-        st = {"flat": flat, "buckets": buckets, "owner": owner, "need": [len(m) for _, _, m in plan],
-              "left": [0] * len(buckets), "sent": [False] * len(buckets), "armed": False, "seen": set()}
+            for u in members:
+                owner[u] = b
+        st = {"flat": flat, "buckets": buckets, "owner": owner, "unit_of": unit_of,
+              "need": [len(m) for _, _, m in plan], "left": [0] * len(buckets), "sent": [False] * len(buckets),
+              "armed": False, "seen": set()}
         self.sets[tag] = st
         for idx, p in enumerate(flat.params):
             hook = self._make_hook(st, idx)
@@ -125,20 +191,23 @@ class OverlappedGradSync(object):
             hooks.append(hook)
 
     def _make_hook(self, st, idx):
-        def hook(_param):
+        def hook(_param, part=None):
             if not st["armed"] or self.world <= 1:
                 return
-            # A parameter reports ONCE per backward pass.  It may be announced twice — by the operator
+            # A unit reports ONCE per backward pass.  A parameter may be announced twice — by the operator
             # that added its gradient in place (ops._touch_hooks) and again by autograd, which runs the
             # post-accumulate hooks of every parameter input of a Function even when the Function
             # returned None for it — and either call comes after the gradient work was enqueued.
-            if idx in st["seen"]:
-                return
-            st["seen"].add(idx)
-            b = st["owner"][idx]
-            st["left"][b] -= 1
-            if st["left"][b] == 0 and not st["sent"][b]:
-                self._send(st, b)
+            # ``part``: one row chunk of a split parameter; None: the whole parameter (every chunk not yet seen).
+            mine = st["unit_of"][idx]
+            for u in (mine if part is None else [mine[part]]):
+                if u in st["seen"]:
+                    continue
+                st["seen"].add(u)
+                b = st["owner"][u]
+                st["left"][b] -= 1
+                if st["left"][b] == 0 and not st["sent"][b]:
+                    self._send(st, b)
         return hook
 
     def _send(self, st, b):

@@ -787,6 +787,12 @@ def _touch_hooks(*params):
             hook(p)
 
 
+def _touch_hooks_part(p, part):
+    """Announce that rows chunk ``part`` of ``p``'s gradient is complete (see dp.OverlappedGradSync)."""
+    for hook in getattr(p, "_glis_grad_hooks", ()):
+        hook(p, part)
+
+
 class Overlap(object):
     """Weight-gradient work (wgrad kernel + weight-norm projection) on a SIDE stream.
 
@@ -1021,9 +1027,16 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                 _require_f32(small, "an fp32 weight gradient")
                 _require_f32(big, "an fp32 weight gradient")
                 pc, pp = spec.perm or (0, 0)
-                with L.timed(tag + " fp32 (fused projection)"):
-                    L.call("glis_linear_wgrad_project", L.ptr(small), L.ptr(big), L.ptr(wc), L.ptr(sc), L.ptr(pw.norm),
-                           L.ptr(dw_buf), L.ptr(ds_buf), n, cout, cin, pc, pp, acc, L.stream())
+                # a large gradient that a data-parallel exchange wants in pieces (dp.OverlappedGradSync marks the
+                # parameter): one launch per row chunk, each announced as soon as it is enqueued
+                parts = getattr(weight, "_glis_grad_parts", None) if acc else None
+                for k, (r0, rc) in enumerate(parts or [(0, cout)]):
+                    with L.timed(tag + " fp32 (fused projection)"):
+                        L.call("glis_linear_wgrad_project", L.ptr(small), L.ptr(big), L.ptr(wc), L.ptr(sc),
+                               L.ptr(pw.norm), L.ptr(dw_buf), L.ptr(ds_buf), n, cout, cin, pc, pp, acc, r0, rc,
+                               L.stream())
+                    if parts:
+                        _touch_hooks_part(weight, k)
                 if acc:
                     _touch_hooks(weight, scale)
                 return

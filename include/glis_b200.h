@@ -139,11 +139,13 @@ int glis_wn_project_multi(const glis_wn_proj_t* items, int n, void* stream);
 /* Weight gradient of a weight-normalised LINEAR layer and the projection below in ONE kernel (the raw gradient
  * never exists in memory): with G[row(a)][:] = sum_m dy[m][a] x[m][:] (row(a) as in glis_linear_wgrad),
  * dw[o] (+)= (s/n)(G[o] - w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n  (c = 1).  For batch-sized M and rows of
- * at most 1024 inputs (glis_linear_wgrad_project_supported): G's initial linear, the LIS linears. */
+ * at most 1024 inputs (glis_linear_wgrad_project_supported): G's initial linear, the LIS linears.  Only master rows
+ * [row_begin, row_begin + row_count) are produced: a large layer's gradient can be made — and, under data
+ * parallelism, exchanged — in row chunks. */
 int glis_linear_wgrad_project_supported(int M, int Ca, int Cb);
 int glis_linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale, const float* norm,
                               float* dw, float* dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
-                              void* stream);
+                              int row_begin, int row_count, void* stream);
 
 /* Backward of the normalisation: given the raw gradient G w.r.t. w_hat
  * (master layout), dw[o] (+)= (s/n)(G[o] - c w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n.

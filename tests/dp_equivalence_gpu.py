@@ -39,7 +39,7 @@ def main():
     depths = [(2, 1), (0, 2), (2, 1)]
     for use_graph in (False, True):
         g, d = build(dev)
-        tr = GLISTrainer(g, d, lr=lr, grad_sync=dp.OverlappedGradSync(world, bucket_mb=0.05))
+        tr = GLISTrainer(g, d, lr=lr, grad_sync=dp.OverlappedGradSync(world, bucket_mb=0.05, split_mb=0.05))
         stepper = GraphedStep(tr, B, 32, 32, code, dev, warmup=1) if use_graph else tr
         sl = slice(rank * B, (rank + 1) * B)
         losses = []

@@ -112,6 +112,7 @@ def test_overlapped_sync_counts_each_parameter_once(monkeypatch):
     st = sync.sets["net"]
     assert [sorted(m) for m in ([i for i, o in enumerate(st["owner"]) if o == b] for b in range(len(st["buckets"])))] \
         == [[4, 5], [2, 3], [0, 1]]
+    assert st["unit_of"] == [[0], [1], [2], [3], [4], [5]]         # small parameters: one unit each
     sync.begin("net")
     hooks = [p._glis_grad_hooks[0] for p in flat.params]
     for idx in (5, 5, 5):                 # the same parameter announced three times: still one report
@@ -129,3 +130,46 @@ def test_overlapped_sync_counts_each_parameter_once(monkeypatch):
         hooks[idx](flat.params[idx])
         hooks[idx](flat.params[idx])
     assert sent == [0, 1, 2]
+
+
+def test_large_linear_weight_is_exchanged_in_row_chunks(monkeypatch):
+    """The generator's initial linear (12800 x 256, the LAST gradient backward produces) is cut into row chunks that
+    are buckets of their own: each chunk leaves as soon as the operator announces it, the whole-parameter
+    announcement (autograd's hook, or an operator that does not work in chunks) completes whatever is left."""
+    from glis_b200 import dp
+
+    assert dp.split_rows(12800, 256, 800_000) == [(0, 3200), (3200, 3200), (6400, 3200), (9600, 3200)]
+    assert dp.split_rows(100, 10, 10 ** 9) == [(0, 100)]
+    parts = dp.split_rows(1000, 256, 40_000)
+    assert sum(n for _, n in parts) == 1000 and all(r % 32 == 0 for r, _ in parts) and len(parts) <= 8
+
+    class Flat(object):
+        def __init__(self):
+            self.params = [torch.nn.Parameter(torch.zeros(16)), torch.nn.Parameter(torch.zeros(12800, 256)),
+                           torch.nn.Parameter(torch.zeros(512))]
+            self.offsets = [0, 16, 16 + 12800 * 256]
+            self.numel = 16 + 12800 * 256 + 512
+            self.g = torch.zeros(self.numel)
+
+    flat = Flat()
+    sync = dp.OverlappedGradSync(world=8, bucket_mb=2, split_mb=6)      # (off by default: GLIS_DP_SPLIT_MB)
+    sent = []
+    monkeypatch.setattr(sync, "_send", lambda st, b: (sent.append(st["buckets"][b]), st["sent"].__setitem__(b, True)))
+    sync.register("gen", flat)
+    st = sync.sets["gen"]
+    big = flat.params[1]
+    parts = big._glis_grad_parts
+    assert parts == dp.split_rows(12800, 256, 2 * (1 << 20) // 4) and 4 <= len(parts) <= 8
+    assert len(st["unit_of"][1]) == len(parts) and sum(n for _, n in st["buckets"]) == flat.numel
+    sync.begin("gen")
+    hook = big._glis_grad_hooks[0]
+    flat.params[2]._glis_grad_hooks[0](flat.params[2])          # the small trailing parameter first
+    last = len(parts) - 1
+    hook(big, last)                                             # last chunk ready: its bucket (with the tail) leaves
+    assert sent == [(16 + parts[last][0] * 256, parts[last][1] * 256 + 512)]
+    hook(big, 1); hook(big, 1)
+    assert sent[-1] == (16 + parts[1][0] * 256, parts[1][1] * 256) and len(sent) == 2
+    hook(big)                                                   # whole-parameter announcement: every other chunk
+    assert len(sent) == len(parts)
+    flat.params[0]._glis_grad_hooks[0](flat.params[0])          # (the 16-element head shares chunk 0's bucket)
+    assert len(set(sent)) == len(sent) and sum(n for _, n in sent) == flat.numel
