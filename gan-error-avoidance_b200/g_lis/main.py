@@ -239,7 +239,7 @@ def _reconstruction_loop(gen, targets, opt):
     total = 0.0
     for i in range(0, targets.size(0), opt.batch_size):
         tgt = targets[i:i + opt.batch_size]
-        code = torch.zeros(tgt.size(0), opt.code_size, device=tgt.device, requires_grad=True)
+        code = torch.zeros(tgt.size(0), opt.code_size, device=tgt.device, dtype=tgt.dtype, requires_grad=True)
         test_opt = torch.optim.RMSprop([code], lr=opt.test_lr, eps=1e-6, alpha=0.9)
         for _ in range(opt.test_steps):
             out, _ = gen(code)

@@ -1537,3 +1537,76 @@ def test_cli_train_r(tmp_path, precision):
         assert os.path.exists(os.path.join(arch, f)), f
     assert os.path.exists(os.path.join(out, "samples_both", "sample_2_both.jpg"))
     assert torch.load(os.path.join(arch, "4_state.pt"), weights_only=False)["current_iter"] == 4
+
+
+# ---------------------------------------------------------------- forward-only consumers
+def _load_cli(name, *parts):
+    import importlib.util
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, *parts))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_reconstruction_test_matches_oracle():
+    """`test()` of g_lis/main.py:398-453 — held-out images embedded by 50 RMSprop steps on the latent code with G
+    frozen: G forward + data-gradient-only backward.  The same function on the product's generator (GPU) and on
+    the oracle's (CPU, fp64) must follow the same trajectory."""
+    import argparse
+    pm, _ = _product()
+    m = _load_cli("glis_main_f3", "g_lis", "main.py")
+    torch.manual_seed(101)
+    og = oracle.GeneratorLearnedInputSpace(32, 32, 16, 3, 32, "weight", 2, "fractional")
+    pg = pm.GeneratorLearnedInputSpace(32, 32, 16, 3, 32, "weight", 2, "fractional")
+    copy_params(pg, og)
+    targets = torch.rand(6, 3, 32, 32)
+    opt = argparse.Namespace(batch_size=4, code_size=32, test_lr=0.01, test_steps=8)
+    want = m.reconstruction_test(og.double(), targets.double(), opt)
+    got = m.reconstruction_test(pg.to(DEV), targets.to(DEV), opt)
+    assert abs(got - want) <= 1e-3 * abs(want), (got, want)
+    assert all(p.requires_grad for p in pg.parameters()) and pg.training
+
+
+def test_samplers_match_oracle(tmp_path):
+    """g_lis/sample_images.py: image grids per LIS depth (with an R-separate repair), interpolations, perturbations
+    and the embedding of given images — the product's generator / reverser against the oracle's through the SAME
+    sampler functions (uint8 images: at most one grey level apart; embedded codes: 1e-3), and the command line."""
+    pm, _ = _product()
+    S = _load_cli("glis_sample_images", "g_lis", "sample_images.py")
+    torch.manual_seed(102)
+    og = oracle.GeneratorLearnedInputSpace(32, 32, 16, 3, 32, "weight", 2, "fractional").eval()
+    orv = oracle.build_reverser(32, 32, 8, 3, 32, "weight", 0).eval()
+    pg = pm.GeneratorLearnedInputSpace(32, 32, 16, 3, 32, "weight", 2, "fractional").eval()
+    prv = pm.build_reverser(32, 32, 8, 3, 32, "weight", 0).eval()
+    copy_params(pg, og); copy_params(prv, orv)
+    pg, prv = pg.to(DEV), prv.to(DEV)
+    code = torch.randn(10, 32)
+
+    def close(a, b):
+        d = (a.cpu().int() - b.cpu().int()).abs()
+        return d.max().item() <= 1 and (d > 0).float().mean().item() < 0.02      # rounding to grey levels
+    for depth in (0, 1, 2):
+        a, af = S.generate_images(pg, prv, code.to(DEV), depth, 4)
+        b, bf = S.generate_images(og, orv, code, depth, 4)
+        assert a.shape == (10, 32, 32, 3) and close(a, b) and close(af, bf), depth
+        assert close(S.generate_interpolations(pg, code[0].to(DEV), code[1].to(DEV), 8, depth),
+                     S.generate_interpolations(og, code[0], code[1], 8, depth))
+        assert close(S.generate_perturbations(pg, code[2].to(DEV), 7, 1.0, 9, depth),
+                     S.generate_perturbations(og, code[2], 7, 1.0, 9, depth))
+    real = torch.rand(3, 3, 32, 32)
+    ca = S.embed_real_images(pg, prv, real.to(DEV), lr=1e-2, test_steps=6)
+    cb = S.embed_real_images(og, orv, real, lr=1e-2, test_steps=6)
+    # (Adam's step is lr * m / (sqrt(v) + 1e-8): sign-like where |g| is tiny, so rounding-level gradient differences
+    #  move single elements by up to lr per step; the codes agree to a few 1e-3 of their scale, not to 1e-6)
+    assert rel_err(ca, cb) <= 2e-2 and rel_l2(ca, cb) <= 5e-3
+    gp, rp = str(tmp_path / "g.pt"), str(tmp_path / "r.pt")
+    torch.save(pg.state_dict(), gp); torch.save(prv.state_dict(), rp); torch.save(real, str(tmp_path / "real.pt"))
+    out = str(tmp_path / "samples")
+    S.main(["--image_size", "32", "--nfeature", "16", "--code_size", "32", "--norm", "weight", "--r_iterations", "2",
+            "--load_path_g", gp, "--load_path_r", rp, "--save_path", out, "--rounds", "1", "--with_real_images",
+            "--real_images", str(tmp_path / "real.pt"), "--embed_steps", "3"])
+    for f in ("sampled_images_r2/r2_full_0000.jpg", "sampled_images_rsep_r1_both/rsep_r1_chain_full_0000.jpg",
+              "sampled_images_chains/chain_small_0000.jpg", "sampled_images_interpolations_all/interp_all_0000.jpg",
+              "sampled_images_perturbations_r0/pert_r0_0000.jpg", "sampled_images_real_images_perturbations/pert_real_0002.jpg"):
+        assert os.path.exists(os.path.join(out, f)), f
