@@ -150,3 +150,83 @@ extern "C" int glis_wn_pack_matrix_bf16(const float* w, const float* scale, cons
   GLIS_CHECK_LAUNCH("glis_wn_pack_matrix_bf16");
   return GLIS_OK;
 }
+
+// ---------------------------------------------------------------------------- input augmentation
+// The reference augments every training image on the HOST with imgaug (g_lis/main.py:176-231: horizontal flip,
+// additive Gaussian noise, brightness multiply, contrast normalisation, affine scale / rotate / translate), one PIL
+// image at a time inside its synchronous loader loop.  Here the decoded batch is augmented on the DEVICE in one
+// pass: per image a 12-float parameter row (drawn on the host, a few hundred bytes per batch)
+//   [a00 a01 a02 a10 a11 a12  mul  alpha  sigma  flip  border  _]
+// with (a..) the INVERSE affine map in pixel coordinates (output pixel centre -> source position), bilinear
+// sampling, border 0 = constant black, 1 = symmetric reflection; then  v = v * mul;  v = 0.5 + alpha (v - 0.5);
+// v += sigma * N(0, 1) (Philox, keyed by seed and the element);  clamp to [0, 1].  NCHW in (what the decoder
+// delivers), NHWC out (what the kernels read).
+namespace glis {
+
+__device__ __forceinline__ float aug_fetch(const float* __restrict__ img, int H, int W, int y, int x, int border) {
+  if (border) {            // symmetric: ... 1 0 | 0 1 2 ... W-1 | W-1 W-2 ...
+    const int pw = 2 * W, ph = 2 * H;
+    x = ((x % pw) + pw) % pw; if (x >= W) x = pw - 1 - x;
+    y = ((y % ph) + ph) % ph; if (y >= H) y = ph - 1 - y;
+    return __ldg(img + (size_t)y * W + x);
+  }
+  return (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(img + (size_t)y * W + x) : 0.f;
+}
+
+__device__ __forceinline__ void aug_philox(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x61756721u, 0u};   // (a stream of its own)
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0], hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+__global__ void __launch_bounds__(IS_NT)
+augment_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ params, int N, int C, int H,
+               int W, uint64_t seed) {
+  const int64_t total = (int64_t)N * H * W;
+  for (int64_t p = (int64_t)blockIdx.x * IS_NT + threadIdx.x; p < total; p += (int64_t)gridDim.x * IS_NT) {
+    const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((int64_t)W * H));
+    const float* q = params + (size_t)n * 12;
+    const float fx = q[9] != 0.f ? (float)(W - 1 - x) : (float)x;      // horizontal flip of the OUTPUT
+    const float sx = q[0] * fx + q[1] * (float)y + q[2], sy = q[3] * fx + q[4] * (float)y + q[5];
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const int x0 = (int)x0f, y0 = (int)y0f, border = q[10] != 0.f;
+    const float wx = sx - x0f, wy = sy - y0f;
+    uint32_t r[4] = {0, 0, 0, 0};
+    if (q[8] > 0.f) aug_philox(seed, (uint64_t)p, r);
+    for (int c = 0; c < C; ++c) {
+      const float* img = in + ((size_t)n * C + c) * H * W;
+      float v = (1.f - wy) * ((1.f - wx) * aug_fetch(img, H, W, y0, x0, border) + wx * aug_fetch(img, H, W, y0, x0 + 1, border)) +
+                wy * ((1.f - wx) * aug_fetch(img, H, W, y0 + 1, x0, border) + wx * aug_fetch(img, H, W, y0 + 1, x0 + 1, border));
+      v *= q[6];
+      v = 0.5f + q[7] * (v - 0.5f);
+      if (q[8] > 0.f) {        // one Gaussian per PIXEL, shared by the channels (imgaug per_channel=False)
+        const float u1 = 1.f - (float)(r[0] >> 8) * (1.f / 16777216.f), u2 = (float)(r[1] >> 8) * (1.f / 16777216.f);
+        float s, co;
+        sincospif(2.f * u2, &s, &co);
+        v += q[8] * sqrtf(-2.f * logf(u1)) * co;
+      }
+      out[(size_t)p * C + c] = fminf(fmaxf(v, 0.f), 1.f);
+    }
+  }
+}
+
+}  // namespace glis
+
+extern "C" int glis_augment(const float* in_nchw, float* out_nhwc, const float* params, int N, int C, int H, int W,
+                            uint64_t seed, void* stream) {
+  using namespace glis;
+  GLIS_REQUIRE(in_nchw && out_nhwc && params, GLIS_E_BADARG, "glis_augment: NULL pointer");
+  GLIS_REQUIRE(N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, GLIS_E_BADARG, "glis_augment: bad shape (N=%d C=%d H=%d W=%d)", N, C, H, W);
+  augment_kernel<<<is_blocks((int64_t)N * H * W), IS_NT, 0, (cudaStream_t)stream>>>(in_nchw, out_nhwc, params, N, C, H, W, seed);
+  GLIS_CHECK_LAUNCH("glis_augment");
+  return GLIS_OK;
+}

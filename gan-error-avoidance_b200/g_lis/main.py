@@ -80,6 +80,7 @@ def build_parser():
     a("--precision", default=None, choices=["fp32", "bf16x3", "bf16"], help="contraction arithmetic")
     a("--no_graph", action="store_true", default=False, help="do not replay the step as a CUDA graph")
     a("--log_interval", type=int, default=1, help="print (and synchronise for) the losses every N iterations")
+    a("--workers", type=int, default=min(8, os.cpu_count() or 1), help="decoder processes of the input pipeline")
     return p
 
 
@@ -168,19 +169,20 @@ class SyntheticData(object):
 
 
 class DatasetData(object):
-    """The reference's per-sample loader (g_lis/main.py:169-297, :543-554) on modern torchvision,
-    sharded by rank.  Host-bound by design; `--synthetic` is the device-bound path."""
+    """The reference's data source (g_lis/main.py:169-297, :543-554) — CenterCrop / Scale / CenterCrop / ToTensor,
+    the `data_index.pt` split, the `index_shuffle` sample order — behind `glis_b200.data.PrefetchLoader`: decoded by
+    `--workers` processes, copied through pinned memory on a copy stream, augmented (`--augment`, horizontal flip
+    included) on the device, sharded by rank."""
 
-    def __init__(self, opt, device, rank, world):
+    def __init__(self, opt, device, rank, world, seed, out=None):
         import torchvision.datasets as datasets
         import torchvision.transforms as transforms
+        from glis_b200.data import PrefetchLoader
         tl = []
         if opt.crop_height > 0 and opt.crop_width > 0:
             tl.append(transforms.CenterCrop((opt.crop_height, opt.crop_width)))
-        tl += [transforms.Resize((opt.height, opt.width)), transforms.CenterCrop((opt.height, opt.width))]
-        if opt.augment != "none":
-            raise NotImplementedError("--augment needs imgaug, which is outside this path")
-        tl.append(transforms.ToTensor())
+        tl += [transforms.Resize((opt.height, opt.width)), transforms.CenterCrop((opt.height, opt.width)),
+               transforms.ToTensor()]
         tf = transforms.Compose(tl)
         if opt.dataset == "cifar10":
             parts = [datasets.CIFAR10(root=opt.dataroot, download=False, transform=tf),
@@ -193,30 +195,31 @@ class DatasetData(object):
         else:
             raise ValueError("unknown --dataset %r" % (opt.dataset,))
         index = torch.load(os.path.join(opt.dataroot, "data_index.pt"))
-        self.train_index = index["train"][rank::world]
+        self.train_index = index["train"]
         self.test_index = index["final_test" if opt.final_test else "running_test"]
-        self.shuffle = torch.randperm(self.train_index.size(0))
-        self.current, self.opt, self.device = 0, opt, device
-        self.host = torch.empty(opt.batch_size, 3, opt.height, opt.width).pin_memory()
+        self.make = lambda shuffle, current: PrefetchLoader(
+            self.dataset, self.train_index, opt.batch_size, device, rank, world, workers=opt.workers,
+            augment_set=opt.augment, seed=seed, shuffle=shuffle, current=current, out=out)
+        self.loader = None
+        self._resume = (None, 0)
         n_test = min(self.test_index.size(0), opt.vis_row * opt.vis_col)
         self.test = torch.stack([self.dataset[int(self.test_index[i])][0] for i in range(n_test)]).to(device)
 
     def next_batch(self):
-        for i in range(self.opt.batch_size):
-            self.host[i].copy_(self.dataset[int(self.train_index[self.shuffle[self.current]])][0])
-            self.current += 1
-            if self.current == self.train_index.size(0):
-                self.current, self.shuffle = 0, torch.randperm(self.train_index.size(0))
-        return self.host.to(self.device, non_blocking=True)
+        if self.loader is None:
+            self.loader = self.make(*self._resume)
+        return self.loader.next_batch()
 
     def position(self):
         """``index_shuffle`` / ``current_sample`` of the reference's state file (g_lis/main.py:350-357)."""
-        return {"index_shuffle": self.shuffle.clone(), "current_sample": self.current}
+        if self.loader is None:
+            self.loader = self.make(*self._resume)
+        return self.loader.position()
 
     def restore(self, state):
         sh = state.get("index_shuffle")
-        if sh is not None and sh.numel() == self.train_index.size(0):
-            self.shuffle, self.current = sh.clone(), int(state.get("current_sample", 0))
+        if sh is not None and sh.numel() > 0:        # (a permutation of THIS rank's share; one of another size is ignored)
+            self._resume = (sh.clone(), int(state.get("current_sample", 0)))
 
 
 def reconstruction_test(gen, targets, opt):
@@ -359,8 +362,9 @@ def main(argv=None):
     use_graph = not opt.no_graph
     graphed = GraphedStep(trainer, opt.batch_size, opt.height, opt.width, opt.code_size, device) if use_graph else None
     # synthetic images are generated straight into the step's static input (the first half of D's 2B batch)
-    data = SyntheticData(opt, device, data_seed, out=graphed.real if graphed is not None else None) if opt.synthetic \
-        else DatasetData(opt, device, rank, world)
+    static_in = graphed.real if graphed is not None else None
+    data = SyntheticData(opt, device, data_seed, out=static_in) if opt.synthetic \
+        else DatasetData(opt, device, rank, world, data_seed, out=static_in)
     noise = NoiseSource(opt.batch_size, opt.code_size, device, data_seed)
 
     state = {"current_iter": 0, "best_iter": 0, "min_loss": 1e100}

@@ -77,6 +77,7 @@ SIGNATURES = {
     "glis_lsq_logits": [_vp, _f, _i, _f, _vp, _vp, _vp, _vp],
     "glis_dropout": [_vp, _vp, _i64, _i, _i, _i64, _i, _f, _u64, _vp, _u64, _vp],
     "glis_counter_add": [_vp, _u64, _vp],
+    "glis_augment": [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _vp],
     "glis_rmsprop": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "glis_randn": [_vp, _i64, _u64, _u64, _vp],
     "glis_uniform": [_vp, _i64, _u64, _u64, _vp],

@@ -295,6 +295,14 @@ int glis_bce_logits(const float* logit, float target, int B, float gscale, float
 int glis_lsq_logits(const float* logit, float target, int B, float gscale, float* loss,
                     float* dlogit, float* prob, void* stream);
 
+/* Training-image augmentation on the device (the reference augments on the host with imgaug, one PIL image at a time:
+ * g_lis/main.py:176-231): in NCHW [0,1] (C <= 4), out NHWC [0,1]; params = 12 floats per image
+ * [a00 a01 a02 a10 a11 a12 mul alpha sigma flip border _]: (a..) the inverse affine map in pixel coordinates
+ * (output pixel -> source position, bilinear), flip != 0 mirrors the output horizontally, border 0 = black /
+ * 1 = symmetric; then v*mul, 0.5 + alpha (v - 0.5), + sigma N(0,1) (one draw per pixel, Philox keyed by seed), clamp. */
+int glis_augment(const float* in_nchw, float* out_nhwc, const float* params, int N, int C, int H, int W, uint64_t seed,
+                 void* stream);
+
 /* nn.Dropout(p) before D's final convolution (common/model.py:52-53) and nn.Dropout2d(p) in R (:344-346):
  * out = keep ? x / (1 - p) : 0.  The mask is a pure function of (seed, *counter + call, element):
  * keep(e) = u01(Philox4x32-10(key = seed, counter = {e / 4, *counter + call})[e % 4]) >= p, u01(r) = (r >> 8) / 2^24.

@@ -1610,3 +1610,115 @@ def test_samplers_match_oracle(tmp_path):
               "sampled_images_chains/chain_small_0000.jpg", "sampled_images_interpolations_all/interp_all_0000.jpg",
               "sampled_images_perturbations_r0/pert_r0_0000.jpg", "sampled_images_real_images_perturbations/pert_real_0002.jpg"):
         assert os.path.exists(os.path.join(out, f)), f
+
+
+# ---------------------------------------------------------------- input pipeline
+def _augment_reference(x, q):
+    """The arithmetic of glis_augment restated with torch gathers (fp32): inverse affine map + bilinear sampling with
+    constant / symmetric border, horizontal flip of the output, multiply, contrast about 0.5, clamp (no noise)."""
+    n, c, h, w = x.shape
+    out = torch.empty(n, c, h, w)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    for i in range(n):
+        a = q[i]
+        fx = (w - 1 - xs) if a[9] != 0 else xs
+        sx, sy = a[0] * fx + a[1] * ys + a[2], a[3] * fx + a[4] * ys + a[5]
+        x0, y0 = torch.floor(sx), torch.floor(sy)
+        wx, wy = sx - x0, sy - y0
+
+        def fetch(yy, xx):
+            yy, xx = yy.long(), xx.long()
+            if a[10] != 0:
+                xx = xx % (2 * w); xx = torch.where(xx >= w, 2 * w - 1 - xx, xx)
+                yy = yy % (2 * h); yy = torch.where(yy >= h, 2 * h - 1 - yy, yy)
+                return x[i][:, yy, xx]
+            ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            return x[i][:, yy.clamp(0, h - 1), xx.clamp(0, w - 1)] * ok
+        v = (1 - wy) * ((1 - wx) * fetch(y0, x0) + wx * fetch(y0, x0 + 1)) + wy * ((1 - wx) * fetch(y0 + 1, x0) + wx * fetch(y0 + 1, x0 + 1))
+        out[i] = (0.5 + a[7] * (v * a[6] - 0.5)).clamp(0, 1)
+    return out
+
+
+def test_augment_kernel_matches_torch_restatement():
+    import random
+    from glis_b200 import data
+    g = torch.Generator().manual_seed(201)
+    x = torch.rand(6, 3, 20, 28, generator=g)
+    for name in ("none", "flowers102", "cifar10", "10kcats", "lsun_churches"):
+        q = data.augment_params(name, 6, 20, 28, random.Random(5))
+        sigma = q[:, 8].clone()
+        q[:, 8] = 0                      # noise apart: compared exactly
+        got = data.augment(x.to(DEV), q.to(DEV), seed=1)
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        assert rel_err(got, _augment_reference(x, q)) <= 2e-6, name
+        if name == "none":               # only the flip: every image is the input or its mirror
+            for i in range(6):
+                assert torch.equal(got[i].cpu(), x[i].flip(-1) if q[i, 9] else x[i])
+        if sigma.max() > 0:              # additive Gaussian noise: one draw per pixel, shared by the channels
+            q2 = torch.zeros(6, 12); q2[:, 0] = q2[:, 4] = q2[:, 6] = q2[:, 7] = 1; q2[:, 8] = 0.03
+            y = data.augment(torch.full((6, 3, 64, 64), 0.5, device=DEV), q2.to(DEV), seed=3).cpu() - 0.5
+            assert abs(y.std().item() - 0.03) < 2e-3 and abs(y.mean().item()) < 1e-3
+            assert torch.equal(y[:, 0], y[:, 1]) and torch.equal(y[:, 0], y[:, 2])
+            y3 = data.augment(torch.full((6, 3, 64, 64), 0.5, device=DEV), q2.to(DEV), seed=4).cpu() - 0.5
+            assert not torch.equal(y, y3)
+
+
+def test_prefetch_loader_order_sharding_and_position():
+    """The input pipeline delivers the reference's sample order (a permutation consumed front to back, redrawn at the
+    wrap) from worker processes, shards by rank, and reports the position of the batch the trainer holds."""
+    from glis_b200.data import PrefetchLoader, ShuffledOrder
+    n, B = 37, 8
+    images = torch.arange(n, dtype=torch.float32).view(n, 1, 1, 1).expand(n, 3, 4, 6).contiguous() / 100.0   # image k is all k/100
+    ds = torch.utils.data.TensorDataset(images, torch.zeros(n))
+    train_index = torch.arange(n)
+    for rank, world in ((0, 1), (1, 2)):
+        mine = train_index[rank::world]
+        ref = ShuffledOrder(len(mine), B, 9 * 7919 + rank)
+        want = iter(ref)
+        loader = PrefetchLoader(ds, train_index, B, torch.device(DEV, 0), rank, world, workers=2, augment_set="none", seed=9)
+        pos0 = loader.position()
+        assert pos0["current_sample"] == 0 and sorted(pos0["index_shuffle"].tolist()) == list(range(len(mine)))
+        for it in range(9):                       # > one epoch of this rank's share: crosses the reshuffle
+            batch = loader.next_batch()
+            ids = (batch[:, 0, 0, 0] * 100).round().long().cpu().tolist()
+            assert ids == [int(mine[k]) for k in next(want)], (rank, it)
+            pos = loader.position()
+            assert pos["current_sample"] == ref.log[it][1] and torch.equal(pos["index_shuffle"], ref.log[it][0])
+        # resume from the reported position: the stream continues where it stopped
+        resumed = PrefetchLoader(ds, train_index, B, torch.device(DEV, 0), rank, world, workers=0, augment_set="none",
+                                 seed=9, shuffle=pos["index_shuffle"], current=pos["current_sample"])
+        ids = (resumed.next_batch()[:, 0, 0, 0] * 100).round().long().cpu().tolist()
+        perm, cur = pos["index_shuffle"], pos["current_sample"]
+        assert ids[:min(B, len(mine) - cur)] == [int(mine[int(perm[cur + k])]) for k in range(min(B, len(mine) - cur))]
+        del loader, resumed
+
+
+def test_cli_trains_from_an_image_folder_with_augmentation(tmp_path, precision):
+    """g_lis/main.py on a real (tiny) image folder: `data_index.pt` split, decoder workers, device-side
+    `--augment flowers102`, checkpoint with the data position, resume."""
+    if precision == "fp32":
+        pytest.skip("host-side test: once is enough")
+    from PIL import Image
+    root = tmp_path / "data"
+    (root / "cls").mkdir(parents=True)
+    g = torch.Generator().manual_seed(7)
+    for i in range(40):
+        arr = (torch.rand(40, 48, 3, generator=g) * 255).to(torch.uint8).numpy()
+        Image.fromarray(arr).save(str(root / "cls" / ("img%03d.png" % i)))
+    perm = torch.randperm(40, generator=g)
+    torch.save({"running_test": perm[:4], "final_test": perm[4:8], "train": perm[8:]}, str(root / "data_index.pt"))
+    m = _load_cli("glis_main_data", "g_lis", "main.py")
+    save = str(tmp_path / "exp")
+    common = ["--dataset", "folder", "--dataroot", str(root), "--crop_size", "40", "--image_size", "32", "--nfeature", "16",
+              "--code_size", "32", "--norm", "weight", "--r_iterations", "1", "--batch_size", "8", "--lr", "0.0002",
+              "--vis_interval", "100", "--save_interval", "100", "--test_interval", "1000", "--vis_size", "2",
+              "--augment", "flowers102", "--workers", "2"]
+    m.main(common + ["--niter", "6", "--save_path", save])
+    state = torch.load(os.path.join(save, "net_archive", "last_state.pt"), weights_only=False)
+    assert state["current_iter"] == 6 and state["index_shuffle"].numel() == 32
+    assert state["current_sample"] == (6 * 8) % 32          # 48 samples drawn from a 32-image training set
+    m.main(common + ["--niter", "8", "--load_path", save])
+    state = torch.load(os.path.join(save, "net_archive", "last_state.pt"), weights_only=False)
+    assert state["current_iter"] == 8 and state["current_sample"] == (8 * 8) % 32
+    with pytest.raises(Exception):
+        m.main(common + ["--niter", "1", "--save_path", save, "--augment", "nonsense"])
