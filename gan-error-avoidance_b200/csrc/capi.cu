@@ -32,8 +32,9 @@ int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bf
                   const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                   __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
 int tc_wgrad_supported(const glis_geom_t* g);
+int tc_wgrad_splits(const glis_geom_t* g);
 int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo, const __nv_bfloat16* b_hi,
-             const __nv_bfloat16* b_lo, float* G, int precision, cudaStream_t st);
+             const __nv_bfloat16* b_lo, float* G, int n_slabs, int precision, cudaStream_t st);
 int split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t numel, cudaStream_t st);
 
 }  // namespace glis
@@ -147,5 +148,22 @@ extern "C" int glis_conv_wgrad_bf16(const glis_geom_t* g, const void* small_hi, 
                "glis_conv_wgrad_bf16: precision must be GLIS_PREC_BF16X3 or GLIS_PREC_BF16");
   GLIS_REQUIRE(G != nullptr, GLIS_E_BADARG, "glis_conv_wgrad_bf16: G is NULL");
   return tc_wgrad(g, (const __nv_bfloat16*)small_hi, (const __nv_bfloat16*)small_lo, (const __nv_bfloat16*)big_hi,
-                  (const __nv_bfloat16*)big_lo, G, precision, (cudaStream_t)stream);
+                  (const __nv_bfloat16*)big_lo, G, 0, precision, (cudaStream_t)stream);
+}
+
+extern "C" int glis_wgrad_tc_splits(const glis_geom_t* g) {
+  if (validate_geom(g, "glis_wgrad_tc_splits") != GLIS_OK) return 0;
+  return tc_wgrad_splits(g);
+}
+
+extern "C" int glis_conv_wgrad_bf16_slabs(const glis_geom_t* g, const void* small_hi, const void* small_lo,
+                                          const void* big_hi, const void* big_lo, float* slabs, int n_slabs, int precision,
+                                          void* stream) {
+  int rc = validate_geom(g, "glis_conv_wgrad_bf16_slabs");
+  if (rc != GLIS_OK) return rc;
+  GLIS_REQUIRE(precision == GLIS_PREC_BF16X3 || precision == GLIS_PREC_BF16, GLIS_E_BADARG,
+               "glis_conv_wgrad_bf16_slabs: precision must be GLIS_PREC_BF16X3 or GLIS_PREC_BF16");
+  GLIS_REQUIRE(slabs != nullptr && n_slabs > 0, GLIS_E_BADARG, "glis_conv_wgrad_bf16_slabs: no slabs");
+  return tc_wgrad(g, (const __nv_bfloat16*)small_hi, (const __nv_bfloat16*)small_lo, (const __nv_bfloat16*)big_hi,
+                  (const __nv_bfloat16*)big_lo, slabs, n_slabs, precision, (cudaStream_t)stream);
 }

@@ -37,6 +37,8 @@ struct TcWgradParams {
   int passes, stages;
   int tiles_h, tiles_total, tiles_per_split;
   float* G;
+  long long slab_stride;   // > 0: deterministic form — K split i STORES its partial sums at G + i * slab_stride (one slab per
+                           // split, summed in a fixed order by glis_wn_project_slabs) instead of adding them atomically
   int debug;         // GLIS_WG_DEBUG bits (profiling experiments only): 1 = no stores, 2 = no MMA, 4 = no B loads, 8 = no S loads
 };
 
@@ -180,7 +182,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
       const bool st_ok = a < Ca && !(P.debug & 1);
-      float* row = P.G + (size_t)a * Cb * T + tap0;
+      float* row = P.G + (size_t)blockIdx.x * (size_t)P.slab_stride + (size_t)a * Cb * T + tap0;
+      const bool slabs = P.slab_stride > 0;
       if (P.tpc == 4) {
         // columns = [tap][b]: gather the 4 taps of 16 b-channels, then ONE 16-byte reduction per (a, b)
         // (taps are the contiguous axis of the master layout; tap0 is a multiple of 4)
@@ -193,9 +196,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int b = b0 + bb + j;
-              if (b < Cb)
-                red_add_v4(row + (size_t)b * T, __uint_as_float(v[0][j]), __uint_as_float(v[1][j]),
-                           __uint_as_float(v[2][j]), __uint_as_float(v[3][j]));
+              if (b < Cb) {
+                if (slabs)
+                  *reinterpret_cast<float4*>(row + (size_t)b * T) = make_float4(__uint_as_float(v[0][j]), __uint_as_float(v[1][j]),
+                                                                                __uint_as_float(v[2][j]), __uint_as_float(v[3][j]));
+                else
+                  red_add_v4(row + (size_t)b * T, __uint_as_float(v[0][j]), __uint_as_float(v[1][j]),
+                             __uint_as_float(v[2][j]), __uint_as_float(v[3][j]));
+              }
             }
           }
         }
@@ -209,7 +217,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int b = b0 + bb + j;
-              if (b < Cb) red_add_v2(row + (size_t)b * T, __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+              if (b < Cb) {
+                if (slabs) *reinterpret_cast<float2*>(row + (size_t)b * T) = make_float2(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+                else red_add_v2(row + (size_t)b * T, __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+              }
             }
           }
         }
@@ -223,9 +234,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int b = b0 + cb + j;
-              if (b < Cb)
-                red_add_v4(row + b, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                           __uint_as_float(v[j + 3]));
+              if (b < Cb) {
+                if (slabs)
+                  *reinterpret_cast<float4*>(row + b) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                else
+                  red_add_v4(row + b, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                             __uint_as_float(v[j + 3]));
+              }
             }
           }
         }
@@ -239,7 +255,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int b = bb + j;
-              if (b < Cb) atomicAdd(row + (size_t)b * T + tl, __uint_as_float(v[j]));
+              if (b < Cb) {
+                if (slabs) row[(size_t)b * T + tl] = __uint_as_float(v[j]);
+                else atomicAdd(row + (size_t)b * T + tl, __uint_as_float(v[j]));
+              }
             }
           }
         }
@@ -259,13 +278,8 @@ int tc_wgrad_supported(const glis_geom_t* g) {
   return 1;
 }
 
-int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo, const __nv_bfloat16* b_hi,
-             const __nv_bfloat16* b_lo, float* G, int precision, cudaStream_t st) {
-  GLIS_REQUIRE(tc_wgrad_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: geometry not tileable for tcgen05");
-  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
-  GLIS_REQUIRE(s_hi && b_hi && (passes == 1 || (s_lo && b_lo)), GLIS_E_BADARG,
-               "glis_conv_wgrad_bf16: missing hi/lo operand planes");
-  TcWgradParams P;
+// Tile shape, taps per CTA, K split and stage count.  Returns the number of K splits (grid.x) or a negative error.
+static int wg_plan(const glis_geom_t* g, int passes, TcWgradParams& P, int& n_atiles_out) {
   P.g = *g;
   const int KMAX = 64;
   P.tw = g->Wo;
@@ -340,11 +354,44 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
   GLIS_REQUIRE(stages >= 2, GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: tile does not fit shared memory");
   P.stages = stages;
+  n_atiles_out = n_atiles;
+  return splits;
+}
+
+// Number of K splits a launch of this geometry uses = slabs glis_conv_wgrad_bf16_slabs needs (0 if unsupported).
+int tc_wgrad_splits(const glis_geom_t* g) {
+  if (!tc_wgrad_supported(g)) return 0;
+  TcWgradParams P;
+  int n_atiles;
+  const int splits = wg_plan(g, 3, P, n_atiles);
+  return splits > 0 ? splits : 0;
+}
+
+int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo, const __nv_bfloat16* b_hi,
+             const __nv_bfloat16* b_lo, float* G, int n_slabs, int precision, cudaStream_t st) {
+  GLIS_REQUIRE(tc_wgrad_supported(g), GLIS_E_UNSUPPORTED, "glis_conv_wgrad_bf16: geometry not tileable for tcgen05");
+  const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
+  GLIS_REQUIRE(s_hi && b_hi && (passes == 1 || (s_lo && b_lo)), GLIS_E_BADARG,
+               "glis_conv_wgrad_bf16: missing hi/lo operand planes");
+  TcWgradParams P;
+  int n_atiles;
+  int splits = wg_plan(g, passes, P, n_atiles);
+  if (splits < 0) return splits;
+  const int T = g->KH * g->KW;
+  P.passes = passes;
   P.G = G;
+  P.slab_stride = 0;
+  if (n_slabs > 0) {
+    GLIS_REQUIRE(n_slabs == splits, GLIS_E_BADARG, "glis_conv_wgrad_bf16_slabs: %d slabs for %d K splits (glis_wgrad_tc_splits)",
+                 n_slabs, splits);
+    P.slab_stride = (long long)g->Co * g->Ci * T;
+  }
   {
     const char* dbg = getenv("GLIS_WG_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
   }
+  const size_t stage_bytes = 2 * (size_t)(2 + P.tpc * (P.nb / 64)) * P.kp * 128;
+  const int stages = P.stages;
 
   CUtensorMap ms_hi, ms_lo, mb_hi, mb_lo;
   {

@@ -135,13 +135,21 @@ __global__ void wn_pack_bf16_kernel(const float* __restrict__ w, const float* __
   }
 }
 
+// Raw gradient element idx: the sum of the K-split slabs of a deterministic weight-gradient launch, always in slab
+// order (n_slabs = 1: the plain buffer).
+__device__ __forceinline__ float slab_sum(const float* __restrict__ G, int64_t idx, int n_slabs, int64_t slab_stride) {
+  float v = __ldg(G + idx);
+  for (int s = 1; s < n_slabs; ++s) v += __ldg(G + (int64_t)s * slab_stride + idx);
+  return v;
+}
+
 // One block per output channel, at most PER elements of the row per thread: G and w are read ONCE,
 // with every load in flight together, and stay in registers between the dot product and the update.
 template <int NT, int PER>
 __global__ void __launch_bounds__(NT)
 wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                   const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
-                  float* __restrict__ dw, float* __restrict__ dscale, int accumulate) {
+                  float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
   __shared__ float red[33];
   const int o = blockIdx.x;
   const int R = Cin * T;
@@ -154,7 +162,7 @@ wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, cons
     if (r < R) {
       const int i = r / T, t = r - i * T;
       const int64_t idx = master_index(out_axis, Cout, Cin, T, o, i, t);
-      gv[u] = __ldg(G + idx);
+      gv[u] = slab_sum(G, idx, n_slabs, slab_stride);
       wv[u] = __ldg(w + idx);
       if (accumulate) old[u] = dw[idx];
     }
@@ -179,7 +187,7 @@ wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, cons
 __global__ void __launch_bounds__(1024)
 wn_project_long_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                        const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
-                       float* __restrict__ dw, float* __restrict__ dscale, int accumulate) {
+                       float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
   constexpr int NT = 1024;
   __shared__ float red[33];
   const int o = blockIdx.x;
@@ -189,7 +197,7 @@ wn_project_long_kernel(const float* __restrict__ G, const float* __restrict__ w,
   for (int r = threadIdx.x; r < R; r += NT) {
     const int i = r / T, t = r - i * T;
     const int64_t idx = master_index(out_axis, Cout, Cin, T, o, i, t);
-    dot = fmaf(__ldg(G + idx), __ldg(w + idx), dot);
+    dot = fmaf(slab_sum(G, idx, n_slabs, slab_stride), __ldg(w + idx), dot);
   }
   dot = block_sum<NT>(dot, red, true);
   const float n = __ldg(norm + o), s = scale ? __ldg(scale + o) : 1.f;
@@ -198,7 +206,7 @@ wn_project_long_kernel(const float* __restrict__ G, const float* __restrict__ w,
   for (int r = threadIdx.x; r < R; r += NT) {
     const int i = r / T, t = r - i * T;
     const int64_t idx = master_index(out_axis, Cout, Cin, T, o, i, t);
-    const float v = a * (__ldg(G + idx) - k * __ldg(w + idx));
+    const float v = a * (slab_sum(G, idx, n_slabs, slab_stride) - k * __ldg(w + idx));
     dw[idx] = accumulate ? dw[idx] + v : v;
   }
   if (dscale && threadIdx.x == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
@@ -208,7 +216,7 @@ wn_project_long_kernel(const float* __restrict__ G, const float* __restrict__ w,
 __global__ void __launch_bounds__(WN_NT)
 wn_project_warp_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                        const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
-                       float* __restrict__ dw, float* __restrict__ dscale, int accumulate) {
+                       float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
   const int o = blockIdx.x * (WN_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= Cout) return;
   const int R = Cin * T;
@@ -217,7 +225,7 @@ wn_project_warp_kernel(const float* __restrict__ G, const float* __restrict__ w,
   for (int r = lane; r < R; r += 32) {
     const int i = r / T, t = r - i * T;
     const int64_t idx = master_index(out_axis, Cout, Cin, T, o, i, t);
-    dot = fmaf(__ldg(G + idx), __ldg(w + idx), dot);
+    dot = fmaf(slab_sum(G, idx, n_slabs, slab_stride), __ldg(w + idx), dot);
   }
   dot = warp_sum(dot);
   const float n = __ldg(norm + o), s = scale ? __ldg(scale + o) : 1.f;
@@ -226,7 +234,7 @@ wn_project_warp_kernel(const float* __restrict__ G, const float* __restrict__ w,
   for (int r = lane; r < R; r += 32) {
     const int i = r / T, t = r - i * T;
     const int64_t idx = master_index(out_axis, Cout, Cin, T, o, i, t);
-    const float v = a * (__ldg(G + idx) - k * __ldg(w + idx));
+    const float v = a * (slab_sum(G, idx, n_slabs, slab_stride) - k * __ldg(w + idx));
     dw[idx] = accumulate ? dw[idx] + v : v;
   }
   if (dscale && lane == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
@@ -390,6 +398,29 @@ wn_project_multi_kernel(const __grid_constant__ WnProjMultiParams P) {
   if (Y.dscale && r0 == 0) Y.dscale[o] = Y.accumulate ? Y.dscale[o] + dot / n : dot / n;
 }
 
+// out[i] = slabs[0][i] + slabs[1][i] + ... in slab order: the K-split partial sums of a deterministic weight-gradient
+// launch.  Pure streaming (float4, every slab's load of an element in flight together).
+__global__ void __launch_bounds__(WN_NT)
+slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int64_t slab_stride, float* __restrict__ out, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * WN_NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * WN_NT) {
+    float4 acc = __ldg(reinterpret_cast<const float4*>(slabs) + i);
+    int s = 1;
+    for (; s + 3 < n_slabs; s += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(slabs + (int64_t)s * slab_stride) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(slabs + (int64_t)(s + 1) * slab_stride) + i);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(slabs + (int64_t)(s + 2) * slab_stride) + i);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(slabs + (int64_t)(s + 3) * slab_stride) + i);
+      acc.x = (((acc.x + a.x) + b.x) + c.x) + d.x; acc.y = (((acc.y + a.y) + b.y) + c.y) + d.y;
+      acc.z = (((acc.z + a.z) + b.z) + c.z) + d.z; acc.w = (((acc.w + a.w) + b.w) + c.w) + d.w;
+    }
+    for (; s < n_slabs; ++s) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(slabs + (int64_t)s * slab_stride) + i);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 }  // namespace glis
 
 using namespace glis;
@@ -533,12 +564,20 @@ extern "C" int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int
 extern "C" int glis_wn_project(const float* G, const float* w, const float* scale, const float* norm,
                                int out_axis, int Cout, int Cin, int T, float c, float* dw, float* dscale,
                                int accumulate, void* stream) {
+  return glis_wn_project_slabs(G, 1, 0, w, scale, norm, out_axis, Cout, Cin, T, c, dw, dscale, accumulate, stream);
+}
+
+extern "C" int glis_wn_project_slabs(const float* G, int n_slabs, int64_t slab_stride, const float* w, const float* scale,
+                                     const float* norm, int out_axis, int Cout, int Cin, int T, float c, float* dw,
+                                     float* dscale, int accumulate, void* stream) {
   GLIS_REQUIRE(G && w && norm && dw, GLIS_E_BADARG, "glis_wn_project: NULL pointer");
+  GLIS_REQUIRE(n_slabs >= 1 && (n_slabs == 1 || slab_stride >= (int64_t)Cout * Cin * T), GLIS_E_BADARG,
+               "glis_wn_project_slabs: bad slab layout");
   GLIS_REQUIRE(Cout > 0 && Cin > 0 && T > 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
                "glis_wn_project: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t R = (int64_t)Cin * T;
-#define WN_PROJECT_ARGS G, w, scale, norm, out_axis, Cout, Cin, T, c, dw, dscale, accumulate
+#define WN_PROJECT_ARGS G, w, scale, norm, out_axis, Cout, Cin, T, c, dw, dscale, accumulate, n_slabs, slab_stride
   if (R <= 512 && Cout >= 64)
     wn_project_warp_kernel<<<(Cout + WN_NT / 32 - 1) / (WN_NT / 32), WN_NT, 0, st>>>(WN_PROJECT_ARGS);
   else if (R <= 8 * 128) wn_project_kernel<128, 8><<<Cout, 128, 0, st>>>(WN_PROJECT_ARGS);
@@ -552,5 +591,19 @@ extern "C" int glis_wn_project(const float* G, const float* w, const float* scal
   else wn_project_long_kernel<<<Cout, 1024, 0, st>>>(WN_PROJECT_ARGS);
 #undef WN_PROJECT_ARGS
   GLIS_CHECK_LAUNCH("glis_wn_project");
+  return GLIS_OK;
+}
+
+extern "C" int glis_slab_reduce(const float* slabs, int n_slabs, int64_t slab_stride, float* out, int64_t numel, void* stream) {
+  GLIS_REQUIRE(slabs && out && n_slabs >= 1 && numel >= 0 && slab_stride >= numel, GLIS_E_BADARG, "glis_slab_reduce: bad arguments");
+  GLIS_REQUIRE(numel % 4 == 0 && slab_stride % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(slabs) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               GLIS_E_UNSUPPORTED, "glis_slab_reduce: sizes must be multiples of 4 floats and buffers 16-byte aligned");
+  if (numel == 0) return GLIS_OK;
+  const int64_t n4 = numel / 4;
+  int64_t blocks = (n4 + WN_NT - 1) / WN_NT;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  slab_reduce_kernel<<<(int)blocks, WN_NT, 0, (cudaStream_t)stream>>>(slabs, n_slabs, slab_stride, out, n4);
+  GLIS_CHECK_LAUNCH("glis_slab_reduce");
   return GLIS_OK;
 }

@@ -68,6 +68,10 @@ SIGNATURES = {
     "glis_conv_forward_bf16": [C.POINTER(Geom), _vp, _vp, _vp, _vp, C.POINTER(Epilogue), _vp, _vp, _vp, _i, _vp],
     "glis_wgrad_tc_supported": [C.POINTER(Geom)],
     "glis_conv_wgrad_bf16": [C.POINTER(Geom), _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "glis_wgrad_tc_splits": [C.POINTER(Geom)],
+    "glis_slab_reduce": [_vp, _i, _i64, _vp, _i64, _vp],
+    "glis_conv_wgrad_bf16_slabs": [C.POINTER(Geom), _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "glis_wn_project_slabs": [_vp, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp],
     "glis_tprelu_forward": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_tprelu_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_tprelu_backward_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],

@@ -136,6 +136,12 @@ typedef struct glis_wn_proj {
 } glis_wn_proj_t;
 int glis_wn_project_multi(const glis_wn_proj_t* items, int n, void* stream);
 
+/* glis_wn_project reading the raw gradient as the sum of n_slabs K-split slabs (slab s at G + s * slab_stride), added
+ * in slab order: the deterministic companion of glis_conv_wgrad_bf16_slabs. */
+int glis_wn_project_slabs(const float* G, int n_slabs, int64_t slab_stride, const float* w, const float* scale,
+                          const float* norm, int out_axis, int Cout, int Cin, int T, float c, float* dw, float* dscale,
+                          int accumulate, void* stream);
+
 /* Weight gradient of a weight-normalised LINEAR layer and the projection below in ONE kernel (the raw gradient
  * never exists in memory): with G[row(a)][:] = sum_m dy[m][a] x[m][:] (row(a) as in glis_linear_wgrad),
  * dw[o] (+)= (s/n)(G[o] - w[o] <G[o],w[o]>/n^2), dscale[o] (+)= <G[o],w[o]>/n  (c = 1).  For batch-sized M and rows of
@@ -218,6 +224,16 @@ int glis_wgrad_tc_supported(const glis_geom_t* g);
 /* glis_conv_wgrad on tcgen05 (both operands MN-major straight from the NHWC planes); adds into G. */
 int glis_conv_wgrad_bf16(const glis_geom_t* g, const void* small_hi, const void* small_lo,
                          const void* big_hi, const void* big_lo, float* G, int precision, void* stream);
+
+/* Deterministic form: the kernel splits the pixel contraction over glis_wgrad_tc_splits(g) CTAs per output tile; with
+ * slabs every split STORES its partial sums into its own slab (slab s at slabs + s * Co*Ci*KH*KW floats, n_slabs =
+ * that count) instead of adding them atomically into one buffer; glis_wn_project_slabs adds the slabs in a fixed
+ * order.  Same inputs -> bit-identical weight gradients; nothing to zero-fill. */
+int glis_wgrad_tc_splits(const glis_geom_t* g);
+/* out[i] = sum_s slabs[s * slab_stride + i], added in slab order (numel, slab_stride multiples of 4). */
+int glis_slab_reduce(const float* slabs, int n_slabs, int64_t slab_stride, float* out, int64_t numel, void* stream);
+int glis_conv_wgrad_bf16_slabs(const glis_geom_t* g, const void* small_hi, const void* small_lo, const void* big_hi,
+                               const void* big_lo, float* slabs, int n_slabs, int precision, void* stream);
 
 /* ---- image-side layers (C <= 4 colour channels on one side; 4x4 kernel, stride 2, pad 1) ------------
  * Unfolding the image side into J = 16*C columns per coarse pixel, j = c*16 + kh*4 + kw, turns

@@ -1722,3 +1722,35 @@ def test_cli_trains_from_an_image_folder_with_augmentation(tmp_path, precision):
     assert state["current_iter"] == 8 and state["current_sample"] == (8 * 8) % 32
     with pytest.raises(Exception):
         m.main(common + ["--niter", "1", "--save_path", save, "--augment", "nonsense"])
+
+
+def test_tensor_core_weight_gradients_are_bit_reproducible(monkeypatch):
+    """tcgen05 weight gradients split the pixel contraction over many CTAs (36 for D's level 1 at the 2B batch, 147
+    for the image-side level 0).  Every split stores its partial sums into its own slab and the weight-norm projection
+    adds the slabs in a fixed order (glis_conv_wgrad_bf16_slabs / glis_wn_project_slabs): two runs on the same inputs
+    give bit-identical weight gradients (with atomically added partial sums the last bits changed from run to run)."""
+    import ctypes as C
+    from glis_b200 import _lib, ops
+    _lib.set_precision("bf16x3")
+    _, pmod = _product()
+    monkeypatch.setattr(ops, "DETERMINISTIC_WGRAD", True)      # opt-in (GLIS_DETERMINISTIC_WGRAD=1): +3 % per iteration
+    for ci, co, h, n in ((64, 128, 40, 128), (3, 64, 80, 128), (256, 512, 10, 64)):
+        torch.manual_seed(301)
+        conv = pmod.WeightNormalizedConv2d(ci, co, 4, 2, 1, scale=False, bias=False).to(DEV)
+        x = torch.rand(n, ci, h, h, device=DEV)
+        r = torch.randn(n, co, h // 2, h // 2, device=DEV)
+        grads = []
+        for _ in range(3):
+            conv.weight.grad = None
+            (conv(x) * r).sum().backward()
+            grads.append(conv.weight.grad.clone())
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2]), (ci, co)
+        # ... and equal to the default (atomic) form up to summation order
+        monkeypatch.setattr(ops, "DETERMINISTIC_WGRAD", False)
+        conv.weight.grad = None
+        (conv(x) * r).sum().backward()
+        assert rel_err(conv.weight.grad, grads[0]) <= 1e-5
+        monkeypatch.setattr(ops, "DETERMINISTIC_WGRAD", True)
+        if ci >= 32:
+            g = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1)).geom(_lib.CONV, n, h, h, ci, h // 2, h // 2, co)
+            assert _lib.load().glis_wgrad_tc_splits(C.byref(g)) > 1          # the contraction really is split
