@@ -60,4 +60,49 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 33 floats 
 
 int validate_geom(const glis_geom_t* g, const char* who);
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched through launch_pdl() may start while its predecessor in the stream is still draining: its
+// CTAs are scheduled as the predecessor's exit, run their prologue (barrier init, TMEM allocation, descriptor
+// prefetch, index tables) and then block in pdl_wait() until the predecessor has COMPLETED and its writes are
+// visible.  Rules every such kernel follows: pdl_launch_dependents() first, NO global-memory access (read or
+// write) before pdl_wait(), and pdl_wait() on every path — a kernel that skipped it would let ITS dependents run
+// ahead of the predecessor.  Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+int pdl_enabled();   // capi.cu: GLIS_PDL (default on), glis_set_pdl()
+
+template <typename... KP, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
+}
+
+// `kernel<<<grid, block, smem, stream>>>(args)` with the attribute above; a launch error returns GLIS_E_CUDA.
+#define GLIS_LAUNCH(kernel, grid, block, smem, st, ...)                                              \
+  do {                                                                                               \
+    cudaError_t le__ = ::glis::launch_pdl(kernel, grid, block, smem, st, __VA_ARGS__);               \
+    if (le__ != cudaSuccess) {                                                                       \
+      ::glis::set_error("%s: launch failed: %s", #kernel, cudaGetErrorString(le__));                 \
+      return GLIS_E_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+// The attribute for launches that build their own cudaLaunchConfig_t (cluster launches): attr[i] = pdl_attr().
+static inline cudaLaunchAttribute pdl_attr() {
+  cudaLaunchAttribute a;
+  a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a.val.programmaticStreamSerializationAllowed = 1;
+  return a;
+}
+
 }  // namespace glis

@@ -31,6 +31,8 @@ constexpr int IS_NT = 256;
 __global__ void __launch_bounds__(IS_NT)
 unfold4x4s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, __nv_bfloat16* __restrict__ hi,
                    __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, J = 16 * C;
   const int64_t total = (int64_t)N * Ho * Wo * 4;
   for (int64_t i = (int64_t)blockIdx.x * IS_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * IS_NT) {
@@ -61,6 +63,8 @@ unfold4x4s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, __nv
 __global__ void __launch_bounds__(IS_NT)
 fold4x4s2_kernel(const float* __restrict__ cols, int N, int Hi, int Wi, int C, const float* __restrict__ bias, int act,
                  float* __restrict__ out) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int Ho = 2 * Hi, Wo = 2 * Wi, J = 16 * C;
   const int64_t total = (int64_t)N * Ho * Wo;
   for (int64_t pix = (int64_t)blockIdx.x * IS_NT + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * IS_NT) {
@@ -95,6 +99,8 @@ pack_matrix_bf16_kernel(const float* __restrict__ w, const float* __restrict__ s
                         int out_axis, int A, int J, int T, __nv_bfloat16* __restrict__ e_hi,
                         __nv_bfloat16* __restrict__ e_lo, __nv_bfloat16* __restrict__ et_hi,
                         __nv_bfloat16* __restrict__ et_lo) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int total = A * J;
   for (int i = blockIdx.x * IS_NT + threadIdx.x; i < total; i += gridDim.x * IS_NT) {
     const int a = i / J, j = i - a * J;
@@ -121,7 +127,7 @@ extern "C" int glis_unfold4x4s2_bf16(const float* x, int N, int H, int W, int C,
   GLIS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0, GLIS_E_BADARG,
                "glis_unfold4x4s2_bf16: bad shape (N=%d H=%d W=%d C=%d)", N, H, W, C);
   GLIS_REQUIRE((int64_t)N * H * W < ((int64_t)1 << 31), GLIS_E_UNSUPPORTED, "glis_unfold4x4s2_bf16: more than 2^31 pixels");
-  unfold4x4s2_kernel<<<is_blocks((int64_t)N * (H / 2) * (W / 2) * 4), IS_NT, 0, (cudaStream_t)stream>>>(
+  GLIS_LAUNCH(unfold4x4s2_kernel, dim3(is_blocks((int64_t)N * (H / 2) * (W / 2) * 4)), dim3(IS_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
       x, N, H, W, C, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   GLIS_CHECK_LAUNCH("glis_unfold4x4s2_bf16");
   return GLIS_OK;
@@ -133,7 +139,7 @@ extern "C" int glis_fold4x4s2(const float* cols, int N, int Hi, int Wi, int C, c
   GLIS_REQUIRE(N > 0 && Hi > 0 && Wi > 0 && C > 0 && C <= 4, GLIS_E_BADARG, "glis_fold4x4s2: bad shape");
   GLIS_REQUIRE((int64_t)N * Hi * Wi * 4 < ((int64_t)1 << 31), GLIS_E_UNSUPPORTED, "glis_fold4x4s2: more than 2^31 pixels");
   GLIS_REQUIRE(act == GLIS_ACT_NONE || act == GLIS_ACT_SIGMOID, GLIS_E_UNSUPPORTED, "glis_fold4x4s2: activation %d", act);
-  fold4x4s2_kernel<<<is_blocks((int64_t)N * Hi * Wi * 4), IS_NT, 0, (cudaStream_t)stream>>>(cols, N, Hi, Wi, C, bias, act,
+  GLIS_LAUNCH(fold4x4s2_kernel, dim3(is_blocks((int64_t)N * Hi * Wi * 4)), dim3(IS_NT), 0, (cudaStream_t)((cudaStream_t)stream), cols, N, Hi, Wi, C, bias, act,
                                                                                          out);
   GLIS_CHECK_LAUNCH("glis_fold4x4s2");
   return GLIS_OK;
@@ -144,7 +150,7 @@ extern "C" int glis_wn_pack_matrix_bf16(const float* w, const float* scale, cons
   GLIS_REQUIRE(w && norm && (e_hi || et_hi), GLIS_E_BADARG, "glis_wn_pack_matrix_bf16: NULL pointer");
   GLIS_REQUIRE(A > 0 && J > 0 && T > 0 && J % T == 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
                "glis_wn_pack_matrix_bf16: bad shape");
-  pack_matrix_bf16_kernel<<<is_blocks((int64_t)A * J), IS_NT, 0, (cudaStream_t)stream>>>(
+  GLIS_LAUNCH(pack_matrix_bf16_kernel, dim3(is_blocks((int64_t)A * J)), dim3(IS_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
       w, scale, norm, out_axis, A, J, T, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, (__nv_bfloat16*)et_hi,
       (__nv_bfloat16*)et_lo);
   GLIS_CHECK_LAUNCH("glis_wn_pack_matrix_bf16");
@@ -191,6 +197,8 @@ __device__ __forceinline__ void aug_philox(uint64_t seed, uint64_t ctr, uint32_t
 __global__ void __launch_bounds__(IS_NT)
 augment_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ params, int N, int C, int H,
                int W, uint64_t seed) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int64_t total = (int64_t)N * H * W;
   for (int64_t p = (int64_t)blockIdx.x * IS_NT + threadIdx.x; p < total; p += (int64_t)gridDim.x * IS_NT) {
     const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((int64_t)W * H));
@@ -226,7 +234,7 @@ extern "C" int glis_augment(const float* in_nchw, float* out_nhwc, const float* 
   using namespace glis;
   GLIS_REQUIRE(in_nchw && out_nhwc && params, GLIS_E_BADARG, "glis_augment: NULL pointer");
   GLIS_REQUIRE(N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, GLIS_E_BADARG, "glis_augment: bad shape (N=%d C=%d H=%d W=%d)", N, C, H, W);
-  augment_kernel<<<is_blocks((int64_t)N * H * W), IS_NT, 0, (cudaStream_t)stream>>>(in_nchw, out_nhwc, params, N, C, H, W, seed);
+  GLIS_LAUNCH(augment_kernel, dim3(is_blocks((int64_t)N * H * W)), dim3(IS_NT), 0, (cudaStream_t)((cudaStream_t)stream), in_nchw, out_nhwc, params, N, C, H, W, seed);
   GLIS_CHECK_LAUNCH("glis_augment");
   return GLIS_OK;
 }

@@ -70,6 +70,8 @@ __device__ __forceinline__ void lis_dot(const float* __restrict__ xs, int ld, co
 template <bool BACKWARD>
 __global__ void __launch_bounds__(LIS_NT)
 lis_chain_kernel(const LisParams P) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   extern __shared__ __align__(16) float lis_smem[];
   float* xs = lis_smem;                                          // [16][code + 4] input row tile, later the full intermediate
   float* ws = xs + LIS_ROWS * (LIS_MAX_CODE + 4);                // [code][32] this CTA's columns of the current pack
@@ -172,11 +174,12 @@ static int lis_launch(const LisParams& P, bool backward, cudaStream_t st) {
   }
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = P.code / LIS_COLS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1] = pdl_attr();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = backward ? cudaLaunchKernelEx(&cfg, lis_chain_kernel<true>, P)
                            : cudaLaunchKernelEx(&cfg, lis_chain_kernel<false>, P);
   GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "glis_lis_%s: launch failed: %s", backward ? "backward" : "forward",

@@ -18,6 +18,8 @@ __device__ __forceinline__ float clamp01(float a) { return fminf(fmaxf(a, 0.f), 
 __global__ void __launch_bounds__(PW_NT)
 tprelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
                   float* __restrict__ out, int64_t numel, int C, int inner) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
     const int c = (int)((i / inner) % C);
     const float bb = __ldg(b + c), a = clamp01(__ldg(a_raw + c));
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(PW_NT)
 tprelu_fwd_planes_kernel(const float* __restrict__ x, int nslabs, int64_t slab_stride, const float* __restrict__ a_raw,
                          const float* __restrict__ b, float* __restrict__ preact, float* __restrict__ out,
                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t numel, int C, int CA) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int64_t n4 = numel >> 2;   // C % 4 == 0: a group of four never straddles a pixel
   for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < n4; q += (int64_t)gridDim.x * PW_NT) {
     float4 v = reinterpret_cast<const float4*>(x)[q];
@@ -59,6 +63,8 @@ tprelu_fwd_planes_kernel(const float* __restrict__ x, int nslabs, int64_t slab_s
 // dy = dout * s * (1 - s): the backward of a sigmoid fused into a contraction's epilogue.
 __global__ void __launch_bounds__(PW_NT)
 sigmoid_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dout, float* __restrict__ dy, int64_t numel) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
     const float v = s[i];
     dy[i] = dout[i] * v * (1.f - v);
@@ -85,6 +91,8 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
                   const float* __restrict__ dout, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
                   __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ da, float* __restrict__ db, int64_t numel,
                   int C, int inner) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float sa[SMEM_CH], sb[SMEM_CH];
   const bool staged = C <= SMEM_CH;
   if (staged) {
@@ -139,6 +147,8 @@ tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_
                        const float* __restrict__ dout, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
                        __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ da, float* __restrict__ db,
                        int64_t rows, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float s_a[1024], s_b[1024];
   for (int c = threadIdx.x; c < C; c += PW_NT) { s_a[c] = 0.f; s_b[c] = 0.f; }
   __syncthreads();
@@ -189,6 +199,8 @@ tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_
 
 __global__ void __launch_bounds__(PW_NT)
 channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, int C, int inner) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float sa[SMEM_CH];
   const bool staged = C <= SMEM_CH;
   if (staged) {
@@ -215,6 +227,8 @@ channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t
 // pixels, keeps C partial sums in registers, warps reduce, one atomic per warp and channel.
 __global__ void __launch_bounds__(PW_NT)
 channel_sum_small_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t r = (int64_t)blockIdx.x * PW_NT + threadIdx.x; r < rows; r += (int64_t)gridDim.x * PW_NT) {
     const float* p = x + r * C;
@@ -234,6 +248,8 @@ channel_sum_small_kernel(const float* __restrict__ x, float* __restrict__ out, i
 __global__ void __launch_bounds__(PW_NT)
 bce_logits_kernel(const float* __restrict__ logit, float target, int B, float gscale, float* __restrict__ loss,
                   float* __restrict__ dlogit, float* __restrict__ prob) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += PW_NT) {
@@ -260,6 +276,8 @@ bce_logits_kernel(const float* __restrict__ logit, float target, int B, float gs
 __global__ void __launch_bounds__(PW_NT)
 lsq_logits_kernel(const float* __restrict__ logit, float target, int B, float gscale, float* __restrict__ loss,
                   float* __restrict__ dlogit, float* __restrict__ prob) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += PW_NT) {
@@ -276,6 +294,8 @@ lsq_logits_kernel(const float* __restrict__ logit, float target, int B, float gs
 __global__ void __launch_bounds__(PW_NT)
 mse_scaled_kernel(const float* __restrict__ u, const float* __restrict__ z, int64_t numel, float lambda,
                   float* __restrict__ loss, float* __restrict__ du, int accumulate) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   float acc = 0.f;
   const float k = 2.f * lambda / (float)numel;
@@ -291,6 +311,8 @@ mse_scaled_kernel(const float* __restrict__ u, const float* __restrict__ z, int6
 __global__ void __launch_bounds__(PW_NT)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, int64_t numel,
                float lr, float alpha, float eps, float gscale) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int64_t n4 = numel >> 2;
   const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)v)) & 15) == 0;
   const int64_t tid = (int64_t)blockIdx.x * PW_NT + threadIdx.x, stride = (int64_t)gridDim.x * PW_NT;
@@ -345,6 +367,8 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.f
 template <bool NORMAL>
 __global__ void __launch_bounds__(PW_NT)
 philox_fill_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint64_t offset) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int64_t quads = (numel + 3) >> 2;
   for (int64_t q = (int64_t)blockIdx.x * PW_NT + threadIdx.x; q < quads; q += (int64_t)gridDim.x * PW_NT) {
     uint32_t r[4];
@@ -389,6 +413,8 @@ __device__ __forceinline__ void philox4_stream(uint64_t seed, uint64_t quad, uin
 __global__ void __launch_bounds__(PW_NT)
 dropout_elem_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, float p, float keep_scale,
                     uint64_t seed, const uint64_t* __restrict__ counter, uint64_t call) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const uint64_t stream = (counter ? *counter : 0ull) + call;
   const int64_t quads = (numel + 3) >> 2;
   const bool vec = ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0;
@@ -416,6 +442,8 @@ __global__ void __launch_bounds__(PW_NT)
 dropout_channel_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t numel, int C, int64_t per_image,
                        int inner, float p, float keep_scale, uint64_t seed, const uint64_t* __restrict__ counter,
                        uint64_t call) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const uint64_t stream = (counter ? *counter : 0ull) + call;
   for (int64_t i = (int64_t)blockIdx.x * PW_NT + threadIdx.x; i < numel; i += (int64_t)gridDim.x * PW_NT) {
     const int64_t e = (i / per_image) * C + (i / inner) % C;
@@ -426,7 +454,9 @@ dropout_channel_kernel(const float* __restrict__ x, float* __restrict__ out, int
   }
 }
 
-__global__ void counter_add_kernel(uint64_t* counter, uint64_t inc) { *counter += inc; }
+__global__ void counter_add_kernel(uint64_t* counter, uint64_t inc) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait(); *counter += inc; }
 
 }  // namespace glis
 
@@ -437,7 +467,7 @@ extern "C" int glis_tprelu_forward(const float* x, const float* a_raw, const flo
   GLIS_REQUIRE(x && a_raw && b && out, GLIS_E_BADARG, "glis_tprelu_forward: NULL pointer");
   GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_forward: bad sizes");
   if (numel == 0) return GLIS_OK;
-  tprelu_fwd_kernel<<<pw_blocks(numel), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, out, numel, C, inner);
+  GLIS_LAUNCH(tprelu_fwd_kernel, dim3(pw_blocks(numel)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), x, a_raw, b, out, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_tprelu_forward");
   return GLIS_OK;
 }
@@ -445,7 +475,7 @@ extern "C" int glis_tprelu_forward(const float* x, const float* a_raw, const flo
 extern "C" int glis_sigmoid_backward(const float* s, const float* dout, float* dy, int64_t numel, void* stream) {
   GLIS_REQUIRE(s && dout && dy && numel >= 0, GLIS_E_BADARG, "glis_sigmoid_backward: bad arguments");
   if (numel == 0) return GLIS_OK;
-  sigmoid_bwd_kernel<<<pw_blocks(numel), PW_NT, 0, (cudaStream_t)stream>>>(s, dout, dy, numel);
+  GLIS_LAUNCH(sigmoid_bwd_kernel, dim3(pw_blocks(numel)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), s, dout, dy, numel);
   GLIS_CHECK_LAUNCH("glis_sigmoid_backward");
   return GLIS_OK;
 }
@@ -461,7 +491,7 @@ extern "C" int glis_tprelu_forward_planes(const float* x, const float* a_raw, co
                    ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 7) == 0,
                GLIS_E_BADARG, "glis_tprelu_forward_planes: misaligned buffer");
   if (numel == 0) return GLIS_OK;
-  tprelu_fwd_planes_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+  GLIS_LAUNCH(tprelu_fwd_planes_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
       x, 1, 0, a_raw, b, nullptr, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C,
       act_channels > 0 ? act_channels : C);
   GLIS_CHECK_LAUNCH("glis_tprelu_forward_planes");
@@ -482,7 +512,7 @@ extern "C" int glis_tprelu_forward_planes_sum(const float* slabs, int nslabs, in
                    ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 7) == 0,
                GLIS_E_BADARG, "glis_tprelu_forward_planes_sum: misaligned buffer");
   if (numel == 0) return GLIS_OK;
-  tprelu_fwd_planes_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+  GLIS_LAUNCH(tprelu_fwd_planes_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
       slabs, nslabs, slab_stride, a_raw, b, preact, out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, numel, C,
       act_channels > 0 ? act_channels : C);
   GLIS_CHECK_LAUNCH("glis_tprelu_forward_planes_sum");
@@ -495,7 +525,7 @@ extern "C" int glis_tprelu_backward(const float* x, const float* a_raw, const fl
   GLIS_REQUIRE(x && a_raw && b && dout && dx && da && db, GLIS_E_BADARG, "glis_tprelu_backward: NULL pointer");
   GLIS_REQUIRE(numel >= 0 && C > 0 && inner > 0, GLIS_E_BADARG, "glis_tprelu_backward: bad sizes");
   if (numel == 0) return GLIS_OK;
-  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(x, a_raw, b, dout, dx, nullptr, nullptr,
+  GLIS_LAUNCH(tprelu_bwd_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), x, a_raw, b, dout, dx, nullptr, nullptr,
                                                                             da, db, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_tprelu_backward");
   return GLIS_OK;
@@ -519,12 +549,12 @@ extern "C" int glis_tprelu_backward_planes(const float* x, const float* a_raw, c
     per = per < 1 ? 1 : (per > 8 ? 8 : per);
     int64_t want = (rows + rows_per_iter * per - 1) / (rows_per_iter * per);
     const int blocks = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
-    tprelu_bwd_nhwc_kernel<<<blocks, PW_NT, 0, (cudaStream_t)stream>>>(
+    GLIS_LAUNCH(tprelu_bwd_nhwc_kernel, dim3(blocks), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
         x, a_raw, b, dout, dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, da, db, rows, C);
     GLIS_CHECK_LAUNCH("glis_tprelu_backward_planes(nhwc)");
     return GLIS_OK;
   }
-  tprelu_bwd_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+  GLIS_LAUNCH(tprelu_bwd_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
       x, a_raw, b, dout, dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, da, db, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_tprelu_backward_planes");
   return GLIS_OK;
@@ -544,11 +574,11 @@ extern "C" int glis_channel_sum(const float* x, float* out, int64_t numel, int C
   if (numel == 0) return GLIS_OK;
   if (inner == 1 && C <= 4 && numel % C == 0) {
     const int64_t rows = numel / C;
-    channel_sum_small_kernel<<<pw_blocks(rows, 8), PW_NT, 0, st>>>(x, out, rows, C);
+    GLIS_LAUNCH(channel_sum_small_kernel, dim3(pw_blocks(rows, 8)), dim3(PW_NT), 0, (cudaStream_t)(st), x, out, rows, C);
     GLIS_CHECK_LAUNCH("glis_channel_sum(small C)");
     return GLIS_OK;
   }
-  channel_sum_kernel<<<pw_blocks(numel, 8), PW_NT, 0, st>>>(x, out, numel, C, inner);
+  GLIS_LAUNCH(channel_sum_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)(st), x, out, numel, C, inner);
   GLIS_CHECK_LAUNCH("glis_channel_sum");
   return GLIS_OK;
 }
@@ -557,7 +587,7 @@ extern "C" int glis_bce_logits(const float* logit, float target, int B, float gs
                                float* prob, void* stream) {
   GLIS_REQUIRE(logit && loss, GLIS_E_BADARG, "glis_bce_logits: NULL pointer");
   GLIS_REQUIRE(B > 0, GLIS_E_BADARG, "glis_bce_logits: empty batch");
-  bce_logits_kernel<<<1, PW_NT, 0, (cudaStream_t)stream>>>(logit, target, B, gscale, loss, dlogit, prob);
+  GLIS_LAUNCH(bce_logits_kernel, dim3(1), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), logit, target, B, gscale, loss, dlogit, prob);
   GLIS_CHECK_LAUNCH("glis_bce_logits");
   return GLIS_OK;
 }
@@ -566,7 +596,7 @@ extern "C" int glis_lsq_logits(const float* logit, float target, int B, float gs
                                float* prob, void* stream) {
   GLIS_REQUIRE(logit && loss, GLIS_E_BADARG, "glis_lsq_logits: NULL pointer");
   GLIS_REQUIRE(B > 0, GLIS_E_BADARG, "glis_lsq_logits: empty batch");
-  lsq_logits_kernel<<<1, PW_NT, 0, (cudaStream_t)stream>>>(logit, target, B, gscale, loss, dlogit, prob);
+  GLIS_LAUNCH(lsq_logits_kernel, dim3(1), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), logit, target, B, gscale, loss, dlogit, prob);
   GLIS_CHECK_LAUNCH("glis_lsq_logits");
   return GLIS_OK;
 }
@@ -581,10 +611,10 @@ extern "C" int glis_dropout(const float* x, float* out, int64_t numel, int C, in
   if (channel_mode) {
     GLIS_REQUIRE(C > 0 && inner > 0 && per_image > 0 && per_image % ((int64_t)C * inner) == 0, GLIS_E_BADARG,
                  "glis_dropout: channel mode needs C, inner and the elements per image");
-    dropout_channel_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(
+    GLIS_LAUNCH(dropout_channel_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
         x, out, numel, C, per_image, inner, p, keep_scale, seed, (const uint64_t*)counter, call);
   } else {
-    dropout_elem_kernel<<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(
+    GLIS_LAUNCH(dropout_elem_kernel, dim3(pw_blocks(numel, 16)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), 
         x, out, numel, p, keep_scale, seed, (const uint64_t*)counter, call);
   }
   GLIS_CHECK_LAUNCH("glis_dropout");
@@ -593,7 +623,7 @@ extern "C" int glis_dropout(const float* x, float* out, int64_t numel, int C, in
 
 extern "C" int glis_counter_add(void* counter, uint64_t inc, void* stream) {
   GLIS_REQUIRE(counter, GLIS_E_BADARG, "glis_counter_add: NULL pointer");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)counter, inc);
+  GLIS_LAUNCH(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)((cudaStream_t)stream), (uint64_t*)counter, inc);
   GLIS_CHECK_LAUNCH("glis_counter_add");
   return GLIS_OK;
 }
@@ -607,7 +637,7 @@ extern "C" int glis_mse_scaled(const float* u, const float* z, int64_t numel, fl
     set_error("glis_mse_scaled: memset failed");
     return GLIS_E_CUDA;
   }
-  mse_scaled_kernel<<<pw_blocks(numel), PW_NT, 0, st>>>(u, z, numel, lambda, loss, du, accumulate);
+  GLIS_LAUNCH(mse_scaled_kernel, dim3(pw_blocks(numel)), dim3(PW_NT), 0, (cudaStream_t)(st), u, z, numel, lambda, loss, du, accumulate);
   GLIS_CHECK_LAUNCH("glis_mse_scaled");
   return GLIS_OK;
 }
@@ -617,7 +647,7 @@ extern "C" int glis_rmsprop(float* p, const float* g, float* v, int64_t numel, f
   GLIS_REQUIRE(p && g && v, GLIS_E_BADARG, "glis_rmsprop: NULL pointer");
   GLIS_REQUIRE(numel >= 0, GLIS_E_BADARG, "glis_rmsprop: negative size");
   if (numel == 0) return GLIS_OK;
-  rmsprop_kernel<<<pw_blocks(numel, 8), PW_NT, 0, (cudaStream_t)stream>>>(p, g, v, numel, lr, alpha, eps, gscale);
+  GLIS_LAUNCH(rmsprop_kernel, dim3(pw_blocks(numel, 8)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), p, g, v, numel, lr, alpha, eps, gscale);
   GLIS_CHECK_LAUNCH("glis_rmsprop");
   return GLIS_OK;
 }
@@ -625,7 +655,7 @@ extern "C" int glis_rmsprop(float* p, const float* g, float* v, int64_t numel, f
 extern "C" int glis_randn(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream) {
   GLIS_REQUIRE(out && numel >= 0, GLIS_E_BADARG, "glis_randn: bad arguments");
   if (numel == 0) return GLIS_OK;
-  philox_fill_kernel<true><<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(out, numel, seed, offset);
+  GLIS_LAUNCH((philox_fill_kernel<true>), dim3(pw_blocks(numel, 16)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), out, numel, seed, offset);
   GLIS_CHECK_LAUNCH("glis_randn");
   return GLIS_OK;
 }
@@ -633,7 +663,7 @@ extern "C" int glis_randn(float* out, int64_t numel, uint64_t seed, uint64_t off
 extern "C" int glis_uniform(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream) {
   GLIS_REQUIRE(out && numel >= 0, GLIS_E_BADARG, "glis_uniform: bad arguments");
   if (numel == 0) return GLIS_OK;
-  philox_fill_kernel<false><<<pw_blocks(numel, 16), PW_NT, 0, (cudaStream_t)stream>>>(out, numel, seed, offset);
+  GLIS_LAUNCH((philox_fill_kernel<false>), dim3(pw_blocks(numel, 16)), dim3(PW_NT), 0, (cudaStream_t)((cudaStream_t)stream), out, numel, seed, offset);
   GLIS_CHECK_LAUNCH("glis_uniform");
   return GLIS_OK;
 }

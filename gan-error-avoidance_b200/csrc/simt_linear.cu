@@ -35,6 +35,8 @@ template <int CPT>
 __global__ void __launch_bounds__(LC_NT)
 linear_cluster_kernel(const float* __restrict__ X, const float* __restrict__ Wp, int M, int N, int K,
                       const glis_epilogue_t ep, float* __restrict__ out, int kgroups, int chunks) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   constexpr int TN = 32 * CPT;
   __shared__ __align__(16) float Xs[LC_KC * LC_LD];   // [k][row]
   __shared__ __align__(16) float Ws[LC_KC * TN];      // [k][col]; afterwards this block's partial tile [row][col]
@@ -217,11 +219,12 @@ int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpac
   cfg.blockDim = dim3(LC_NT);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cs;
+  attr[1] = pdl_attr();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cpt == 2
       ? cudaLaunchKernelEx(&cfg, linear_cluster_kernel<2>, in, wpack, M, N, K, *ep, out, kgroups, chunks)
       : cudaLaunchKernelEx(&cfg, linear_cluster_kernel<1>, in, wpack, M, N, K, *ep, out, kgroups, chunks);
@@ -242,6 +245,8 @@ template <int APT>
 __global__ void __launch_bounds__(LW_NT)
 linear_wgrad_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ G,
                     int M, int Ca, int Cb, int T, int perm_c, int perm_p) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ __align__(16) float xs[LW_MC * LW_TJ];   // [m][j]
   constexpr int LW_TN = 8 * APT;
   __shared__ __align__(16) float ds[LW_MC * LW_TN];   // [m][a]
@@ -350,9 +355,9 @@ static int launch_linear_wgrad(const float* small, const float* big, float* G, i
   if (M > 4096) return GLIS_E_UNSUPPORTED;
   const int gx = (Cb * T + LW_TJ - 1) / LW_TJ;
   if (gx * ((Ca + 31) / 32) >= 296)
-    linear_wgrad_kernel<4><<<dim3(gx, (Ca + 31) / 32), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T, perm_c, perm_p);
+    GLIS_LAUNCH((linear_wgrad_kernel<4>), dim3(dim3(gx, (Ca + 31) / 32)), dim3(LW_NT), 0, (cudaStream_t)(st), small, big, G, M, Ca, Cb, T, perm_c, perm_p);
   else
-    linear_wgrad_kernel<2><<<dim3(gx, (Ca + 15) / 16), LW_NT, 0, st>>>(small, big, G, M, Ca, Cb, T, perm_c, perm_p);
+    GLIS_LAUNCH((linear_wgrad_kernel<2>), dim3(dim3(gx, (Ca + 15) / 16)), dim3(LW_NT), 0, (cudaStream_t)(st), small, big, G, M, Ca, Cb, T, perm_c, perm_p);
   GLIS_CHECK_LAUNCH("glis_conv_wgrad(fp32, linear)");
   return GLIS_OK;
 }
@@ -367,32 +372,52 @@ static int launch_linear_wgrad(const float* small, const float* big, float* G, i
 // wn_project_warp_kernel: 51 + 26 us for G's 12800 x 256 initial linear) by one (~10 us), at the END of G's
 // backward, where nothing else is left to overlap with.
 constexpr int LP_NT = 256;
-constexpr int LP_ROWS = 4;   // rows a warp carries at once: every x value read from shared memory feeds 4 FMAs
+// rows a warp carries at once: every x value read from shared memory feeds that many FMAs (bounded by registers)
 template <int PER>   // outputs per lane: Cb <= 32 * PER
-__global__ void __launch_bounds__(LP_NT)
+__global__ void __launch_bounds__(LP_NT, (PER <= 8 ? 3 : 1))
 linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ scale, const float* __restrict__ norm, float* __restrict__ dw,
                             float* __restrict__ dscale, int M, int Ca, int Cb, int perm_c, int perm_p, int accumulate,
                             int rows_per_block, int row_begin, int row_count) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   extern __shared__ __align__(16) float lp_xs[];        // [M][Cb]
+  constexpr int LP_ROWS = PER <= 8 ? 4 : (PER <= 16 ? 2 : 1);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  {
-    // stage x: batches of 8 independent loads per thread (a plain load -> store loop serialises on the load latency)
-    const int total = M * Cb;
-    for (int i0 = tid; i0 < total; i0 += 8 * LP_NT) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (i0 + u * LP_NT < total) ? __ldg(x + i0 + u * LP_NT) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u * LP_NT < total) lp_xs[i0 + u * LP_NT] = v[u];
-    }
-  }
-  __syncthreads();
   // rows are MASTER rows o in [row_begin, row_begin + row_count): dw is written contiguously; the matching column of
   // dy is a(o) = (o % P) * C + o / P under the NHWC row permutation of glis_wn_prepare_perm
   const int a_beg = row_begin + blockIdx.x * rows_per_block, a_end = min(row_begin + row_count, a_beg + rows_per_block);
-  for (int a0 = a_beg + wid * LP_ROWS; a0 < a_end; a0 += (LP_NT / 32) * LP_ROWS) {
+  // The kernel is a chain of dependent phases (stage x -> dy -> FMA loop -> w -> store) run by a few warps per SM, so
+  // what it costs is the number of memory round trips on that chain, not bytes: the first rows' dy columns and
+  // w rows are requested BEFORE x is staged, and x is staged with every load of a thread in flight at once.
+  const int a_first = a_beg + wid * LP_ROWS;
+  float dpre[2][LP_ROWS];      // dy[m0 + lane][a_first + r] for the first two 32-row chunks of the batch
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+      const int o = a_first + r, m = c * 32 + lane;
+      const int a = perm_c ? (o % perm_p) * perm_c + o / perm_p : o;
+      dpre[c][r] = (m < M && o < a_end) ? __ldg(dy + (size_t)m * Ca + a) : 0.f;
+    }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) {      // a misaligned view: scalar staging
+    for (int i = tid; i < M * Cb; i += LP_NT) lp_xs[i] = __ldg(x + i);
+  } else {
+    const int total4 = (M * Cb) >> 2;                     // Cb % 4 == 0 (checked by the host): 16-byte staging
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* s4 = reinterpret_cast<float4*>(lp_xs);
+    for (int i0 = tid; i0 < total4; i0 += 8 * LP_NT) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * LP_NT < total4) v[u] = __ldg(x4 + i0 + u * LP_NT);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * LP_NT < total4) s4[i0 + u * LP_NT] = v[u];
+    }
+  }
+  __syncthreads();
+  for (int a0 = a_first; a0 < a_end; a0 += (LP_NT / 32) * LP_ROWS) {
     float acc[LP_ROWS][PER];
 #pragma unroll
     for (int r = 0; r < LP_ROWS; ++r)
@@ -401,13 +426,19 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
     // dy[m][a0 .. a0 + 3]: lanes fetch 32 batch rows at a time, then broadcast
     for (int m0 = 0; m0 < M; m0 += 32) {
       float dmine[LP_ROWS];
+      const bool pre = a0 == a_first && m0 < 64;
 #pragma unroll
       for (int r = 0; r < LP_ROWS; ++r) {
-        const int o = a0 + r;
-        const int a = perm_c ? (o % perm_p) * perm_c + o / perm_p : o;
-        dmine[r] = (m0 + lane < M && o < a_end) ? __ldg(dy + (size_t)(m0 + lane) * Ca + a) : 0.f;
+        if (pre) {
+          dmine[r] = m0 == 0 ? dpre[0][r] : dpre[1][r];
+        } else {
+          const int o = a0 + r;
+          const int a = perm_c ? (o % perm_p) * perm_c + o / perm_p : o;
+          dmine[r] = (m0 + lane < M && o < a_end) ? __ldg(dy + (size_t)(m0 + lane) * Ca + a) : 0.f;
+        }
       }
       const int mc = min(32, M - m0);
+#pragma unroll 4
       for (int mm = 0; mm < mc; ++mm) {
         float d[LP_ROWS];
 #pragma unroll
@@ -422,36 +453,52 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
         }
       }
     }
+    // every row's w load in flight before the first dot product needs it
+    float wv[LP_ROWS][PER], nrm[LP_ROWS], scl[LP_ROWS];
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+      const int o = a0 + r;
+      const bool row_ok = o < a_end;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int j = lane + 32 * u;
+        wv[r][u] = (row_ok && j < Cb) ? __ldg(w + (size_t)o * Cb + j) : 0.f;
+      }
+      nrm[r] = row_ok ? __ldg(norm + o) : 1.f;
+      scl[r] = (row_ok && scale) ? __ldg(scale + o) : 1.f;
+    }
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+      float dot = 0.f;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) dot = fmaf(acc[r][u], wv[r][u], dot);
+      dot = warp_sum(dot);
+      const float n = nrm[r];
+      const float k1 = scl[r] / n, k2 = dot / (n * n);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) acc[r][u] = k1 * (acc[r][u] - k2 * wv[r][u]);
+      nrm[r] = dot / n;    // the scale gradient of the row
+    }
+    // stores (read-modify-writes when accumulating: independent of each other, one round trip for all of them)
 #pragma unroll
     for (int r = 0; r < LP_ROWS; ++r) {
       const int o = a0 + r;
       if (o >= a_end) break;                                             // (uniform across the warp)
-      float wv[PER], dot = 0.f;
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const int j = lane + 32 * u;
-        wv[u] = j < Cb ? __ldg(w + (size_t)o * Cb + j) : 0.f;
-        dot = fmaf(acc[r][u], wv[u], dot);
-      }
-      dot = warp_sum(dot);
-      const float n = __ldg(norm + o), sc = scale ? __ldg(scale + o) : 1.f;
-      const float k1 = sc / n, k2 = dot / (n * n);
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
         const int j = lane + 32 * u;
         if (j < Cb) {
-          const float v = k1 * (acc[r][u] - k2 * wv[u]);
           float* dst = dw + (size_t)o * Cb + j;
-          *dst = accumulate ? *dst + v : v;
+          *dst = accumulate ? *dst + acc[r][u] : acc[r][u];
         }
       }
-      if (dscale && lane == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
+      if (dscale && lane == 0) dscale[o] = accumulate ? dscale[o] + nrm[r] : nrm[r];
     }
   }
 }
 
 int linear_wgrad_project_supported(int M, int Ca, int Cb) {
-  return M >= 1 && M <= 512 && Cb >= 1 && Cb <= 1024 && (size_t)M * Cb * sizeof(float) <= 200 * 1024 && Ca >= 1;
+  return M >= 1 && M <= 512 && Cb >= 4 && Cb <= 1024 && (Cb & 3) == 0 && (size_t)M * Cb * sizeof(float) <= 200 * 1024 && Ca >= 1;
 }
 
 int linear_wgrad_project(const float* dy, const float* x, const float* w, const float* scale, const float* norm,
@@ -464,7 +511,11 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
   GLIS_REQUIRE(row_begin >= 0 && row_count >= 0 && row_begin + row_count <= Ca, GLIS_E_BADARG,
                "glis_linear_wgrad_project: rows [%d, %d) of %d", row_begin, row_begin + row_count, Ca);
   if (row_count == 0) return GLIS_OK;
-  int rows_per_block = (row_count + 148 * 2 - 1) / (148 * 2);
+  // blocks resident at once: shared memory (x staged per block) and 2048 threads bound the blocks per SM
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int rows_per_block = (row_count + 148 * per_sm - 1) / (148 * per_sm);
   rows_per_block = (rows_per_block + 31) / 32 * 32;       // 8 warps x LP_ROWS rows per pass
   if (rows_per_block < 32) rows_per_block = 32;
   const int blocks = (row_count + rows_per_block - 1) / rows_per_block;
@@ -477,7 +528,7 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
       GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(linear_wgrad_project): %s", cudaGetErrorString(e)); \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-    linear_wgrad_project_kernel<PER><<<blocks, LP_NT, smem, st>>>(dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
+    GLIS_LAUNCH((linear_wgrad_project_kernel<PER>), dim3(blocks), dim3(LP_NT), smem, (cudaStream_t)(st), dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
                                                                   perm_p, accumulate, rows_per_block, row_begin,   \
                                                                   row_count);                                      \
   } while (0)

@@ -166,6 +166,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   uint32_t* rel = tmem_slot + 4;   // [256] column -> element offset from the tile origin
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this one's tail (common.cuh)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
@@ -193,6 +194,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  pdl_wait();   // everything above touched shared memory, TMEM and kernel parameters only
   if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1087] = global_timer_ns();
 
   if (warp == 0) {
@@ -406,6 +408,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
 // fp32 -> bf16 hi/lo planes (same element order)
 __global__ void split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int64_t numel) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = numel >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -728,9 +732,10 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1] = pdl_attr();
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent: as many clusters as the device can hold at once (one CTA per SM), at most one per group
@@ -744,6 +749,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   }
   const int n_clusters = P.n_groups < max_clusters[cs] ? P.n_groups : max_clusters[cs];
   cfg.gridDim = dim3(n_clusters * cs);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_kernel, mw_hi, mw_lo, mx_hi, mx_lo, P);
   GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16: launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16");
@@ -754,7 +760,8 @@ int split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n
   int blocks = (int)((numel / 4 + 255) / 256);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  split_planes_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, numel);
+  cudaError_t le = launch_pdl(split_planes_kernel, dim3(blocks), dim3(256), 0, st, x, hi, lo, numel);
+  GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_split_bf16: launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_split_bf16");
   return GLIS_OK;
 }

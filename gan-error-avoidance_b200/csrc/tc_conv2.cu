@@ -158,6 +158,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
   uint32_t* rel = tmem_slot + 4;   // [256] accumulator column -> element offset from the tile origin, or T2_SKIP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this one's tail (common.cuh)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_x_hi);
@@ -183,6 +184,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)P.tmem_cols / 2;
   const int n_ctas = (int)gridDim.x;
+  pdl_wait();   // everything above touched shared memory, TMEM and kernel parameters only
   if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1216] = global_timer_ns();
 
   if (warp == 0) {
@@ -716,8 +718,9 @@ int tc_conv_halo_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const 
   }
   const int num_sms = t2_num_sms();
   const int grid = P.n_groups < num_sms ? P.n_groups : num_sms;
-  if (P.bk == 64) tc_conv_halo_kernel<64><<<grid, T2_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);
-  else tc_conv_halo_kernel<32><<<grid, T2_THREADS, smem, st>>>(mw_hi, mw_lo, mx_hi, mx_lo, P);
+  cudaError_t le = launch_pdl(P.bk == 64 ? tc_conv_halo_kernel<64> : tc_conv_halo_kernel<32>, dim3(grid), dim3(T2_THREADS),
+                              smem, st, mw_hi, mw_lo, mx_hi, mx_lo, P);
+  GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16(halo): launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16(halo)");
   return GLIS_OK;
 }

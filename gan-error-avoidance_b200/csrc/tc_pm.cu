@@ -109,6 +109,7 @@ tc_pm_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant
   float* s_t = s_a + PM_MAX_N;                               // [N] TPReLU translations
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this one's tail (common.cuh)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x_hi); tma_prefetch_desc(&map_w_hi);
     if (P.passes == 3) { tma_prefetch_desc(&map_x_lo); tma_prefetch_desc(&map_w_lo); }
@@ -118,6 +119,7 @@ tc_pm_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  pdl_wait();   // first global-memory access below (bias / TPReLU parameters: the optimizer may be the predecessor)
   for (int c = threadIdx.x; c < P.N; c += PM_THREADS) {
     s_bias[c] = P.bias ? __ldg(P.bias + c) : 0.f;
     s_a[c] = P.act == GLIS_ACT_TPRELU ? fminf(fmaxf(__ldg(P.act_a + c), 0.f), 1.f) : 0.f;
@@ -330,7 +332,8 @@ int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bf
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = P.tiles < num_sms ? P.tiles : num_sms;
-  tc_pm_kernel<<<grid, PM_THREADS, smem, st>>>(mx_hi, mx_lo, mw_hi, mw_lo, P);
+  cudaError_t le = launch_pdl(tc_pm_kernel, dim3(grid), dim3(PM_THREADS), smem, st, mx_hi, mx_lo, mw_hi, mw_lo, P);
+  GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16(pixel-major): launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16(pixel-major)");
   return GLIS_OK;
 }

@@ -70,6 +70,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = n_cols <= 64 ? 64 : (n_cols <= 128 ? 128 : 256);
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this one's tail (common.cuh)
 
   // zero the tail rows (never written by TMA) of every group so they contribute nothing
   if (P.kp > P.rows) {
@@ -94,6 +95,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched shared memory, TMEM and kernel parameters only
 
   if (ksteps > 0) {
     if (warp == 0) {
@@ -422,7 +424,8 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
     attr_set = true;
   }
   dim3 grid(splits, n_atiles * P.n_btiles, T / P.tpc);
-  tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(ms_hi, ms_lo, mb_hi, mb_lo, P);
+  cudaError_t le = launch_pdl(tc_wgrad_kernel, grid, dim3(WG_THREADS), smem, st, ms_hi, ms_lo, mb_hi, mb_lo, P);
+  GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_wgrad_bf16: launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_wgrad_bf16");
   return GLIS_OK;
 }

@@ -20,6 +20,8 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 wn_norm_kernel(const float* __restrict__ w, int out_axis, int Cout, int Cin, int T, float c,
                float* __restrict__ norm) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   const int o = blockIdx.x;
   const int R = Cin * T;
@@ -45,6 +47,8 @@ wn_norm_kernel(const float* __restrict__ w, int out_axis, int Cout, int Cin, int
 __global__ void __launch_bounds__(WN_NT)
 wn_norm_warp_kernel(const float* __restrict__ w, int out_axis, int Cout, int Cin, int T, float c,
                     float* __restrict__ norm) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int o = blockIdx.x * (WN_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= Cout) return;
   const int R = Cin * T;
@@ -59,17 +63,18 @@ wn_norm_warp_kernel(const float* __restrict__ w, int out_axis, int Cout, int Cin
   if (lane == 0) norm[o] = sqrtf(ss * c + 1e-6f);
 }
 
-static void launch_wn_norm(const float* w, int out_axis, int Cout, int Cin, int T, float c, float* norm,
+static int launch_wn_norm(const float* w, int out_axis, int Cout, int Cin, int T, float c, float* norm,
                            cudaStream_t st) {
   const int64_t R = (int64_t)Cin * T;
   if (R <= 512 && Cout >= 64)
-    wn_norm_warp_kernel<<<(Cout + WN_NT / 32 - 1) / (WN_NT / 32), WN_NT, 0, st>>>(w, out_axis, Cout, Cin, T, c, norm);
+    GLIS_LAUNCH(wn_norm_warp_kernel, dim3((Cout + WN_NT / 32 - 1) / (WN_NT / 32)), dim3(WN_NT), 0, (cudaStream_t)(st), w, out_axis, Cout, Cin, T, c, norm);
   else if (R >= 8192 || (Cout <= 16 && R >= 4096))
-    wn_norm_kernel<1024><<<Cout, 1024, 0, st>>>(w, out_axis, Cout, Cin, T, c, norm);
+    GLIS_LAUNCH((wn_norm_kernel<1024>), dim3(Cout), dim3(1024), 0, (cudaStream_t)(st), w, out_axis, Cout, Cin, T, c, norm);
   else if (R >= 4096)
-    wn_norm_kernel<512><<<Cout, 512, 0, st>>>(w, out_axis, Cout, Cin, T, c, norm);
+    GLIS_LAUNCH((wn_norm_kernel<512>), dim3(Cout), dim3(512), 0, (cudaStream_t)(st), w, out_axis, Cout, Cin, T, c, norm);
   else
-    wn_norm_kernel<WN_NT><<<Cout, WN_NT, 0, st>>>(w, out_axis, Cout, Cin, T, c, norm);
+    GLIS_LAUNCH((wn_norm_kernel<WN_NT>), dim3(Cout), dim3(WN_NT), 0, (cudaStream_t)(st), w, out_axis, Cout, Cin, T, c, norm);
+  return GLIS_OK;
 }
 
 // One thread per packed element; writes coalesced, reads gathered through L2.
@@ -85,6 +90,8 @@ template <typename IDX>
 __global__ void wn_pack_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T,
                                float* __restrict__ pack_io, float* __restrict__ pack_oi, int perm_c, int perm_p) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const IDX total = (IDX)T * (IDX)Cin * (IDX)Cout;
   for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (IDX)gridDim.x * blockDim.x) {
     if (pack_io) {  // [t][i][o]
@@ -111,6 +118,8 @@ __global__ void wn_pack_bf16_kernel(const float* __restrict__ w, const float* __
                                     __nv_bfloat16* __restrict__ fwd_hi, __nv_bfloat16* __restrict__ fwd_lo,
                                     __nv_bfloat16* __restrict__ bwd_hi, __nv_bfloat16* __restrict__ bwd_lo,
                                     int perm_c, int perm_p) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const IDX total = (IDX)T * (IDX)Cin * (IDX)Cout;
   for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (IDX)gridDim.x * blockDim.x) {
     if (fwd_hi) {  // [t][o][i]
@@ -150,6 +159,8 @@ __global__ void __launch_bounds__(NT)
 wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                   const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
                   float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   const int o = blockIdx.x;
   const int R = Cin * T;
@@ -188,6 +199,8 @@ __global__ void __launch_bounds__(1024)
 wn_project_long_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                        const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
                        float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   constexpr int NT = 1024;
   __shared__ float red[33];
   const int o = blockIdx.x;
@@ -217,6 +230,8 @@ __global__ void __launch_bounds__(WN_NT)
 wn_project_warp_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ scale,
                        const float* __restrict__ norm, int out_axis, int Cout, int Cin, int T, float c,
                        float* __restrict__ dw, float* __restrict__ dscale, int accumulate, int n_slabs, int64_t slab_stride) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int o = blockIdx.x * (WN_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= Cout) return;
   const int R = Cin * T;
@@ -262,6 +277,8 @@ struct WnMultiParams {
 
 __global__ void __launch_bounds__(WN_NT)
 wn_norm_multi_kernel(const __grid_constant__ WnMultiParams P) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   int l = 0;
   while (l + 1 < P.n && (int)blockIdx.x >= P.norm_block_begin[l + 1]) ++l;
@@ -299,6 +316,8 @@ constexpr int WN_PACK_PER_BLOCK = WN_NT * 8;   // packed elements per block of t
 
 __global__ void __launch_bounds__(WN_NT)
 wn_pack_multi_kernel(const __grid_constant__ WnMultiParams P) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   int l = 0;
   while (l + 1 < P.n && (int)blockIdx.x >= P.pack_block_begin[l + 1]) ++l;
   const glis_wn_layer_t& Y = P.L[l];
@@ -365,6 +384,8 @@ struct WnProjMultiParams {
 // Rows of <= 512 elements: one warp per output channel, 8 per block; longer rows: one block per channel.
 __global__ void __launch_bounds__(WN_NT)
 wn_project_multi_kernel(const __grid_constant__ WnProjMultiParams P) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   __shared__ float red[33];
   int l = 0;
   while (l + 1 < P.n && (int)blockIdx.x >= P.block_begin[l + 1]) ++l;
@@ -402,6 +423,8 @@ wn_project_multi_kernel(const __grid_constant__ WnProjMultiParams P) {
 // launch.  Pure streaming (float4, every slab's load of an element in flight together).
 __global__ void __launch_bounds__(WN_NT)
 slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int64_t slab_stride, float* __restrict__ out, int64_t n4) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * WN_NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * WN_NT) {
     float4 acc = __ldg(reinterpret_cast<const float4*>(slabs) + i);
     int s = 1;
@@ -442,7 +465,7 @@ extern "C" int glis_wn_project_multi(const glis_wn_proj_t* items, int n, void* s
     }
     P.block_begin[P.n] = nb;
     if (nb > 0) {
-      wn_project_multi_kernel<<<nb, WN_NT, 0, st>>>(P);
+      GLIS_LAUNCH(wn_project_multi_kernel, dim3(nb), dim3(WN_NT), 0, (cudaStream_t)(st), P);
       GLIS_CHECK_LAUNCH("glis_wn_project_multi");
     }
   }
@@ -488,11 +511,11 @@ extern "C" int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void*
     P.pack_block_begin[P.n] = pb;
     // (a layer without work owns an empty block range: the prefix scan skips it)
     if (any_norm && nb > 0) {
-      wn_norm_multi_kernel<<<nb, WN_NT, 0, st>>>(P);
+      GLIS_LAUNCH(wn_norm_multi_kernel, dim3(nb), dim3(WN_NT), 0, (cudaStream_t)(st), P);
       GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(norm)");
     }
     if (any_pack && pb > 0) {
-      wn_pack_multi_kernel<<<pb, WN_NT, 0, st>>>(P);
+      GLIS_LAUNCH(wn_pack_multi_kernel, dim3(pb), dim3(WN_NT), 0, (cudaStream_t)(st), P);
       GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(pack)");
     }
   }
@@ -514,15 +537,15 @@ extern "C" int glis_wn_prepare_perm(const float* w, const float* scale, int out_
   GLIS_REQUIRE(Cout > 0 && Cin > 0 && T > 0 && (out_axis == 0 || out_axis == 1), GLIS_E_BADARG,
                "glis_wn_prepare: bad shape (Cout=%d Cin=%d T=%d axis=%d)", Cout, Cin, T, out_axis);
   cudaStream_t st = (cudaStream_t)stream;
-  launch_wn_norm(w, out_axis, Cout, Cin, T, c, norm, st);
+  { const int rc_n = launch_wn_norm(w, out_axis, Cout, Cin, T, c, norm, st); if (rc_n != GLIS_OK) return rc_n; }
   GLIS_CHECK_LAUNCH("glis_wn_prepare(norm)");
   if (pack_io || pack_oi) {
     const int64_t total = (int64_t)T * Cin * Cout;
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
     if (total < ((int64_t)1 << 31))
-      wn_pack_kernel<uint32_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
+      GLIS_LAUNCH((wn_pack_kernel<uint32_t>), dim3(blocks), dim3(256), 0, (cudaStream_t)(st), w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
     else
-      wn_pack_kernel<int64_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
+      GLIS_LAUNCH((wn_pack_kernel<int64_t>), dim3(blocks), dim3(256), 0, (cudaStream_t)(st), w, scale, norm, out_axis, Cout, Cin, T, pack_io, pack_oi, perm_c, perm_p);
     GLIS_CHECK_LAUNCH("glis_wn_prepare(pack)");
   }
   return GLIS_OK;
@@ -543,17 +566,17 @@ extern "C" int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int
                "glis_wn_prepare_bf16: bad shape (Cout=%d Cin=%d T=%d axis=%d)", Cout, Cin, T, out_axis);
   GLIS_REQUIRE((fwd_hi || !fwd_lo) && (bwd_hi || !bwd_lo), GLIS_E_BADARG, "glis_wn_prepare_bf16: lo plane without hi");
   cudaStream_t st = (cudaStream_t)stream;
-  launch_wn_norm(w, out_axis, Cout, Cin, T, c, norm, st);
+  { const int rc_n = launch_wn_norm(w, out_axis, Cout, Cin, T, c, norm, st); if (rc_n != GLIS_OK) return rc_n; }
   GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(norm)");
   if (fwd_hi || bwd_hi) {
     const int64_t total = (int64_t)T * Cin * Cout;
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
     if (total < ((int64_t)1 << 31))
-      wn_pack_bf16_kernel<uint32_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
+      GLIS_LAUNCH((wn_pack_bf16_kernel<uint32_t>), dim3(blocks), dim3(256), 0, (cudaStream_t)(st), w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
                                                            (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi,
                                                            (__nv_bfloat16*)bwd_lo, perm_c, perm_p);
     else
-      wn_pack_bf16_kernel<int64_t><<<blocks, 256, 0, st>>>(w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
+      GLIS_LAUNCH((wn_pack_bf16_kernel<int64_t>), dim3(blocks), dim3(256), 0, (cudaStream_t)(st), w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,
                                                           (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)bwd_hi,
                                                           (__nv_bfloat16*)bwd_lo, perm_c, perm_p);
     GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(pack)");
@@ -579,16 +602,16 @@ extern "C" int glis_wn_project_slabs(const float* G, int n_slabs, int64_t slab_s
   const int64_t R = (int64_t)Cin * T;
 #define WN_PROJECT_ARGS G, w, scale, norm, out_axis, Cout, Cin, T, c, dw, dscale, accumulate, n_slabs, slab_stride
   if (R <= 512 && Cout >= 64)
-    wn_project_warp_kernel<<<(Cout + WN_NT / 32 - 1) / (WN_NT / 32), WN_NT, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 8 * 128) wn_project_kernel<128, 8><<<Cout, 128, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 16 * 128 && Cout >= 148) wn_project_kernel<128, 16><<<Cout, 128, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 8 * 256) wn_project_kernel<256, 8><<<Cout, 256, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 16 * 256 && Cout >= 148) wn_project_kernel<256, 16><<<Cout, 256, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 8 * 512) wn_project_kernel<512, 8><<<Cout, 512, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 16 * 512 && Cout >= 148) wn_project_kernel<512, 16><<<Cout, 512, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 8 * 1024) wn_project_kernel<1024, 8><<<Cout, 1024, 0, st>>>(WN_PROJECT_ARGS);
-  else if (R <= 16 * 1024) wn_project_kernel<1024, 16><<<Cout, 1024, 0, st>>>(WN_PROJECT_ARGS);
-  else wn_project_long_kernel<<<Cout, 1024, 0, st>>>(WN_PROJECT_ARGS);
+    GLIS_LAUNCH(wn_project_warp_kernel, dim3((Cout + WN_NT / 32 - 1) / (WN_NT / 32)), dim3(WN_NT), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 8 * 128) GLIS_LAUNCH((wn_project_kernel<128, 8>), dim3(Cout), dim3(128), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 16 * 128 && Cout >= 148) GLIS_LAUNCH((wn_project_kernel<128, 16>), dim3(Cout), dim3(128), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 8 * 256) GLIS_LAUNCH((wn_project_kernel<256, 8>), dim3(Cout), dim3(256), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 16 * 256 && Cout >= 148) GLIS_LAUNCH((wn_project_kernel<256, 16>), dim3(Cout), dim3(256), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 8 * 512) GLIS_LAUNCH((wn_project_kernel<512, 8>), dim3(Cout), dim3(512), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 16 * 512 && Cout >= 148) GLIS_LAUNCH((wn_project_kernel<512, 16>), dim3(Cout), dim3(512), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 8 * 1024) GLIS_LAUNCH((wn_project_kernel<1024, 8>), dim3(Cout), dim3(1024), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else if (R <= 16 * 1024) GLIS_LAUNCH((wn_project_kernel<1024, 16>), dim3(Cout), dim3(1024), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
+  else GLIS_LAUNCH(wn_project_long_kernel, dim3(Cout), dim3(1024), 0, (cudaStream_t)(st), WN_PROJECT_ARGS);
 #undef WN_PROJECT_ARGS
   GLIS_CHECK_LAUNCH("glis_wn_project");
   return GLIS_OK;
@@ -603,7 +626,7 @@ extern "C" int glis_slab_reduce(const float* slabs, int n_slabs, int64_t slab_st
   const int64_t n4 = numel / 4;
   int64_t blocks = (n4 + WN_NT - 1) / WN_NT;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  slab_reduce_kernel<<<(int)blocks, WN_NT, 0, (cudaStream_t)stream>>>(slabs, n_slabs, slab_stride, out, n4);
+  GLIS_LAUNCH(slab_reduce_kernel, dim3((int)blocks), dim3(WN_NT), 0, (cudaStream_t)((cudaStream_t)stream), slabs, n_slabs, slab_stride, out, n4);
   GLIS_CHECK_LAUNCH("glis_slab_reduce");
   return GLIS_OK;
 }

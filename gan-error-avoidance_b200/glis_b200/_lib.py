@@ -116,6 +116,8 @@ def load():
     lib.glis_last_error.argtypes = []
     lib.glis_version.restype = C.c_int
     lib.glis_version.argtypes = []
+    lib.glis_set_pdl.restype = C.c_int
+    lib.glis_set_pdl.argtypes = [C.c_int]
     _lib = lib
     return lib
 

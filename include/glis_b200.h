@@ -82,6 +82,14 @@ typedef struct glis_epilogue {
 const char* glis_last_error(void);
 int glis_version(void);
 
+/* Programmatic dependent launch (process-wide switch, default on; env GLIS_PDL=0 turns it off).  When on, the
+ * library's stream-ordered kernels are enqueued with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's
+ * CTAs are scheduled while its predecessor in the stream drains, run their prologue and block in
+ * `griddepcontrol.wait` until the predecessor has completed — stream semantics are unchanged (no memory access
+ * precedes the wait), only the launch latency between dependent kernels is hidden.  No reference counterpart
+ * (PyTorch launches every kernel fully serialised).  Returns the previous setting. */
+int glis_set_pdl(int on);
+
 /* ---- weight normalisation ------------------------------------------------------
  * Replaces `_WeightNormalizedConvNd.weight_norm` (common/modules/WeightNormalizedConv.py:29-38)
  * and `WeightNormalizedLinear.weight_norm` (WeightNormalizedLinear.py:30-31), plus the

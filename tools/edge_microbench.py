@@ -65,3 +65,20 @@ wgrad("D0 wgrad small=dy64 big=x3 2B", 128, 80, 80, 3, 40, 40, 64, 4, 2, 1)
 wgrad("G0 wgrad small=x64 big=dy3", 64, 80, 80, 3, 40, 40, 64, 4, 2, 1)
 wgrad("linear wgrad 12800x256 K=64", 64, 1, 1, 256, 1, 1, 12800, 1, 1, 0)
 wgrad("LIS wgrad 256x256 K=64", 64, 1, 1, 256, 1, 1, 256, 1, 1, 0)
+
+
+def wgrad_project(name, m, ca, cb, perm=(0, 0)):
+    """linear weight gradient + weight-norm projection as one kernel (glis_linear_wgrad_project)"""
+    dy = torch.randn(m, ca, device=dev); x = torch.randn(m, cb, device=dev)
+    w = torch.randn(ca, cb, device=dev) * 0.05
+    scale = torch.ones(ca, device=dev); norm = w.norm(dim=1).contiguous()
+    dw = torch.zeros(ca, cb, device=dev); ds = torch.zeros(ca, device=dev)
+    for acc in (0, 1):
+        t = timeit(lambda: L.call("glis_linear_wgrad_project", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(scale), L.ptr(norm),
+                                  L.ptr(dw), L.ptr(ds), m, ca, cb, perm[0], perm[1], acc, 0, ca, L.stream()))
+        print("%-44s %7.1f us" % (name + (" (accumulate)" if acc else ""), t))
+
+
+wgrad_project("wgrad+project 12800x256 K=64", 64, 12800, 256)
+wgrad_project("wgrad+project 12800x256 K=64 perm(512,25)", 64, 12800, 256, (512, 25))
+wgrad_project("wgrad+project LIS 256x256 K=64", 64, 256, 256)

@@ -38,6 +38,13 @@ def main():
         wh, wl = ops.split_bf16(w)
         out = torch.empty(n, ho, wo, co, device=dev)
         ep = L.Epilogue(None, 0, None, None, None)
+        out_f32, out_hi, out_lo = out, None, None
+        if os.environ.get("TCMB_EPILOGUE") == "1":    # the fused-chain forward epilogue: bias + TPReLU, pre-activation + bf16 planes
+            bias = torch.randn(co, device=dev); ta = torch.full((co,), 0.25, device=dev); tb = torch.zeros(co, device=dev)
+            pre = torch.empty_like(out)
+            out_hi = torch.empty(n, ho, wo, co, device=dev, dtype=torch.bfloat16); out_lo = torch.empty_like(out_hi)
+            ep = L.Epilogue(L.ptr(bias), L.ACT_TPRELU, L.ptr(ta), L.ptr(tb), L.ptr(pre))
+            out_f32 = None
         res = []
         ref = None
         for cl in (sys.argv[1:] or ["1", "2", "4"]):
@@ -79,7 +86,7 @@ def main():
             for prec in (L.PREC_BF16X3,):
                 def run():
                     L.call("glis_conv_forward_bf16", C.byref(g), L.ptr16(xh), L.ptr16(xl), L.ptr16(wh), L.ptr16(wl),
-                           C.byref(ep), L.ptr(out), None, None, prec, L.stream())
+                           C.byref(ep), L.ptr(out_f32), L.ptr16(out_hi), L.ptr16(out_lo), prec, L.stream())
                 for _ in range(3):
                     run()
                 torch.cuda.synchronize()
@@ -94,12 +101,13 @@ def main():
                 graph.replay()
                 e1.record()
                 torch.cuda.synchronize()
-                out.zero_()
+                chk = out if out_f32 is not None else pre
+                chk.zero_()
                 run()
                 torch.cuda.synchronize()
                 if ref is None:
-                    ref = out.clone()
-                err = ((out - ref).abs().max() / ref.abs().max()).item()
+                    ref = chk.clone()
+                err = ((chk - ref).abs().max() / ref.abs().max()).item()
                 res.append("cl%s %6.1fus (dev %.1e)" % (cl, e0.elapsed_time(e1) * 50, err))
         flop = 2.0 * n * (ho * wo if rel == L.CONV else hi * wi) * co * ci * (16 if rel == L.CONV else 16)
         print("%-28s %5.2f GFLOP | %s" % (name, flop / 1e9, "  ".join(res)))
