@@ -373,7 +373,7 @@ static int launch_linear_wgrad(const float* small, const float* big, float* G, i
 // backward, where nothing else is left to overlap with.
 constexpr int LP_NT = 256;
 // rows a warp carries at once: every x value read from shared memory feeds that many FMAs (bounded by registers)
-template <int PER>   // outputs per lane: Cb <= 32 * PER
+template <int PER, int LP_ROWS>   // outputs per lane: Cb <= 32 * PER; rows per warp and pass
 __global__ void __launch_bounds__(LP_NT, (PER <= 8 ? 3 : 1))
 linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ scale, const float* __restrict__ norm, float* __restrict__ dw,
@@ -382,7 +382,6 @@ linear_wgrad_project_kernel(const float* __restrict__ dy, const float* __restric
   pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
   pdl_wait();
   extern __shared__ __align__(16) float lp_xs[];        // [M][Cb]
-  constexpr int LP_ROWS = PER <= 8 ? 4 : (PER <= 16 ? 2 : 1);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // rows are MASTER rows o in [row_begin, row_begin + row_count): dw is written contiguously; the matching column of
   // dy is a(o) = (o % P) * C + o / P under the NHWC row permutation of glis_wn_prepare_perm
@@ -515,20 +514,27 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
+  // rows per warp and pass: as many as the registers hold (every x value read from shared memory then feeds that
+  // many FMAs) — unless the layer is so small that blocks of 8 x that many rows leave most SMs idle (the LIS linears:
+  // 256 rows; the kernel is a latency chain there, and more, shorter blocks shorten it)
+  const int rows_max = Cb <= 256 ? 4 : (Cb <= 512 ? 2 : 1);
+  const int rows = row_count >= 148 * 8 * rows_max ? rows_max : 1;
+  const int gran = 8 * rows;
   int rows_per_block = (row_count + 148 * per_sm - 1) / (148 * per_sm);
-  rows_per_block = (rows_per_block + 31) / 32 * 32;       // 8 warps x LP_ROWS rows per pass
-  if (rows_per_block < 32) rows_per_block = 32;
+  rows_per_block = (rows_per_block + gran - 1) / gran * gran;       // 8 warps x `rows` rows per pass
+  if (rows_per_block < gran) rows_per_block = gran;
   const int blocks = (row_count + rows_per_block - 1) / rows_per_block;
-#define LP_LAUNCH(PER)                                                                                              \
+#define LP_LAUNCH(PER) do { if (rows == 1) LP_LAUNCH2(PER, 1); else if (rows == 2) LP_LAUNCH2(PER, 2); else LP_LAUNCH2(PER, 4); } while (0)
+#define LP_LAUNCH2(PER, ROWS)                                                                                       \
   do {                                                                                                              \
     static bool attr_set = false;                                                                                   \
     if (!attr_set) {                                                                                                \
-      cudaError_t e = cudaFuncSetAttribute(linear_wgrad_project_kernel<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      cudaError_t e = cudaFuncSetAttribute(linear_wgrad_project_kernel<PER, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            200 * 1024);                                                             \
       GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(linear_wgrad_project): %s", cudaGetErrorString(e)); \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-    GLIS_LAUNCH((linear_wgrad_project_kernel<PER>), dim3(blocks), dim3(LP_NT), smem, (cudaStream_t)(st), dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
+    GLIS_LAUNCH((linear_wgrad_project_kernel<PER, ROWS>), dim3(blocks), dim3(LP_NT), smem, (cudaStream_t)(st), dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
                                                                   perm_p, accumulate, rows_per_block, row_begin,   \
                                                                   row_count);                                      \
   } while (0)
@@ -537,6 +543,7 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
   else if (Cb <= 512) LP_LAUNCH(16);
   else LP_LAUNCH(32);
 #undef LP_LAUNCH
+#undef LP_LAUNCH2
   GLIS_CHECK_LAUNCH("glis_linear_wgrad_project");
   return GLIS_OK;
 }

@@ -14,6 +14,17 @@ __device__ __forceinline__ int64_t master_index(int out_axis, int Cout, int Cin,
 
 constexpr int WN_NT = 256;
 
+// Float offset of quad q (4 consecutive floats) of output channel o's row; needs R % 4 == 0 and, along axis 1, T % 4 == 0.
+__device__ __forceinline__ int64_t master_quad(int out_axis, int Cout, int Cin, int T, int o, int q) {
+  if (out_axis == 0) return (int64_t)o * Cin * T + 4 * (int64_t)q;
+  const int r = 4 * q, i = r / T, t = r - i * T;
+  return ((int64_t)i * Cout + o) * T + t;
+}
+__device__ __forceinline__ bool quads_ok(const void* p0, const void* p1, const void* p2, int out_axis, int R, int T) {
+  return (R & 3) == 0 && (out_axis == 0 || (T & 3) == 0) &&
+         ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2)) & 15) == 0;
+}
+
 // One block per output channel.  NT = 1024 serves the few-channel / long-row heads (Cout = 1,
 // R = 12800), where one 256-thread block would be a long serial chain of loads.
 template <int NT>
@@ -164,8 +175,45 @@ wn_project_kernel(const float* __restrict__ G, const float* __restrict__ w, cons
   __shared__ float red[33];
   const int o = blockIdx.x;
   const int R = Cin * T;
-  float gv[PER], wv[PER], old[PER];
   float dot = 0.f;
+  if (n_slabs == 1 && quads_ok(G, w, dw, out_axis, R, T)) {
+    // 16-byte form: PER / 4 quads per thread, every load in flight before the dot product
+    constexpr int PQ = PER / 4;
+    const int R4 = R >> 2;
+    float4 gq[PQ], wq[PQ], oq[PQ];
+#pragma unroll
+    for (int u = 0; u < PQ; ++u) {
+      const int q = threadIdx.x + u * NT;
+      gq[u] = wq[u] = oq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < R4) {
+        const int64_t idx = master_quad(out_axis, Cout, Cin, T, o, q);
+        gq[u] = __ldg(reinterpret_cast<const float4*>(G + idx));
+        wq[u] = __ldg(reinterpret_cast<const float4*>(w + idx));
+        if (accumulate) oq[u] = *reinterpret_cast<const float4*>(dw + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PQ; ++u) {
+      dot = fmaf(gq[u].x, wq[u].x, dot); dot = fmaf(gq[u].y, wq[u].y, dot);
+      dot = fmaf(gq[u].z, wq[u].z, dot); dot = fmaf(gq[u].w, wq[u].w, dot);
+    }
+    dot = block_sum<NT>(dot, red, true);
+    const float n = __ldg(norm + o), s = scale ? __ldg(scale + o) : 1.f;
+    const float a = s / n, k = c * dot / (n * n);
+#pragma unroll
+    for (int u = 0; u < PQ; ++u) {
+      const int q = threadIdx.x + u * NT;
+      if (q < R4) {
+        float4 r4;
+        r4.x = oq[u].x + a * (gq[u].x - k * wq[u].x); r4.y = oq[u].y + a * (gq[u].y - k * wq[u].y);
+        r4.z = oq[u].z + a * (gq[u].z - k * wq[u].z); r4.w = oq[u].w + a * (gq[u].w - k * wq[u].w);
+        *reinterpret_cast<float4*>(dw + master_quad(out_axis, Cout, Cin, T, o, q)) = r4;
+      }
+    }
+    if (dscale && threadIdx.x == 0) dscale[o] = accumulate ? dscale[o] + dot / n : dot / n;
+    return;
+  }
+  float gv[PER], wv[PER], old[PER];
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
     const int r = threadIdx.x + u * NT;
@@ -290,11 +338,20 @@ wn_norm_multi_kernel(const __grid_constant__ WnMultiParams P) {
     const int o = b * (WN_NT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= Y.Cout) return;
     float ss = 0.f;
+    if (quads_ok(w, nullptr, nullptr, Y.out_axis, R, Y.T)) {
+      const int R4 = R >> 2;
+#pragma unroll 4
+      for (int q = lane; q < R4; q += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w + master_quad(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, q)));
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+    } else {
 #pragma unroll 8
-    for (int r = lane; r < R; r += 32) {
-      const int i = r / Y.T, t = r - i * Y.T;
-      const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
-      ss = fmaf(v, v, ss);
+      for (int r = lane; r < R; r += 32) {
+        const int i = r / Y.T, t = r - i * Y.T;
+        const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
+        ss = fmaf(v, v, ss);
+      }
     }
     ss = warp_sum(ss);
     if (lane == 0) Y.norm[o] = sqrtf(ss * Y.c + 1e-6f);
@@ -302,11 +359,20 @@ wn_norm_multi_kernel(const __grid_constant__ WnMultiParams P) {
   }
   const int o = b;                     // one block per output channel
   float ss = 0.f;
+  if (quads_ok(w, nullptr, nullptr, Y.out_axis, R, Y.T)) {   // 16-byte loads, 8 of them in flight per thread
+    const int R4 = R >> 2;
 #pragma unroll 8
-  for (int r = threadIdx.x; r < R; r += WN_NT) {
-    const int i = r / Y.T, t = r - i * Y.T;
-    const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
-    ss = fmaf(v, v, ss);
+    for (int q = threadIdx.x; q < R4; q += WN_NT) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w + master_quad(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, q)));
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+  } else {
+#pragma unroll 8
+    for (int r = threadIdx.x; r < R; r += WN_NT) {
+      const int i = r / Y.T, t = r - i * Y.T;
+      const float v = __ldg(w + master_index(Y.out_axis, Y.Cout, Y.Cin, Y.T, o, i, t));
+      ss = fmaf(v, v, ss);
+    }
   }
   ss = block_sum<WN_NT>(ss, red);
   if (threadIdx.x == 0) Y.norm[o] = sqrtf(ss * Y.c + 1e-6f);
@@ -371,6 +437,217 @@ wn_pack_multi_kernel(const __grid_constant__ WnMultiParams P) {
       if (et_hi) { et_hi[(size_t)j * Y.mat_rows + a] = h; if (et_lo) et_lo[(size_t)j * Y.mat_rows + a] = lo_; }
     }
   }
+}
+
+// ---------------------------------------------------------------------------- wide bf16 packs
+// What bounds the element-wise pack above is neither bytes nor the gather but the NUMBER OF STORE INSTRUCTIONS: it
+// issues four 2-byte stores per weight (hi / lo of both packs), one load in flight per thread.  2.1 M weights take
+// 18 us whatever the access pattern (tools/pack_microbench.py; a shared-memory-tiled variant that kept the 2-byte
+// stores had the same floor).  Here every store carries FOUR bf16 (8 bytes per lane), every load is 16 bytes, and a
+// thread has 4..16 loads in flight:
+//   phase F (the pack whose innermost axis is the master's inner channel axis): a thread owns 4 consecutive inner
+//            channels x T taps = 4T contiguous floats, and writes one bf16 quad per tap and plane;
+//   phase C (the pack whose innermost axis is the master's OUTER axis): a thread owns 4 consecutive outer channels
+//            x T taps of one inner channel (four T-float rows, a master row pitch apart) — or, for one-tap (linear)
+//            layers, a 4 x 4 block that it transposes in registers.
+// No shared memory; master order [outer][inner][T]: out_axis 0 -> (outer, inner) = (Cout, Cin), 1 -> (Cin, Cout).
+struct WnWideItem { int layer, phase; };     // phase 0 = F, 1 = C
+struct WnWideParams {
+  int n_items;
+  int block_begin[2 * WN_MULTI_MAX + 1];
+  WnWideItem item[2 * WN_MULTI_MAX];
+  glis_wn_layer_t L[WN_MULTI_MAX];
+};
+
+static bool wn_wide_applies(const glis_wn_layer_t& Y) {
+  if (Y.pack_io || Y.pack_oi || Y.mat_hi || Y.matt_hi) return false;      // fp32 packs / matrix packs: element-wise kernel
+  if (!Y.fwd_hi && !Y.bwd_hi) return false;
+  if ((Y.Cout & 3) || (Y.Cin & 3)) return false;                             // bf16 quads along either axis
+  if (Y.T == 1 && ((Y.Cout & 7) || (Y.Cin & 7))) return false;               // linear layers: bf16 octets
+  if (Y.T != 1 && Y.T != 4 && Y.T != 9 && Y.T != 16) return false;           // (registers: 4 T floats per thread)
+  if ((reinterpret_cast<uintptr_t>(Y.w) & 15) != 0) return false;            // 16-byte loads
+  if (((reinterpret_cast<uintptr_t>(Y.fwd_hi) | reinterpret_cast<uintptr_t>(Y.fwd_lo) | reinterpret_cast<uintptr_t>(Y.bwd_hi) |
+        reinterpret_cast<uintptr_t>(Y.bwd_lo)) & 15) != 0) return false;     // 8- / 16-byte stores
+  return true;
+}
+
+// threads of one phase of a layer
+static int64_t wn_wide_threads(const glis_wn_layer_t& Y, int phase) {
+  const int64_t pairs = (int64_t)Y.Cout * Y.Cin;
+  if (Y.T == 1) return phase == 0 ? pairs / 8 : pairs / 32;   // 8 inner channels per thread / an 8 (outer) x 4 (inner) block
+  return pairs / 4;
+}
+
+__device__ __forceinline__ void store_quad(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t e, const float (&x)[4]) {
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sm100::split_bf16(x[k], h[k], l[k]);
+  uint2 qh, ql;
+  qh.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+  qh.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+  *reinterpret_cast<uint2*>(hi + e) = qh;
+  if (lo) {
+    ql.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    ql.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(lo + e) = ql;
+  }
+}
+
+// eight consecutive bf16 per plane: one 16-byte store each
+__device__ __forceinline__ void store_octet(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t e, const float (&x)[8]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    sm100::split_bf16(x[2 * k], h0, l0);
+    sm100::split_bf16(x[2 * k + 1], h1, l1);
+    ph[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    pl[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi + e) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + e) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+__device__ __forceinline__ float wn_factor(const glis_wn_layer_t& Y, int o_master) {
+  return (Y.scale ? __ldg(Y.scale + o_master) : 1.f) / __ldg(Y.norm + o_master);
+}
+
+template <int T>
+__device__ __forceinline__ void wn_wide_phase_f(const glis_wn_layer_t& Y, int64_t g) {
+  const int n_outer = Y.out_axis == 0 ? Y.Cout : Y.Cin, n_inner = Y.out_axis == 0 ? Y.Cin : Y.Cout;
+  __nv_bfloat16* d_hi = (__nv_bfloat16*)(Y.out_axis == 0 ? Y.fwd_hi : Y.bwd_hi);
+  __nv_bfloat16* d_lo = (__nv_bfloat16*)(Y.out_axis == 0 ? Y.fwd_lo : Y.bwd_lo);
+  if (T == 1) {   // linear layers: a converting copy, eight inner channels per thread
+    const int o_inner = n_inner >> 3;
+    const int outer = (int)(g / o_inner), inner = (int)(g - (int64_t)outer * o_inner) * 8;
+    if (outer >= n_outer) return;
+    const int m_outer = Y.out_axis == 0 ? master_channel(outer, Y.perm_c, Y.perm_p) : outer;
+    const float4* src = reinterpret_cast<const float4*>(Y.w + (size_t)m_outer * n_inner + inner);
+    const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
+    float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float a_row = Y.out_axis == 0 ? wn_factor(Y, m_outer) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] *= Y.out_axis == 0 ? a_row : wn_factor(Y, inner + k);
+    store_octet(d_hi, d_lo, (size_t)outer * n_inner + inner, x);
+    return;
+  }
+  const int q_inner = n_inner >> 2;
+  const int outer = (int)(g / q_inner), inner = (int)(g - (int64_t)outer * q_inner) * 4;
+  if (outer >= n_outer) return;
+  const int m_outer = Y.out_axis == 0 ? master_channel(outer, Y.perm_c, Y.perm_p) : outer;
+  // 4 T contiguous floats, 16-byte aligned (inner and n_inner are multiples of 4)
+  const float4* src = reinterpret_cast<const float4*>(Y.w + ((size_t)m_outer * n_inner + inner) * T);
+  float v[4 * T];
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const float4 q = __ldg(src + j);
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+  }
+  float a[4];
+  if (Y.out_axis == 0) {
+    a[0] = a[1] = a[2] = a[3] = wn_factor(Y, m_outer);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = wn_factor(Y, inner + k);
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = v[k * T + t] * a[k];
+    store_quad(d_hi, d_lo, ((size_t)t * n_outer + outer) * n_inner + inner, x);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void wn_wide_phase_c(const glis_wn_layer_t& Y, int64_t g) {
+  const int n_outer = Y.out_axis == 0 ? Y.Cout : Y.Cin, n_inner = Y.out_axis == 0 ? Y.Cin : Y.Cout;
+  const int q_outer = n_outer >> 2;
+  __nv_bfloat16* c_hi = (__nv_bfloat16*)(Y.out_axis == 0 ? Y.bwd_hi : Y.fwd_hi);
+  __nv_bfloat16* c_lo = (__nv_bfloat16*)(Y.out_axis == 0 ? Y.bwd_lo : Y.fwd_lo);
+  if (T == 1) {
+    // 8 x 4 block: rows outer .. outer + 7 (pack order), columns inner .. inner + 3; transposed in registers
+    const int q_inner = n_inner >> 2, o_outer = n_outer >> 3;
+    const int i4 = (int)(g / o_outer), outer = (int)(g - (int64_t)i4 * o_outer) * 8, inner = i4 * 4;
+    if (i4 >= q_inner) return;
+    float m[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int m_outer = Y.out_axis == 0 ? master_channel(outer + k, Y.perm_c, Y.perm_p) : outer + k;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(Y.w + (size_t)m_outer * n_inner + inner));
+      const float a = Y.out_axis == 0 ? wn_factor(Y, m_outer) : 1.f;
+      m[k][0] = q.x * a; m[k][1] = q.y * a; m[k][2] = q.z * a; m[k][3] = q.w * a;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = Y.out_axis == 1 ? wn_factor(Y, inner + j) : 1.f;
+      const float x[8] = {m[0][j] * a, m[1][j] * a, m[2][j] * a, m[3][j] * a, m[4][j] * a, m[5][j] * a, m[6][j] * a, m[7][j] * a};
+      store_octet(c_hi, c_lo, (size_t)(inner + j) * n_outer + outer, x);
+    }
+    return;
+  }
+  const int inner = (int)(g / q_outer), outer = (int)(g - (int64_t)inner * q_outer) * 4;
+  if (inner >= n_inner) return;
+  float v[4][T], a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m_outer = Y.out_axis == 0 ? master_channel(outer + k, Y.perm_c, Y.perm_p) : outer + k;
+    const float* src = Y.w + ((size_t)m_outer * n_inner + inner) * T;
+    if (T % 4 == 0) {
+#pragma unroll
+      for (int t = 0; t < T; t += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src + t));
+        v[k][t] = q.x; v[k][t + 1] = q.y; v[k][t + 2] = q.z; v[k][t + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t) v[k][t] = __ldg(src + t);
+    }
+    a[k] = Y.out_axis == 0 ? wn_factor(Y, m_outer) : 0.f;
+  }
+  if (Y.out_axis == 1) a[0] = a[1] = a[2] = a[3] = wn_factor(Y, inner);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float x[4] = {v[0][t] * a[0], v[1][t] * a[1], v[2][t] * a[2], v[3][t] * a[3]};
+    store_quad(c_hi, c_lo, ((size_t)t * n_inner + inner) * n_outer + outer, x);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void wn_wide_dispatch(const glis_wn_layer_t& Y, int phase, int64_t g) {
+  if (phase == 0) wn_wide_phase_f<T>(Y, g); else wn_wide_phase_c<T>(Y, g);
+}
+
+__global__ void __launch_bounds__(WN_NT)
+wn_pack_wide_kernel(const __grid_constant__ WnWideParams P) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  int it = 0;
+  while (it + 1 < P.n_items && (int)blockIdx.x >= P.block_begin[it + 1]) ++it;
+  const glis_wn_layer_t& Y = P.L[P.item[it].layer];
+  const int phase = P.item[it].phase;
+  const int64_t g = (int64_t)(blockIdx.x - P.block_begin[it]) * WN_NT + threadIdx.x;
+  switch (Y.T) {
+    case 1: wn_wide_dispatch<1>(Y, phase, g); break;
+    case 4: wn_wide_dispatch<4>(Y, phase, g); break;
+    case 9: wn_wide_dispatch<9>(Y, phase, g); break;
+    case 16: wn_wide_dispatch<16>(Y, phase, g); break;
+    default: break;   // (wn_wide_applies admits no other tap count)
+  }
+}
+
+// Appends the phases of layer `l` of Q (already stored in Q.L[l]) to the launch list; returns the new block count.
+static int wn_wide_add(WnWideParams& Q, int l, int blocks) {
+  const glis_wn_layer_t& Y = Q.L[l];
+  for (int phase = 0; phase < 2; ++phase) {
+    const bool direct_is_fwd = Y.out_axis == 0;
+    const void* dst = phase == 0 ? (direct_is_fwd ? Y.fwd_hi : Y.bwd_hi) : (direct_is_fwd ? Y.bwd_hi : Y.fwd_hi);
+    if (!dst) continue;
+    Q.item[Q.n_items].layer = l; Q.item[Q.n_items].phase = phase;
+    Q.block_begin[Q.n_items++] = blocks;
+    blocks += (int)((wn_wide_threads(Y, phase) + WN_NT - 1) / WN_NT);
+  }
+  return blocks;
 }
 
 // ---------------------------------------------------------------------------- multi-tensor projection
@@ -478,6 +755,14 @@ extern "C" int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void*
   cudaStream_t st = (cudaStream_t)stream;
   for (int base = 0; base < n; base += WN_MULTI_MAX) {
     WnMultiParams P;
+    WnWideParams Q;
+    Q.n_items = 0;
+    int qb = 0, ql = 0;
+    static int wide_cfg = -1;
+    if (wide_cfg < 0) {
+      const char* e = getenv("GLIS_PACK_WIDE");   // 0: every pack on the element-wise kernel
+      wide_cfg = (e && atoi(e) == 0) ? 0 : 1;
+    }
     P.n = n - base < WN_MULTI_MAX ? n - base : WN_MULTI_MAX;
     int nb = 0, pb = 0;
     bool any_pack = false, any_norm = false;
@@ -501,7 +786,10 @@ extern "C" int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void*
         any_norm = true;
       }
       P.pack_block_begin[l] = pb;
-      if (Y.pack_io || Y.pack_oi || Y.fwd_hi || Y.bwd_hi || mats) {
+      if (wide_cfg && wn_wide_applies(Y)) {
+        Q.L[ql] = Y;
+        qb = wn_wide_add(Q, ql++, qb);
+      } else if (Y.pack_io || Y.pack_oi || Y.fwd_hi || Y.bwd_hi || mats) {
         const int64_t total = (int64_t)Y.T * Y.Cin * Y.Cout;
         pb += (int)((total + WN_PACK_PER_BLOCK - 1) / WN_PACK_PER_BLOCK);
         any_pack = true;
@@ -517,6 +805,11 @@ extern "C" int glis_wn_prepare_multi(const glis_wn_layer_t* layers, int n, void*
     if (any_pack && pb > 0) {
       GLIS_LAUNCH(wn_pack_multi_kernel, dim3(pb), dim3(WN_NT), 0, (cudaStream_t)(st), P);
       GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(pack)");
+    }
+    if (Q.n_items > 0) {
+      Q.block_begin[Q.n_items] = qb;
+      GLIS_LAUNCH(wn_pack_wide_kernel, dim3(qb), dim3(WN_NT), 0, (cudaStream_t)(st), Q);
+      GLIS_CHECK_LAUNCH("glis_wn_prepare_multi(wide pack)");
     }
   }
   return GLIS_OK;
@@ -570,6 +863,21 @@ extern "C" int glis_wn_prepare_bf16_perm(const float* w, const float* scale, int
   GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(norm)");
   if (fwd_hi || bwd_hi) {
     const int64_t total = (int64_t)T * Cin * Cout;
+    {
+      glis_wn_layer_t Y = {};
+      Y.w = w; Y.scale = scale; Y.norm = norm; Y.fwd_hi = fwd_hi; Y.fwd_lo = fwd_lo; Y.bwd_hi = bwd_hi; Y.bwd_lo = bwd_lo;
+      Y.out_axis = out_axis; Y.Cout = Cout; Y.Cin = Cin; Y.T = T; Y.perm_c = perm_c; Y.perm_p = perm_p; Y.c = c;
+      const char* e = getenv("GLIS_PACK_WIDE");
+      if (!(e && atoi(e) == 0) && wn_wide_applies(Y) && total < ((int64_t)1 << 31)) {
+        WnWideParams Q;
+        Q.n_items = 0; Q.L[0] = Y;
+        const int qb = wn_wide_add(Q, 0, 0);
+        Q.block_begin[Q.n_items] = qb;
+        GLIS_LAUNCH(wn_pack_wide_kernel, dim3(qb), dim3(WN_NT), 0, st, Q);
+        GLIS_CHECK_LAUNCH("glis_wn_prepare_bf16(wide pack)");
+        return GLIS_OK;
+      }
+    }
     const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
     if (total < ((int64_t)1 << 31))
       GLIS_LAUNCH((wn_pack_bf16_kernel<uint32_t>), dim3(blocks), dim3(256), 0, (cudaStream_t)(st), w, scale, norm, out_axis, Cout, Cin, T, (__nv_bfloat16*)fwd_hi,

@@ -940,6 +940,16 @@ def _image_side_wgrad(spec, x_shape, dy_shape):
     return (n, ho, wo, cout, cin) if ok else None
 
 
+def _image_side_wgrad_geom(n, hs, ws, c_img, ca):
+    """Geometry of the image-side weight gradient as a 1x1 product over pixels.  A 1x1 product has no spatial
+    structure, so the pixel list is presented as rows of 64: the kernel's K tiles are then 64 full rows (a 40-pixel
+    image row would fill 40 of 48)."""
+    pix = n * hs * ws
+    if pix % 64 == 0:
+        return _spec_1x1().geom(L.CONV, pix // 64, 1, 64, 16 * c_img, 1, 64, ca)
+    return _spec_1x1().geom(L.CONV, n, hs, ws, 16 * c_img, hs, ws, ca)
+
+
 def consumes_planes_only(spec, weight, x_shape, followed_by_tprelu):
     """True when a WN layer with this ``spec`` / ``weight`` reads an input of (NCHW) shape ``x_shape`` through
     its bf16 planes ONLY — forward on tcgen05 (or as the image-side "fold" product) and weight gradient on
@@ -1029,7 +1039,7 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
             g_w = g
             if isw is not None:
                 n_, hs, ws, ca, c_img = isw
-                g_w = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
+                g_w = _image_side_wgrad_geom(n_, hs, ws, c_img, ca)
             n_slabs = int(L.load().glis_wgrad_tc_splits(C.byref(g_w)))
             if n_slabs > 0:
                 slabs = torch.empty((n_slabs, weight.numel()), device=weight.device, dtype=torch.float32)
@@ -1074,7 +1084,7 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                 graw.zero_()
             if isw is not None:
                 n_, hs, ws, ca, c_img = isw
-                g1 = _spec_1x1().geom(L.CONV, n_, hs, ws, 16 * c_img, hs, ws, ca)
+                g1 = _image_side_wgrad_geom(n_, hs, ws, c_img, ca)
                 with L.timed(tag + " tc (image side)"):
                     L.call("glis_conv_wgrad_bf16", C.byref(g1), L.ptr16(sp[0]), L.ptr16(sp[1]), L.ptr16(bp[0]),
                            L.ptr16(bp[1]), L.ptr(graw), prec, L.stream())
