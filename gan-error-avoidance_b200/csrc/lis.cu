@@ -42,12 +42,29 @@ struct LisParams {
 
 // This CTA's 32 columns of a [code][code] pack -> ws[k][32], every load of a thread in flight at once (the
 // kernel is latency-bound: a k-loop that fetched its weights from L2 as it went took 4x longer).
-__device__ __forceinline__ void lis_stage_pack(float* __restrict__ ws, const float* __restrict__ P, int code, int n0,
-                                               int tid) {
-  for (int i = tid; i < code * (LIS_COLS / 4); i += LIS_NT) {
-    const int k = i >> 3, c4 = i & 7;
-    *reinterpret_cast<float4*>(ws + k * LIS_COLS + 4 * c4) =
-        __ldg(reinterpret_cast<const float4*>(P + (size_t)k * code + n0) + c4);
+__device__ __forceinline__ void lis_stage_packs(float* __restrict__ ws, float* __restrict__ ws2, const float* __restrict__ P1,
+                                                const float* __restrict__ P2, int code, int n0, int tid) {
+  // code <= 256: at most 8 quads per thread and pack, ALL of BOTH packs requested before the first one is stored (a
+  // load -> store loop whose trip count the compiler does not know serialises on the load latency, and the second
+  // pack used to be fetched only after the first product: one more round trip on a kernel that is nothing but latency)
+  constexpr int Q = LIS_MAX_CODE * (LIS_COLS / 4) / LIS_NT;
+  const int total = code * (LIS_COLS / 4);
+  float4 v[Q], v2[Q];
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    const int i = tid + u * LIS_NT;
+    if (i < total) {
+      v[u] = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)(i >> 3) * code + n0) + (i & 7));
+      v2[u] = __ldg(reinterpret_cast<const float4*>(P2 + (size_t)(i >> 3) * code + n0) + (i & 7));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    const int i = tid + u * LIS_NT;
+    if (i < total) {
+      *reinterpret_cast<float4*>(ws + (i >> 3) * LIS_COLS + 4 * (i & 7)) = v[u];
+      *reinterpret_cast<float4*>(ws2 + (i >> 3) * LIS_COLS + 4 * (i & 7)) = v2[u];
+    }
   }
 }
 
@@ -75,7 +92,8 @@ lis_chain_kernel(const LisParams P) {
   extern __shared__ __align__(16) float lis_smem[];
   float* xs = lis_smem;                                          // [16][code + 4] input row tile, later the full intermediate
   float* ws = xs + LIS_ROWS * (LIS_MAX_CODE + 4);                // [code][32] this CTA's columns of the current pack
-  float* slice = ws + LIS_MAX_CODE * LIS_COLS;                   // [16][32] this CTA's columns of the intermediate
+  float* ws2 = ws + LIS_MAX_CODE * LIS_COLS;                     // [code][32] ... and of the second pack, fetched up front
+  float* slice = ws2 + LIS_MAX_CODE * LIS_COLS;                  // [16][32] this CTA's columns of the intermediate
   float* red_a = slice + LIS_ROWS * LIS_COLS;                    // [16][32] TPReLU parameter partial sums
   float* red_b = red_a + LIS_ROWS * LIS_COLS;
   cg::cluster_group cluster = cg::this_cluster();
@@ -89,7 +107,7 @@ lis_chain_kernel(const LisParams P) {
   const bool row_ok = m < P.B;
 
   // ---- first pack slice + input row tile (zero rows beyond the batch)
-  lis_stage_pack(ws, P.p1, code, r * LIS_COLS, tid);
+  lis_stage_packs(ws, ws2, P.p1, P.p2, code, r * LIS_COLS, tid);
   for (int i = tid; i < LIS_ROWS * (code >> 2); i += LIS_NT) {
     const int rr = i / (code >> 2), c4 = i - rr * (code >> 2);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -126,7 +144,6 @@ lis_chain_kernel(const LisParams P) {
     if (row_ok && P.mid) P.mid[(size_t)m * code + c] = mid[j];
   }
   __syncthreads();
-  lis_stage_pack(ws, P.p2, code, r * LIS_COLS, tid);     // second pack slice: in flight under the cluster exchange
   if (BACKWARD && P.da && tid < LIS_COLS) {
     // TPReLU parameter gradients: da_raw += sum g*t over the negative side (only while 0 <= a_raw <= 1: the clamp
     // passes no gradient outside), db += (1 - a) * sum g over the negative side
@@ -143,16 +160,30 @@ lis_chain_kernel(const LisParams P) {
   // ---- every CTA assembles the full intermediate row tile from its neighbours' slices
   cluster.sync();
   const int cs = (int)cluster.num_blocks();
-  for (int i = tid; i < LIS_ROWS * code; i += LIS_NT) {
-    const int rr = i / code, k = i - rr * code;
-    const int src = k / LIS_COLS;
-    const float* remote = src < cs ? cluster.map_shared_rank(slice, src) : slice;
-    xs[rr * ld + k] = remote[rr * LIS_COLS + (k - src * LIS_COLS)];
+  {
+    // 16 x code floats per CTA, all distributed-shared-memory loads of a thread in flight together
+    constexpr int G = LIS_ROWS * LIS_MAX_CODE / LIS_NT;
+    float g[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int i = tid + u * LIS_NT;
+      if (i < LIS_ROWS * code) {
+        const int rr = i / code, k = i - rr * code;
+        const int src = k / LIS_COLS;
+        const float* remote = src < cs ? cluster.map_shared_rank(slice, src) : slice;
+        g[u] = remote[rr * LIS_COLS + (k - src * LIS_COLS)];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int i = tid + u * LIS_NT;
+      if (i < LIS_ROWS * code) { const int rr = i / code, k = i - rr * code; xs[rr * ld + k] = g[u]; }
+    }
   }
   cluster.sync();     // all slices read (nobody may leave or overwrite before that), xs complete
 
   // ---- second product + residual
-  lis_dot(xs, ld, ws, code, row, cp, acc);
+  lis_dot(xs, ld, ws2, code, row, cp, acc);
   if (row_ok) {
     float2 res = __ldg(reinterpret_cast<const float2*>(P.x + (size_t)m * code + col0));
     if (!BACKWARD && P.bias2) { res.x += __ldg(P.bias2 + col0); res.y += __ldg(P.bias2 + col0 + 1); }
@@ -164,7 +195,7 @@ static int lis_launch(const LisParams& P, bool backward, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(P.code / LIS_COLS, (P.B + LIS_ROWS - 1) / LIS_ROWS, 1);
   cfg.blockDim = dim3(LIS_NT);
-  const size_t smem = sizeof(float) * (LIS_ROWS * (LIS_MAX_CODE + 4) + LIS_MAX_CODE * LIS_COLS + 3 * LIS_ROWS * LIS_COLS);
+  const size_t smem = sizeof(float) * (LIS_ROWS * (LIS_MAX_CODE + 4) + 2 * LIS_MAX_CODE * LIS_COLS + 3 * LIS_ROWS * LIS_COLS);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(lis_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -16,6 +16,8 @@
 //     in 64-row chunks staged in shared memory; every output has one owner, no atomics.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -191,12 +193,86 @@ bool is_head_dgrad_geom(const glis_geom_t* g) {
          g->dil_h == 1 && g->dil_w == 1 && g->Ho == g->KH && g->Wo == g->KW;
 }
 
+// ---- the two degenerate shapes of a one-channel head (D's final conv and its data gradient), as what they are: a
+// matrix-vector product and an outer product.  The tiled kernel above spent 12.7 / 16.5 us on them (6.5 MB each at
+// batch 128) — on the critical path of both backward passes, with the machine otherwise idle.
+constexpr int HV_NT = 256;
+
+// out[m] = sum_k X[m][k] * w[k] (+ bias): one block per row, every load of a thread in flight before the sum
+__global__ void __launch_bounds__(HV_NT)
+head_gemv_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                 int K) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  __shared__ float red[33];
+  const float* row = X + (size_t)blockIdx.x * K;
+  float acc = 0.f;
+  if ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const int K4 = K >> 2;
+#pragma unroll 4
+    for (int q = threadIdx.x; q < K4; q += HV_NT) {
+      const float4 a = __ldg(r4 + q), b = __ldg(w4 + q);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+  } else {
+    for (int k = threadIdx.x; k < K; k += HV_NT) acc = fmaf(__ldg(row + k), __ldg(w + k), acc);
+  }
+  acc = block_sum<HV_NT>(acc, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc + (bias ? __ldg(bias) : 0.f);
+}
+
+// out[m][n] = x[m] * w[n]
+__global__ void __launch_bounds__(HV_NT)
+head_outer_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int M, int N) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+  pdl_wait();
+  const int64_t total = (int64_t)M * N;
+  if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    const int N4 = N >> 2;
+    const int64_t total4 = total >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * HV_NT + threadIdx.x; q < total4; q += (int64_t)gridDim.x * HV_NT) {
+      const int m = (int)(q / N4), n4 = (int)(q - (int64_t)m * N4);
+      const float xv = __ldg(x + m);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + n4);
+      reinterpret_cast<float4*>(out)[q] = make_float4(xv * wv.x, xv * wv.y, xv * wv.z, xv * wv.w);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * HV_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * HV_NT) {
+      const int m = (int)(i / N);
+      out[i] = __ldg(x + m) * __ldg(w + (i - (int64_t)m * N));
+    }
+  }
+}
+
 // Returns GLIS_E_UNSUPPORTED when the generic kernel should run instead.
 int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpack, const glis_epilogue_t* ep,
                         float* out, cudaStream_t st) {
   int M = g->N, N = g->Co, K = g->KH * g->KW * g->Ci;
   if (is_head_dgrad_geom(g)) { N = g->KH * g->KW * g->Co; K = 1; }
   if (M > 4096) return GLIS_E_UNSUPPORTED;
+  {
+    const bool plain = ep->act == GLIS_ACT_NONE && !ep->preact && !ep->out_hi;
+    static int head_fast = -1;
+    if (head_fast < 0) {
+      const char* e = getenv("GLIS_HEAD_FAST");   // 0: the tiled kernel for the one-channel head shapes too
+      head_fast = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (head_fast && plain && N == 1 && K >= 256) {
+      GLIS_LAUNCH(head_gemv_kernel, dim3(M), dim3(HV_NT), 0, st, in, wpack, ep->bias, out, K);
+      GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, head)");
+      return GLIS_OK;
+    }
+    if (head_fast && plain && K == 1 && !ep->bias && N >= 256) {
+      int blocks = (int)(((int64_t)M * N / 4 + HV_NT - 1) / HV_NT);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      if (blocks < 1) blocks = 1;
+      GLIS_LAUNCH(head_outer_kernel, dim3(blocks), dim3(HV_NT), 0, st, in, wpack, out, M, N);
+      GLIS_CHECK_LAUNCH("glis_conv_forward(fp32, head data gradient)");
+      return GLIS_OK;
+    }
+  }
   const int nk = (K + LC_KC - 1) / LC_KC;
   const int gy = (M + LC_TM - 1) / LC_TM;
   // wide tiles once N alone gives every SM a block; then spread over K until ~3 blocks per SM

@@ -216,7 +216,7 @@ class OverlappedGradSync(object):
         ready.record()                      # gradients of this bucket are complete on the current stream ...
         self.side.wait_event(ready)
         from . import ops                   # ... and on the other one of (main, weight-gradient side stream)
-        for other in (ops.Overlap.main_stream(), ops.Overlap.side_stream()):
+        for other in [ops.Overlap.main_stream()] + ops.Overlap.side_streams():
             if other is not None and other != torch.cuda.current_stream():
                 ev = torch.cuda.Event()
                 ev.record(other)

@@ -834,6 +834,26 @@ class Overlap(object):
             cls._side = torch.cuda.Stream()
         return cls._side
 
+    # A second side stream for LIGHT weight gradients (the LIS linears: a few dozen blocks, ~7 us): at the end of
+    # G's backward they would otherwise queue behind the generator head's 13 MB weight gradient although they only
+    # need a fraction of the machine — and that queue is the tail of the iteration.
+    light_enabled = os.environ.get("GLIS_LIGHT_STREAM", "1") != "0"
+    _light = None
+    _dirty_light = False
+
+    @classmethod
+    def light_stream(cls):
+        if cls._light is None:
+            cls._light = torch.cuda.Stream()
+        return cls._light
+
+    @classmethod
+    def side_streams(cls):
+        """Every stream weight gradients may have been enqueued on since ``begin()``."""
+        if not cls._on:
+            return []
+        return [cls._side] + ([cls._light] if cls._dirty_light else [])
+
     _aux = []
 
     @classmethod
@@ -849,17 +869,22 @@ class Overlap(object):
             return
         cls.stream()
         cls._main = torch.cuda.current_stream()
-        cls._on, cls._dirty = True, False
+        cls._on, cls._dirty, cls._dirty_light = True, False, False
 
     @classmethod
-    def run(cls, fn, keep=()):
+    def run(cls, fn, keep=(), light=False):
+        light = light and cls.light_enabled
+        side = cls.light_stream() if light else cls._side
         ready = torch.cuda.Event()
         ready.record(cls._main)               # everything the side work reads has been enqueued
-        cls._side.wait_event(ready)
-        with torch.cuda.stream(cls._side):
+        side.wait_event(ready)
+        if light:
+            cls._dirty_light = True           # (before fn: gradient hooks fired inside it ask side_streams())
+        with torch.cuda.stream(side):
             fn()
         cls._keep.append(keep)
-        cls._dirty = True
+        if not light:
+            cls._dirty = True
 
     @classmethod
     def queue_projection(cls, graw, w, scale, norm, out_axis, cout, cin, t, c, dw, dscale, acc):
@@ -889,8 +914,10 @@ class Overlap(object):
         cls.flush_projections()
         if cls._dirty:
             cls._main.wait_stream(cls._side)
+        if cls._dirty_light:
+            cls._main.wait_stream(cls._light)
         cls._keep = []
-        cls._on, cls._dirty = False, False
+        cls._on, cls._dirty, cls._dirty_light = False, False, False
 
 
 class PlanesOnly(object):
@@ -1118,7 +1145,8 @@ def _layer_backward(spec, pw, xc, dyc, dy_planes, need_dx, need_dw, need_dscale,
                 _touch_hooks(weight, scale)
 
         if fork:
-            Overlap.run(weight_gradient, keep=(small, big, sp, bp, wc, sc, graw, slabs))
+            Overlap.run(weight_gradient, keep=(small, big, sp, bp, wc, sc, graw, slabs),
+                        light=fused_lin and cout * cin <= (1 << 18))
         else:
             weight_gradient()
         if not acc:

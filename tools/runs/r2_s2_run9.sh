@@ -1,0 +1,7 @@
+# round 2, session 2, call 9: light side stream for the LIS weight gradients, image-side weight gradient over 64-pixel rows
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/s2_r9_pytest.log 2>&1; tail -3 gpurun_out/s2_r9_pytest.log
+for v in 1 0 1 0; do
+  GLIS_LIGHT_STREAM=$v timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('GLIS_LIGHT_STREAM=$v  %.4f ms  e2e %.4f ms  %d launches' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['details']['launches_per_iteration']))" | tee -a gpurun_out/s2_r9_bench.log
+done
+python tools/wgrad_microbench.py > gpurun_out/s2_wgrad_mb.log 2>&1; cat gpurun_out/s2_wgrad_mb.log | tail -12
