@@ -108,11 +108,26 @@ lis_chain_kernel(const LisParams P) {
 
   // ---- first pack slice + input row tile (zero rows beyond the batch)
   lis_stage_packs(ws, ws2, P.p1, P.p2, code, r * LIS_COLS, tid);
-  for (int i = tid; i < LIS_ROWS * (code >> 2); i += LIS_NT) {
-    const int rr = i / (code >> 2), c4 = i - rr * (code >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m0 + rr < P.B) v = __ldg(reinterpret_cast<const float4*>(P.x + (size_t)(m0 + rr) * code) + c4);
-    *reinterpret_cast<float4*>(xs + rr * ld + 4 * c4) = v;
+  {
+    constexpr int XQ = LIS_ROWS * (LIS_MAX_CODE / 4) / LIS_NT;     // quads of the row tile per thread, all in flight
+    float4 xv[XQ];
+#pragma unroll
+    for (int u = 0; u < XQ; ++u) {
+      const int i = tid + u * LIS_NT;
+      xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < LIS_ROWS * (code >> 2)) {
+        const int rr = i / (code >> 2), c4 = i - rr * (code >> 2);
+        if (m0 + rr < P.B) xv[u] = __ldg(reinterpret_cast<const float4*>(P.x + (size_t)(m0 + rr) * code) + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < XQ; ++u) {
+      const int i = tid + u * LIS_NT;
+      if (i < LIS_ROWS * (code >> 2)) {
+        const int rr = i / (code >> 2), c4 = i - rr * (code >> 2);
+        *reinterpret_cast<float4*>(xs + rr * ld + 4 * c4) = xv[u];
+      }
+    }
   }
   __syncthreads();
 

@@ -22,17 +22,9 @@
 
 #include "common.cuh"
 #include "sm100.cuh"
+#include "tc_common.cuh"
 
 namespace glis {
-
-using namespace sm100;
-
-constexpr int TC_BM = 128;       // channels per CTA (UMMA M)
-constexpr int TC_BK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int TC_EPI_WARPS = 16; // 4 per TMEM lane quarter
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // TMA warp, MMA warp, epilogue warps
-constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_DEFAULT_CLUSTER = 1;
 
 struct TcConvParams {
   glis_geom_t g;
@@ -60,58 +52,6 @@ struct TcConvParams {
   unsigned long long* trace;  // optional timeline buffer (GLIS_TC_TRACE): CTA 0 logs globaltimer per event
   int debug;         // GLIS_TC_DEBUG bits (profiling experiments only): 1 = no stores, 2 = no MMA, 4 = no x loads
 };
-
-struct TcPhase { int ry, rx, Hq, Wq, nth, ntw, py, px; };
-
-__device__ __forceinline__ TcPhase tc_phase(const glis_geom_t& g, int z) {
-  TcPhase p;
-  if (g.relation == GLIS_CONV) {
-    p.ry = p.rx = 0; p.Hq = g.Ho; p.Wq = g.Wo; p.nth = g.KH; p.ntw = g.KW; p.py = p.px = 0;
-  } else {
-    p.py = z / g.stride_w; p.px = z % g.stride_w;
-    p.ry = ((p.py - g.pad_h) % g.stride_h + g.stride_h) % g.stride_h;
-    p.rx = ((p.px - g.pad_w) % g.stride_w + g.stride_w) % g.stride_w;
-    p.Hq = g.Ho > p.ry ? (g.Ho - p.ry + g.stride_h - 1) / g.stride_h : 0;
-    p.Wq = g.Wo > p.rx ? (g.Wo - p.rx + g.stride_w - 1) / g.stride_w : 0;
-    p.nth = g.KH > p.py ? (g.KH - p.py + g.stride_h - 1) / g.stride_h : 0;
-    p.ntw = g.KW > p.px ? (g.KW - p.px + g.stride_w - 1) / g.stride_w : 0;
-  }
-  return p;
-}
-
-__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
-  int q = a / b;
-  return (a % b != 0 && a < 0) ? q - 1 : q;
-}
-
-// Epilogue of one 32-column accumulator chunk for this lane's channel, specialised at compile
-// time so that the per-column code is a handful of predicated instructions.  `rel` = element
-// offsets of the chunk's columns relative to the tile origin (shared memory, built once per CTA:
-// every tile of a launch has the same shape), `base` = the tile origin + this lane's channel.
-template <int ACT, bool PREACT, bool F32, bool PLANES>
-__device__ __forceinline__ void tc_epilogue_chunk(const uint32_t (&v)[32], int nvalid, long long base,
-                                                  const uint32_t* __restrict__ rel, float bias, float ta,
-                                                  float tb, float* __restrict__ preact, float* __restrict__ out_f32,
-                                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < nvalid) {
-      const long long off = base + rel[j];
-      const float y = __uint_as_float(v[j]) + bias;
-      if (PREACT) preact[off] = y;
-      float o = y;
-      if (ACT == GLIS_ACT_TPRELU) { const float t = y - tb; o = (t > 0.f ? t : ta * t) + tb; }
-      if (ACT == GLIS_ACT_SIGMOID) o = 1.f / (1.f + __expf(-y));
-      if (F32) out_f32[off] = o;
-      if (PLANES) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(o, hi, lo);
-        out_hi[off] = hi;
-        if (out_lo) out_lo[off] = lo;
-      }
-    }
-  }
-}
 
 // One output tile of the persistent kernel.
 struct TcTile {
@@ -606,9 +546,16 @@ int tc_conv_halo_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const 
                          const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                          __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
 
+int tc_conv_pair_applies(const glis_geom_t* g, int plain_out);
+int tc_conv_pair_ksplit(const glis_geom_t* g);
+int tc_conv_pair_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
+                         __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
+
 int tc_conv_plan_ksplit(const glis_geom_t* g) {
   if (!tc_conv_supported(g)) return 1;
   if (tc_conv_halo_applies(g, 1)) return tc_conv_halo_ksplit(g);   // the kernel that would run
+  if (tc_conv_pair_applies(g, 1)) return tc_conv_pair_ksplit(g);
   TcConvParams P;
   if (tc_plan(g, true, P) != GLIS_OK) return 1;
   return P.ksplit;
@@ -641,6 +588,9 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
     const bool plain = ep->act == GLIS_ACT_NONE && !ep->preact && out_f32 && !out_hi;
     if (tc_conv_halo_applies(g, plain))
       return tc_conv_halo_forward(g, x_hi, x_lo, w_hi, w_lo, ep, out_f32, out_hi, out_lo, precision, st);
+    // >= 256 output channels on maps too narrow for the halo form: CTA pairs (tc_conv_pair.cu)
+    if (tc_conv_pair_applies(g, plain))
+      return tc_conv_pair_forward(g, x_hi, x_lo, w_hi, w_lo, ep, out_f32, out_hi, out_lo, precision, st);
   }
   const int passes = precision == GLIS_PREC_BF16X3 ? 3 : 1;
   GLIS_REQUIRE(x_hi && w_hi && (passes == 1 || (x_lo && w_lo)), GLIS_E_BADARG,

@@ -54,6 +54,12 @@ def main():
             os.environ.pop("GLIS_T2_DEBUG", None)
             os.environ.pop("GLIS_TC_HALO_BK", None)
             os.environ.pop("GLIS_TC_HALO_MINW", None)
+            os.environ.pop("GLIS_TC_PAIR", None)
+            if cl.startswith("p"):      # "p0" / "p1": one-CTA kernels / cta_group::2 pairs where they apply
+                os.environ["GLIS_TC_PAIR"] = cl[1:]
+                os.environ["GLIS_TC_CLUSTER"] = "1"
+                os.environ.pop("GLIS_TC_KSPLIT", None)
+                cl = "P" + cl[1:]
             if cl.startswith("b"):      # "b32" / "b64": halo kernel on every map width with that many channels per stage
                 os.environ["GLIS_TC_HALO_BK"] = cl[1:]
                 os.environ["GLIS_TC_HALO_MINW"] = "1"
@@ -77,6 +83,8 @@ def main():
                 os.environ["GLIS_TC_HALO"] = cl[1:]
                 os.environ["GLIS_TC_CLUSTER"] = "1"
                 os.environ.pop("GLIS_TC_KSPLIT", None)
+            elif cl.startswith("P"):
+                pass
             elif cl.startswith("k"):      # "k1", "k8": upper bound on the K split, no cluster
                 os.environ["GLIS_TC_CLUSTER"] = "1"
                 os.environ["GLIS_TC_KSPLIT"] = cl[1:]
