@@ -28,6 +28,8 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int precision, cudaStream_t st);
 int tc_conv_halo_describe(const glis_geom_t* g, int plain_out, int out[20]);
+int tc_conv_halo_applies(const glis_geom_t* g, int plain_out);
+int tc_conv_pair_describe(const glis_geom_t* g, int plain_out, int out[16]);
 int tc_pm_supported(const glis_geom_t* g);
 int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                   const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const glis_epilogue_t* ep, float* out_f32,
@@ -119,6 +121,15 @@ extern "C" int glis_conv_tc_halo_plan(const glis_geom_t* g, int plain_out, int* 
   GLIS_REQUIRE(out20 != nullptr, GLIS_E_BADARG, "glis_conv_tc_halo_plan: NULL output");
   rc = tc_conv_halo_describe(g, plain_out, out20);
   if (rc != GLIS_OK) set_error("glis_conv_tc_halo_plan: the halo kernel does not apply to this geometry");
+  return rc;
+}
+
+extern "C" int glis_conv_tc_pair_plan(const glis_geom_t* g, int plain_out, int* out16) {
+  int rc = validate_geom(g, "glis_conv_tc_pair_plan");
+  if (rc != GLIS_OK) return rc;
+  GLIS_REQUIRE(out16 != nullptr, GLIS_E_BADARG, "glis_conv_tc_pair_plan: NULL output");
+  rc = tc_conv_halo_applies(g, plain_out) ? GLIS_E_UNSUPPORTED : tc_conv_pair_describe(g, plain_out, out16);
+  if (rc != GLIS_OK) set_error("glis_conv_tc_pair_plan: the pair kernel does not take this launch");
   return rc;
 }
 

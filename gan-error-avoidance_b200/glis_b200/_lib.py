@@ -59,6 +59,7 @@ SIGNATURES = {
     "glis_conv_tc_ksplit": [C.POINTER(Geom)],
     "glis_conv_tc_plan": [C.POINTER(Geom), _i, C.POINTER(C.c_int)],
     "glis_conv_tc_halo_plan": [C.POINTER(Geom), _i, C.POINTER(C.c_int)],
+    "glis_conv_tc_pair_plan": [C.POINTER(Geom), _i, C.POINTER(C.c_int)],
     "glis_tprelu_forward_planes_sum": [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "glis_lis_supported": [_i],
     "glis_lis_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],

@@ -208,6 +208,12 @@ int glis_conv_tc_plan(const glis_geom_t* g, int plain_out, int* out15);
  * tap classes + 1000 * channels per stage (64: 128-byte rows / SWIZZLE_128B, 32: 64-byte rows / SWIZZLE_64B)}.  glis_conv_forward_bf16 uses this kernel whenever it applies; glis_conv_tc_plan keeps describing the
  * one-box-per-tap kernel of csrc/tc_conv.cu. */
 int glis_conv_tc_halo_plan(const glis_geom_t* g, int plain_out, int* out20);
+/* The plan of the CTA-PAIR kernel (csrc/tc_conv_pair.cu: tcgen05.mma.cta_group::2, M = 256 output channels across
+ * two CTAs, each staging its 128 weight rows and half of the pixel tile) when a launch of this geometry takes it —
+ * GLIS_TC_PAIR=1, Cout a multiple of 256, Cin a multiple of 64, a map too narrow for the halo kernel — and
+ * GLIS_E_UNSUPPORTED otherwise: out16 = {tw, th, tn, half rows, half images, pixel rows per half, UMMA N, TMEM columns,
+ * 64-channel blocks, K split, pipeline stages, row tiles per image, pixel tiles, channel pairs, tiles, work items}. */
+int glis_conv_tc_pair_plan(const glis_geom_t* g, int plain_out, int* out16);
 
 /* Same contraction as glis_conv_forward on tcgen05: TMA-fed implicit GEMM, accumulators in
  * TMEM, epilogue fused.  x planes [N,Hi,Wi,Ci] bf16, w packs [KH*KW][Co][Ci] bf16.  Outputs

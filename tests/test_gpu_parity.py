@@ -778,6 +778,40 @@ def test_cfg2_layer_at_size(case, precision):
         assert dgrad["groups"] > sms and dgrad["n_mma"] >= 208, dgrad
 
 
+@pytest.mark.parametrize("case", [("conv", 128, 256, 20, 128), ("conv", 256, 512, 10, 128), ("conv", 256, 512, 10, 64),
+                                  ("deconv", 512, 256, 5, 64)], ids=lambda c: "%s_%dto%d_%d_n%d" % c)
+def test_cta_pair_kernel_at_size(case, precision, monkeypatch):
+    """The cta_group::2 form (csrc/tc_conv_pair.cu, GLIS_TC_PAIR=1) on the config-2 layers it takes — >= 256 output
+    channels on 5x5 / 10x10 maps, forward with the fused epilogue and the data gradients with 512 / 256 outputs —
+    against the fp64 oracle at the benchmark's batch: forward 1e-4, gradients 1e-3."""
+    import ctypes as C
+    from glis_b200 import _lib as L, ops
+    if precision != "bf16x3":
+        pytest.skip("tensor-core mode only")
+    monkeypatch.setenv("GLIS_TC_PAIR", "1")
+    _, pmod = _product()
+    kind, ci, co, h, n = case
+    spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
+    if kind == "conv":
+        g = spec.geom(L.CONV, n, h, h, ci, h // 2, h // 2, co)
+    else:
+        g = spec.geom(L.TCONV, n, h, h, ci, 2 * h, 2 * h, co)
+    out = (C.c_int * 16)()
+    assert L.load().glis_conv_tc_pair_plan(C.byref(g), 0, out) == 0, "the pair kernel should take this forward launch"
+    assert out[6] % 16 == 0 and out[6] <= 256 and out[10] >= 2      # UMMA N, pipeline stages
+    gen = torch.Generator().manual_seed(300 + h)
+    layer = "WeightNormalizedConv2d" if kind == "conv" else "WeightNormalizedConvTranspose2d"
+    mk = lambda M: [getattr(M, layer)(ci, co, 4, 2, 1, scale=False, bias=False), M.TPReLU(co)]
+    x = torch.rand(n, ci, h, h, generator=gen) * 2 - 1
+    ref_layers = mk(oracle)
+    ref_net = torch.nn.Sequential(*ref_layers)
+    randomize_params_(ref_net, gen)
+    prod_layers = mk(pmod)
+    copy_params(torch.nn.Sequential(*prod_layers), ref_net)
+    prod_layers = [m.to(DEV) for m in prod_layers]
+    _check_chain(ref_layers, prod_layers, x)
+
+
 def test_persistent_multi_tile_paths_are_covered():
     """The plans of the config-2 launches at the benchmark's batch: at least one fused-epilogue forward and one
     plain-output data gradient run more work items than there are SMs (so test_cfg2_layer_at_size exercises the
