@@ -378,7 +378,8 @@ wn_norm_multi_kernel(const __grid_constant__ WnMultiParams P) {
   if (threadIdx.x == 0) Y.norm[o] = sqrtf(ss * Y.c + 1e-6f);
 }
 
-constexpr int WN_PACK_PER_BLOCK = WN_NT * 8;   // packed elements per block of the multi-tensor pack kernel
+constexpr int WN_PACK_PER_BLOCK = WN_NT * 2;   // packed elements per block of the multi-tensor pack kernel (what is left to it
+                                               // are small layers: short blocks, both of a thread's elements in flight)
 
 __global__ void __launch_bounds__(WN_NT)
 wn_pack_multi_kernel(const __grid_constant__ WnMultiParams P) {

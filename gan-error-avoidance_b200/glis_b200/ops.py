@@ -1527,13 +1527,16 @@ class LISModuleFunction(torch.autograd.Function):
         else:
             da = torch.zeros(code, device=uc.device, dtype=torch.float32)
             db = torch.zeros(code, device=uc.device, dtype=torch.float32)
+        # the second linear's weight gradient needs nothing the chain kernel computes (the saved activation and the
+        # incoming gradient): forked FIRST, it runs beside that kernel instead of behind it — this is the tail of
+        # the generator's backward pass, where every microsecond is exposed
+        _, dw2, _, _ = _layer_backward(ctx.spec2, ctx.pw2, act, doc, None, False, ni[2], False, False, None)
         L.call("glis_lis_backward", L.ptr(doc), L.ptr(ctx.pw2.oi), L.ptr(h), L.ptr(a_raw.detach().contiguous()),
                L.ptr(b_t.detach().contiguous()), L.ptr(ctx.pw1.oi), n, code, L.ptr(dh), L.ptr(du), L.ptr(da),
                L.ptr(db), L.stream())
         if direct:
             _touch_hooks(a_raw, b_t)
             da = db = None
-        _, dw2, _, _ = _layer_backward(ctx.spec2, ctx.pw2, act, doc, None, False, ni[2], False, False, None)
         _, dw1, _, _ = _layer_backward(ctx.spec1, ctx.pw1, uc, dh, None, False, ni[1], False, False, None)
         return (du if ni[0] else None), dw1, dw2, da, db, None, None, None
 
