@@ -60,6 +60,17 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 33 floats 
 
 int validate_geom(const glis_geom_t* g, const char* who);
 
+// Profiling experiments inside the tcgen05 kernels (GLIS_TC_DEBUG / GLIS_T2_DEBUG / GLIS_WG_DEBUG bit masks: no
+// stores, no MMAs, no loads; GLIS_TC_TRACE: a globaltimer log of CTA 0) exist only in an instrumented build
+// (`make EXTRA=-DGLIS_TC_INSTRUMENT`): in the release library the branches below are compile-time dead.
+#ifdef GLIS_TC_INSTRUMENT
+#define TC_DEBUG(P) ((P).debug)
+#define TC_TRACE(P) ((P).trace)
+#else
+#define TC_DEBUG(P) 0
+#define TC_TRACE(P) (static_cast<unsigned long long*>(nullptr))
+#endif
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // A kernel launched through launch_pdl() may start while its predecessor in the stream is still draining: its
 // CTAs are scheduled as the predecessor's exit, run their prologue (barrier init, TMEM allocation, descriptor

@@ -135,13 +135,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
   const int cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   pdl_wait();   // everything above touched shared memory, TMEM and kernel parameters only
-  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1087] = global_timer_ns();
+  if (TC_TRACE(P) && blockIdx.x == 0 && threadIdx.x == 0) TC_TRACE(P)[1087] = global_timer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t box_rows = (uint32_t)(P.tw * P.th * P.tn);
-      const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + ((P.debug & 4) ? 0u : box_rows * 128u));
+      const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (a_bytes + ((TC_DEBUG(P) & 4) ? 0u : box_rows * 128u));
       int s = 0; uint32_t parity = 0;
       int tr_n = 0;
       const uint32_t w_rows = (uint32_t)(P.a_rows / cs), w_slice = w_rows * 128u;   // this CTA's share of the weight tile
@@ -173,12 +173,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
           const int tap = kh * g.KW + kw;
           for (int kb = tl.kb_beg; kb < tl.kb_end; ++kb) {
             mbar_wait(&empty_bar[s], parity ^ 1);
-            if (P.trace && blockIdx.x == 0 && tr_n < 512) P.trace[tr_n++] = global_timer_ns();
+            if (TC_TRACE(P) && blockIdx.x == 0 && tr_n < 512) TC_TRACE(P)[tr_n++] = global_timer_ns();
             uint8_t* st = base + (size_t)s * stage_bytes;
             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
             if (cs == 1) tma_load_3d(st, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0, tap);
             else tma_load_3d_mc(st + crank * w_slice, &map_w_hi, &full_bar[s], kb * TC_BK, tl.co0 + crank * (int)w_rows, tap, cmask);
-            if (P.debug & 4) { /* expect_tx below was reduced accordingly */ }
+            if (TC_DEBUG(P) & 4) { /* expect_tx below was reduced accordingly */ }
             else if (g.relation == GLIS_CONV)
               tma_load_5d(st + 2 * a_bytes, &map_x_hi, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
             else
@@ -186,7 +186,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
             if (P.passes == 3) {
               if (cs == 1) tma_load_3d(st + a_bytes, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0, tap);
               else tma_load_3d_mc(st + a_bytes + crank * w_slice, &map_w_lo, &full_bar[s], kb * TC_BK, tl.co0 + crank * (int)w_rows, tap, cmask);
-              if (P.debug & 4) {}
+              if (TC_DEBUG(P) & 4) {}
               else if (g.relation == GLIS_CONV)
                 tma_load_5d(st + 2 * a_bytes + b_bytes, &map_x_lo, &full_bar[s], cpar + kb * TC_BK, c1, c2, c3, tl.n0);
               else
@@ -216,13 +216,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
         for (int ks = 0; ks < tl.ksteps; ++ks) {
           mbar_wait(&full_bar[s], parity);
           tc_fence_after_sync();
-          if (P.trace && blockIdx.x == 0 && tr_n < 1024) P.trace[tr_n++] = global_timer_ns();
+          if (TC_TRACE(P) && blockIdx.x == 0 && tr_n < 1024) TC_TRACE(P)[tr_n++] = global_timer_ns();
           // descriptors differ only in their 14-bit start-address field: one add per MMA operand
           const uint64_t dah0 = desc0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
           const uint64_t dal0 = dah0 + (a_bytes >> 4);
           const uint64_t dbh0 = dah0 + ((2 * a_bytes) >> 4);
           const uint64_t dbl0 = dbh0 + (b_bytes >> 4);
-          if (!(P.debug & 2)) {
+          if (!(TC_DEBUG(P) & 2)) {
             if (P.passes == 3) {
 #pragma unroll
               for (int kk = 0; kk < TC_BK / 16; ++kk) {  // +2 = 32 bytes = 16 bf16 along K in the swizzled row
@@ -263,7 +263,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       const TcTile tl = tc_tile(P, id);
       if (tl.empty) continue;
       const int co = tl.co0 + q * 32 + lane;
-      const bool ch_ok = co < g.Co && !(P.debug & 1) && !tl.ghost;
+      const bool ch_ok = co < g.Co && !(TC_DEBUG(P) & 1) && !tl.ghost;
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias && tl.split == 0) bias = __ldg(P.bias + co);
@@ -278,10 +278,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       const int valid_cols = P.tn == 1 ? min(P.th, tl.ph.Hq - tl.qy0) * P.tw : min(P.tn, g.N - tl.n0) * P.th * P.tw;
       mbar_wait(&tmem_full_bar[acc], (full_phase >> acc) & 1u);
       tc_fence_after_sync();
-      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) P.trace[tr_e++] = global_timer_ns();
+      if (TC_TRACE(P) && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) TC_TRACE(P)[tr_e++] = global_timer_ns();
       const uint32_t tmem_d = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       // a quarter whose 32 channels are all out of range (Cout <= 64 or 96) has nothing to store
-      const bool quarter_ok = tl.co0 + q * 32 < g.Co && !(P.debug & 1) && !tl.ghost;
+      const bool quarter_ok = tl.co0 + q * 32 < g.Co && !(TC_DEBUG(P) & 1) && !tl.ghost;
       for (int cb = part * 32; cb < cols && quarter_ok; cb += 128) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_d + (uint32_t)cb, v);
@@ -333,7 +333,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_consta
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) P.trace[tr_e++] = global_timer_ns();
+      if (TC_TRACE(P) && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1024 + 64) TC_TRACE(P)[tr_e++] = global_timer_ns();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       full_phase ^= (1u << acc);
       acc ^= 1u;

@@ -185,7 +185,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
   const uint32_t acc_stride = (uint32_t)P.tmem_cols / 2;
   const int n_ctas = (int)gridDim.x;
   pdl_wait();   // everything above touched shared memory, TMEM and kernel parameters only
-  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[1216] = global_timer_ns();
+  if (TC_TRACE(P) && blockIdx.x == 0 && threadIdx.x == 0) TC_TRACE(P)[1216] = global_timer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -197,7 +197,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
       const uint32_t x_tx = planes * (uint32_t)P.box_rows * row_bytes, w_tx = planes * a_bytes;
       int xs = 0, ws = 0; uint32_t xpar = 0, wpar = 0;
       int trw = 0, trx = 1024;
-      const bool tracing = P.trace && blockIdx.x == 0;
+      const bool tracing = TC_TRACE(P) && blockIdx.x == 0;
       for (int item = blockIdx.x; item < P.n_groups; item += n_ctas) {
         const T2Tile tl = t2_tile(P, item);
         if (tl.empty) continue;
@@ -207,7 +207,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
           const T2Class& C = P.cls[tl.cls_beg + (c0 + rot) % tl.cls_n];
           for (int kb = tl.kb_beg; kb < tl.kb_end; ++kb) {
             mbar_wait(&x_empty[xs], xpar ^ 1);
-            if (tracing && trx < 1088) P.trace[trx++] = global_timer_ns();
+            if (tracing && trx < 1088) TC_TRACE(P)[trx++] = global_timer_ns();
             uint8_t* xb = xring + (size_t)xs * x_slot;
             mbar_arrive_expect_tx(&x_full[xs], x_tx);
             if (g.relation == GLIS_CONV) {
@@ -223,7 +223,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
             for (int t = 0; t < C.tap_count; ++t) {
               const int tap = P.taps[C.tap_begin + t].tap;
               mbar_wait(&w_empty[ws], wpar ^ 1);
-              if (tracing && trw < 512) P.trace[trw++] = global_timer_ns();
+              if (tracing && trw < 512) TC_TRACE(P)[trw++] = global_timer_ns();
               uint8_t* wb = wring + (size_t)ws * w_slot;
               mbar_arrive_expect_tx(&w_full[ws], w_tx);
               tma_load_3d(wb, &map_w_hi, &w_full[ws], kb * BK, tl.co0, tap);
@@ -246,7 +246,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
       int xs = 0, ws = 0; uint32_t xpar = 0, wpar = 0;
       uint32_t acc = 0, acc_phase = 0;
       int trw = 512, trx = 1088;
-      const bool tracing = P.trace && blockIdx.x == 0;
+      const bool tracing = TC_TRACE(P) && blockIdx.x == 0;
       for (int item = blockIdx.x; item < P.n_groups; item += n_ctas) {
         const T2Tile tl = t2_tile(P, item);
         if (tl.empty) continue;
@@ -260,20 +260,20 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
           for (int kb = tl.kb_beg; kb < tl.kb_end; ++kb) {
             mbar_wait(&x_full[xs], xpar);
             tc_fence_after_sync();
-            if (tracing && trx < 1152) P.trace[trx++] = global_timer_ns();
+            if (tracing && trx < 1152) TC_TRACE(P)[trx++] = global_timer_ns();
             const uint64_t dxh = desc_x0 + (uint64_t)(((uint32_t)xs * x_slot) >> 4);
             const uint64_t dxl = dxh + (x_plane >> 4);
             for (int t = 0; t < C.tap_count; ++t) {
               uint32_t shift8 = (uint32_t)P.taps[C.tap_begin + t].shift * (row_bytes >> 4);   // rows * row bytes >> 4
-              if (P.debug & 1) shift8 = 0;
-              if (P.debug & 8) shift8 &= ~63u;
+              if (TC_DEBUG(P) & 1) shift8 = 0;
+              if (TC_DEBUG(P) & 8) shift8 &= ~63u;
               mbar_wait(&w_full[ws], wpar);
               tc_fence_after_sync();
-              if (tracing && trw < 1024) P.trace[trw++] = global_timer_ns();
+              if (tracing && trw < 1024) TC_TRACE(P)[trw++] = global_timer_ns();
               const uint64_t dah = desc_w0 + (uint64_t)(((uint32_t)ws * w_slot) >> 4);
               const uint64_t dal = dah + (a_bytes >> 4);
               const uint64_t dbh = dxh + shift8, dbl = dxl + shift8;
-              if (P.debug & 2) {
+              if (TC_DEBUG(P) & 2) {
               } else if (P.passes == 3) {
 #pragma unroll
                 for (int kk = 0; kk < nkk; ++kk) {
@@ -313,7 +313,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
       const T2Tile tl = t2_tile(P, item);
       if (tl.empty) continue;
       const int co = tl.co0 + q * 32 + lane;
-      const bool ch_ok = co < g.Co && !tl.ghost && !(P.debug & 4);
+      const bool ch_ok = co < g.Co && !tl.ghost && !(TC_DEBUG(P) & 4);
       float bias = 0.f, ta = 0.f, tb = 0.f;
       if (ch_ok) {
         if (P.bias && tl.split == 0) bias = __ldg(P.bias + co);
@@ -331,7 +331,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
       const int cols = P.tn == 1 ? (P.th - 1) * P.pw + P.tw : ((P.tn - 1) * P.ph + P.th - 1) * P.pw + P.tw;
       mbar_wait(&tmem_full_bar[acc], (full_phase >> acc) & 1u);
       tc_fence_after_sync();
-      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1216) P.trace[tr_e++] = global_timer_ns();
+      if (TC_TRACE(P) && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1216) TC_TRACE(P)[tr_e++] = global_timer_ns();
       const uint32_t tmem_d = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       const bool quarter_ok = tl.co0 + q * 32 < g.Co && !tl.ghost;
       for (int cb = part * 32; cb < cols && quarter_ok; cb += 128) {
@@ -384,7 +384,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1216) P.trace[tr_e++] = global_timer_ns();
+      if (TC_TRACE(P) && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 1216) TC_TRACE(P)[tr_e++] = global_timer_ns();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       full_phase ^= (1u << acc);
       acc ^= 1u;

@@ -101,7 +101,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
     if (warp == 0) {
       if (lane == 0) {
         const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) *
-                                  (uint32_t)(((P.debug & 8) ? 0 : a_groups) + ((P.debug & 4) ? 0 : b_groups)) *
+                                  (uint32_t)(((TC_DEBUG(P) & 8) ? 0 : a_groups) + ((TC_DEBUG(P) & 4) ? 0 : b_groups)) *
                                   (uint32_t)P.rows * 128u;
         const int gpt = P.nb / 64;   // 64-channel groups per tap
         // tap -> (parity, shift) of the fine-grid gather, decoded ONCE: the integer divisions must not
@@ -116,7 +116,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
           bc0[tl] = parx * Cb + b0; bpy[tl] = pary;
           bfy[tl] = (ey - pary) / g.stride_h; bfx[tl] = (ex - parx) / g.stride_w;
         }
-        const int ntl = (P.debug & 4) ? 0 : P.tpc, nag = (P.debug & 8) ? 0 : a_groups;
+        const int ntl = (TC_DEBUG(P) & 4) ? 0 : P.tpc, nag = (TC_DEBUG(P) & 8) ? 0 : a_groups;
         const int npl = P.passes == 3 ? 2 : 1;
         int s = 0; uint32_t parity = 0;
         int tile_h = t_beg % P.tiles_h, tile_n = t_beg / P.tiles_h;
@@ -158,7 +158,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
           const uint64_t dbh0 = dah0 + ((2 * plane_a) >> 4);
           const uint64_t dbl0 = dbh0 + (plane_b >> 4);
           const int nk16 = P.kp / 16;
-          if (P.debug & 2) {
+          if (TC_DEBUG(P) & 2) {
           } else if (P.passes == 3) {
             for (int k16 = 0; k16 < nk16; ++k16) {  // 16 pixel rows of 128 B = 2048 B = 128 descriptor units
               umma_bf16(tmem_base, dah0 + 128 * k16, dbl0 + 128 * k16, idesc, accumulate);
@@ -183,7 +183,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_s_hi, const __grid_const
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool st_ok = a < Ca && !(P.debug & 1);
+      const bool st_ok = a < Ca && !(TC_DEBUG(P) & 1);
       float* row = P.G + (size_t)blockIdx.x * (size_t)P.slab_stride + (size_t)a * Cb * T + tap0;
       const bool slabs = P.slab_stride > 0;
       if (P.tpc == 4) {
