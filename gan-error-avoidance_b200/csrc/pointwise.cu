@@ -142,7 +142,7 @@ tprelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, 
 
 // NHWC fast path (inner == 1, C % 4 == 0, C/4 <= 256): a thread owns four fixed channels and
 // walks rows, so the per-channel sums live in registers and meet global memory once per thread.
-__global__ void __launch_bounds__(PW_NT)
+__global__ void __launch_bounds__(PW_NT, 4)
 tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_raw, const float* __restrict__ b,
                        const float* __restrict__ dout, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
                        __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ da, float* __restrict__ db,
@@ -161,26 +161,42 @@ tprelu_bwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ a_
     const float av[4] = {clamp01(ar.x), clamp01(ar.y), clamp01(ar.z), clamp01(ar.w)};
     const float arv[4] = {ar.x, ar.y, ar.z, ar.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
     float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < rows; r += (int64_t)gridDim.x * rows_per_iter) {
-      const int64_t i4 = r * c4n + cg;
-      const float4 xv = reinterpret_cast<const float4*>(x)[i4];
-      const float4 gv = reinterpret_cast<const float4*>(dout)[i4];
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
-      float d[4];
+    // two row groups per trip, all four loads requested before the first is used: a thread walks only a handful of
+    // rows, so the loop is a chain of memory round trips unless they overlap
+    constexpr int U = 2;
+    const int64_t step = (int64_t)gridDim.x * rows_per_iter;
+    for (int64_t r0 = (int64_t)blockIdx.x * rows_per_iter + rl; r0 < rows; r0 += U * step) {
+      float4 xq[U], gq[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float t = xs[j] - bv[j];
-        const bool neg = !(t > 0.f);
-        d[j] = neg ? av[j] * gs[j] : gs[j];
-        if (neg) { sa[j] = fmaf(gs[j], t, sa[j]); sb[j] += gs[j]; }
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * step;
+        if (r < rows) {
+          xq[u] = reinterpret_cast<const float4*>(x)[r * c4n + cg];
+          gq[u] = reinterpret_cast<const float4*>(dout)[r * c4n + cg];
+        }
       }
-      if (dx) reinterpret_cast<float4*>(dx)[i4] = make_float4(d[0], d[1], d[2], d[3]);
-      if (dx_hi) {
-        __nv_bfloat16 h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sm100::split_bf16(d[j], h[j], l[j]);
-        reinterpret_cast<uint2*>(dx_hi)[i4] = *reinterpret_cast<uint2*>(h);
-        if (dx_lo) reinterpret_cast<uint2*>(dx_lo)[i4] = *reinterpret_cast<uint2*>(l);
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * step;
+        if (r >= rows) break;
+        const int64_t i4 = r * c4n + cg;
+        const float xs[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w}, gs[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t = xs[j] - bv[j];
+          const bool neg = !(t > 0.f);
+          d[j] = neg ? av[j] * gs[j] : gs[j];
+          if (neg) { sa[j] = fmaf(gs[j], t, sa[j]); sb[j] += gs[j]; }
+        }
+        if (dx) reinterpret_cast<float4*>(dx)[i4] = make_float4(d[0], d[1], d[2], d[3]);
+        if (dx_hi) {
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm100::split_bf16(d[j], h[j], l[j]);
+          reinterpret_cast<uint2*>(dx_hi)[i4] = *reinterpret_cast<uint2*>(h);
+          if (dx_lo) reinterpret_cast<uint2*>(dx_lo)[i4] = *reinterpret_cast<uint2*>(l);
+        }
       }
     }
 #pragma unroll
