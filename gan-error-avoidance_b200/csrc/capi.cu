@@ -50,13 +50,14 @@ static int g_pdl = -1;   // -1: not decided yet (GLIS_PDL=1 turns it on; default
 int glis::pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("GLIS_PDL");
-    g_pdl = (e && atoi(e) != 0) ? 1 : 0;
+    g_pdl = e ? atoi(e) : 0;
+    if (g_pdl < 0 || g_pdl > 2) g_pdl = 0;
   }
   return g_pdl;
 }
 extern "C" int glis_set_pdl(int on) {
   const int prev = glis::pdl_enabled();
-  g_pdl = on ? 1 : 0;
+  g_pdl = on < 0 ? 0 : (on > 2 ? 2 : on);
   return prev;
 }
 extern "C" int glis_version(void) { return 100; }

@@ -81,7 +81,17 @@ int validate_geom(const glis_geom_t* g, const char* who);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-int pdl_enabled();   // capi.cu: GLIS_PDL (default on), glis_set_pdl()
+int pdl_enabled();   // capi.cu: GLIS_PDL / glis_set_pdl(): 0 off, 1 small kernels only, 2 every kernel
+
+// Mode 1 gives the attribute to SMALL launches only (at most four blocks per SM, modest shared memory): the losses,
+// heads, LIS and TPReLU kernels that sit on the critical path between the big contractions.  A big persistent
+// kernel scheduled early only parks 200 KB CTAs on SMs the other stream could have used.
+static inline bool pdl_applies(dim3 grid, size_t smem) {
+  const int mode = pdl_enabled();
+  if (mode >= 2) return true;
+  if (mode <= 0) return false;
+  return (size_t)grid.x * grid.y * grid.z <= 148 * 4 && smem <= 100 * 1024;
+}
 
 template <typename... KP, typename... A>
 inline cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
@@ -94,7 +104,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_applies(grid, smem) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
 }
 

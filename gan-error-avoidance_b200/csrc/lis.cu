@@ -225,7 +225,7 @@ static int lis_launch(const LisParams& P, bool backward, cudaStream_t st) {
   attr[0].val.clusterDim.x = P.code / LIS_COLS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1] = pdl_attr();
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_applies(cfg.gridDim, smem) ? 2 : 1;
   cudaError_t e = backward ? cudaLaunchKernelEx(&cfg, lis_chain_kernel<true>, P)
                            : cudaLaunchKernelEx(&cfg, lis_chain_kernel<false>, P);
   GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "glis_lis_%s: launch failed: %s", backward ? "backward" : "forward",

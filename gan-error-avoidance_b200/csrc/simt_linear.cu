@@ -300,7 +300,7 @@ int simt_linear_forward(const glis_geom_t* g, const float* in, const float* wpac
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cs;
   attr[1] = pdl_attr();
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_applies(cfg.gridDim, 0) ? 2 : 1;
   cudaError_t e = cpt == 2
       ? cudaLaunchKernelEx(&cfg, linear_cluster_kernel<2>, in, wpack, M, N, K, *ep, out, kgroups, chunks)
       : cudaLaunchKernelEx(&cfg, linear_cluster_kernel<1>, in, wpack, M, N, K, *ep, out, kgroups, chunks);

@@ -699,7 +699,7 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
   }
   const int n_clusters = P.n_groups < max_clusters[cs] ? P.n_groups : max_clusters[cs];
   cfg.gridDim = dim3(n_clusters * cs);
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_applies(cfg.gridDim, smem) ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_kernel, mw_hi, mw_lo, mx_hi, mx_lo, P);
   GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16: launch failed: %s", cudaGetErrorString(le));
   GLIS_CHECK_LAUNCH("glis_conv_forward_bf16");

@@ -549,7 +549,7 @@ int tc_conv_pair_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const 
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1] = pdl_attr();
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_enabled() >= 2 ? 2 : 1;
   static int max_pairs = 0;
   if (!max_pairs) {
     int nc = 0;

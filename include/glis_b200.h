@@ -82,7 +82,8 @@ typedef struct glis_epilogue {
 const char* glis_last_error(void);
 int glis_version(void);
 
-/* Programmatic dependent launch (process-wide switch, default on; env GLIS_PDL=0 turns it off).  When on, the
+/* Programmatic dependent launch (process-wide mode; env GLIS_PDL): 0 = off, 1 = small launches only (<= 4 blocks per SM:
+ * losses, heads, LIS, TPReLU kernels), 2 = every kernel.  When on, the
  * library's stream-ordered kernels are enqueued with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's
  * CTAs are scheduled while its predecessor in the stream drains, run their prologue and block in
  * `griddepcontrol.wait` until the predecessor has completed — stream semantics are unchanged (no memory access
