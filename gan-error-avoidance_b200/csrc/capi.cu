@@ -46,6 +46,30 @@ using namespace glis;
 
 extern "C" const char* glis_last_error(void) { return g_err; }
 
+static int g_reserved_sms = -1;   // -1: not decided yet (GLIS_RESERVE_SMS, default 0)
+int glis::plan_sms() {
+  static int device_sms = 0;
+  if (!device_sms) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    (void)cudaGetLastError();
+    device_sms = n;
+  }
+  if (g_reserved_sms < 0) {
+    const char* e = getenv("GLIS_RESERVE_SMS");
+    g_reserved_sms = e ? atoi(e) : 0;
+    if (g_reserved_sms < 0) g_reserved_sms = 0;
+  }
+  const int n = device_sms - g_reserved_sms;
+  return n < 8 ? 8 : n;
+}
+extern "C" int glis_set_reserved_sms(int n) {
+  const int prev = g_reserved_sms < 0 ? 0 : g_reserved_sms;
+  g_reserved_sms = n < 0 ? 0 : n;
+  return prev;
+}
+
 static int g_pdl = -1;   // -1: not decided yet (GLIS_PDL=1 turns it on; default off: measured 2.4 % slower in-step)
 int glis::pdl_enabled() {
   if (g_pdl < 0) {

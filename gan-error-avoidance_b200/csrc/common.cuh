@@ -81,6 +81,10 @@ int validate_geom(const glis_geom_t* g, const char* who);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// SMs the launch planners of the persistent kernels fill: the device's count minus a reserve (GLIS_RESERVE_SMS /
+// glis_set_reserved_sms: left free for a communication library's kernels under data parallelism).
+int plan_sms();
+
 int pdl_enabled();   // capi.cu: GLIS_PDL / glis_set_pdl(): 0 off, 1 small kernels only, 2 every kernel
 
 // Mode 1 gives the attribute to SMALL launches only (at most four blocks per SM, modest shared memory): the losses,

@@ -1,0 +1,146 @@
+// Sum all-reduce of one slice of the flat gradient buffer over NVLink peer memory — the gradient exchange of the
+// data-parallel iteration (no reference counterpart: the reference is single-GPU; it replaces the ncclAllReduce calls
+// of glis_b200/dp.py when the gradient buffers live in symmetric memory).
+//
+// Every rank's buffer is mapped into every rank's address space (torch symmetric memory does the allocation and the
+// handle exchange: plumbing).  ONE kernel per rank, "two-shot" in one pass:
+//
+//   barrier A   block b of every rank tells block b of every peer that its rank's gradients are final
+//   reduce      rank r owns the r-th 1/N of the slice; block b of rank r walks its share of it, LOADS the N copies
+//               (its own + N-1 peers' over NVLink), adds them in rank order and STORES the sum into all N buffers
+//   barrier B   ... tells every peer that its sums have landed; a rank's kernel ends when all of its blocks saw that
+//
+// Each element is summed by exactly one rank, in a fixed order, and broadcast: replicas stay bit-identical and the
+// result is run-to-run reproducible.  Per rank the kernel moves (N-1)/N of the slice in and out over NVLink in
+// parallel — 13 MB at 8 ranks ~ 11.5 MB each way — with one launch and no staging copies, where NCCL 2.28 measured
+// 54 us for the same 13 MB at two ranks (243 GB/s of an NVLink that moves 900 GB/s per direction).
+//
+// Flags: a symmetric int32 array, slot [b * N + src] in the destination rank = "block b of rank src reached epoch e";
+// epochs only grow (one per barrier), kept per block in device memory so that CUDA-graph replays continue the count.
+#include "common.cuh"
+
+namespace glis {
+
+constexpr int PA_MAX_RANKS = 8;
+constexpr int PA_NT = 512;
+constexpr int PA_MAX_BLOCKS = 128;
+
+struct PeerParams {
+  float* buf[PA_MAX_RANKS];          // every rank's flat buffer, in this rank's address space
+  uint32_t* flag[PA_MAX_RANKS];      // every rank's flag array
+  uint32_t* epoch;                   // [PA_MAX_BLOCKS] this rank's per-block barrier counter (device memory)
+  int rank, world;
+  long long off, n;                  // slice [off, off + n) in floats; off and n / world are multiples of 4
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// Block b of this rank meets block b of every peer.  Bounded: a rank that never arrives ends in a trap, not a hang.
+__device__ __forceinline__ void peer_barrier(const PeerParams& P, uint32_t e) {
+  __syncthreads();
+  if (threadIdx.x < (unsigned)P.world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(P.flag[peer] + (size_t)blockIdx.x * P.world + P.rank, e);
+    const uint32_t* mine = P.flag[P.rank] + (size_t)blockIdx.x * P.world + peer;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(mine) - e) < 0) {
+      if ((++spins & 0xfff) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (!t0) t0 = t;
+        else if (t - t0 > 5000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(PA_NT)
+peer_allreduce_kernel(const PeerParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = P.epoch[blockIdx.x];
+  __syncthreads();
+  const uint32_t e0 = s_epoch;
+  peer_barrier(P, e0 + 1);                       // every rank's gradients of this slice are final
+  const long long share = P.n / WORLD;           // floats per rank (multiple of 4)
+  const long long q_beg = (P.off + (long long)P.rank * share) >> 2, q_cnt = share >> 2;
+  // U quads per thread and trip, all WORLD * U loads in flight before the first add: a quad costs an NVLink round trip
+  constexpr int U = WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2);
+  const long long stride = (long long)gridDim.x * PA_NT;
+  for (long long q0 = (long long)blockIdx.x * PA_NT + threadIdx.x; q0 < q_cnt; q0 += U * stride) {
+    float4 v[U][WORLD];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < q_cnt) {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) v[u][r] = ld_volatile_f4(P.buf[r] + ((q_beg + q) << 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < q_cnt) {
+        float4 s = v[u][0];
+#pragma unroll
+        for (int r = 1; r < WORLD; ++r) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) *reinterpret_cast<float4*>(P.buf[r] + ((q_beg + q) << 2)) = s;
+      }
+    }
+  }
+  peer_barrier(P, e0 + 2);                       // every rank's sums have landed in this rank's buffer
+  if (threadIdx.x == 0) P.epoch[blockIdx.x] = e0 + 2;
+}
+
+}  // namespace glis
+
+using namespace glis;
+
+extern "C" int glis_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, int64_t offset,
+                                   int64_t count, void* epochs, int blocks, void* stream) {
+  GLIS_REQUIRE(bufs && flags && epochs, GLIS_E_BADARG, "glis_peer_allreduce: NULL pointer");
+  GLIS_REQUIRE(world >= 2 && world <= PA_MAX_RANKS && rank >= 0 && rank < world, GLIS_E_BADARG,
+               "glis_peer_allreduce: rank %d of %d (2..%d ranks)", rank, world, PA_MAX_RANKS);
+  GLIS_REQUIRE(offset >= 0 && count >= 0 && (offset & 3) == 0 && count % (4 * world) == 0, GLIS_E_BADARG,
+               "glis_peer_allreduce: slice [%lld, +%lld) must start at a multiple of 4 floats and hold a multiple of 4 x ranks",
+               (long long)offset, (long long)count);
+  GLIS_REQUIRE(blocks >= 1 && blocks <= PA_MAX_BLOCKS, GLIS_E_BADARG, "glis_peer_allreduce: 1..%d blocks", PA_MAX_BLOCKS);
+  if (count == 0) return GLIS_OK;
+  PeerParams P;
+  for (int r = 0; r < PA_MAX_RANKS; ++r) {
+    P.buf[r] = r < world ? static_cast<float*>(bufs[r]) : nullptr;
+    P.flag[r] = r < world ? static_cast<uint32_t*>(flags[r]) : nullptr;
+    GLIS_REQUIRE(r >= world || (P.buf[r] && P.flag[r]), GLIS_E_BADARG, "glis_peer_allreduce: NULL peer pointer (rank %d)", r);
+  }
+  P.epoch = static_cast<uint32_t*>(epochs);
+  P.rank = rank; P.world = world; P.off = offset; P.n = count;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (world) {
+    case 2: GLIS_LAUNCH(peer_allreduce_kernel<2>, dim3(blocks), dim3(PA_NT), 0, st, P); break;
+    case 4: GLIS_LAUNCH(peer_allreduce_kernel<4>, dim3(blocks), dim3(PA_NT), 0, st, P); break;
+    case 8: GLIS_LAUNCH(peer_allreduce_kernel<8>, dim3(blocks), dim3(PA_NT), 0, st, P); break;
+    default:
+      set_error("glis_peer_allreduce: %d ranks (2, 4 or 8)", world);
+      return GLIS_E_UNSUPPORTED;
+  }
+  GLIS_CHECK_LAUNCH("glis_peer_allreduce");
+  return GLIS_OK;
+}

@@ -431,16 +431,7 @@ int tc_conv_supported(const glis_geom_t* g) {
   return 1;
 }
 
-static int tc_num_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
-  return num_sms;
-}
+static int tc_num_sms() { return plan_sms(); }
 
 // Tile shape, K split and work-item counts of one launch (everything that does not depend on the
 // operand pointers).  `plain_out`: the launch writes fp32 sums only (no activation, pre-activation or

@@ -399,17 +399,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_c
 static int t2_round_up(int a, int b) { return (a + b - 1) / b * b; }
 static int t2_mod(int a, int b) { return ((a % b) + b) % b; }
 
-static int t2_num_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    (void)cudaGetLastError();
-    num_sms = n;
-  }
-  return num_sms;
-}
+static int t2_num_sms() { return plan_sms(); }
 
 // Tap classes of the launch: which taps share a pixel box and where that box sits.  Returns the halo (hx, hy) shared
 // by every class, or -1 when the halo form does not apply (no class with more than one tap, too many taps).

@@ -366,17 +366,7 @@ static int pair_enabled() {
   return e && atoi(e) != 0;
 }
 
-static int pair_num_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    (void)cudaGetLastError();
-    num_sms = n;
-  }
-  return num_sms;
-}
+static int pair_num_sms() { return plan_sms(); }
 
 // Tile shape and K split, or GLIS_E_UNSUPPORTED when the pair form does not apply.
 static int pair_plan(const glis_geom_t* g, bool plain_out, PairParams& P) {

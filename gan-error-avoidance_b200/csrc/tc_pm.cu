@@ -324,13 +324,7 @@ int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bf
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_pm_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = plan_sms();
   const int grid = P.tiles < num_sms ? P.tiles : num_sms;
   cudaError_t le = launch_pdl(tc_pm_kernel, dim3(grid), dim3(PM_THREADS), smem, st, mx_hi, mx_lo, mw_hi, mw_lo, P);
   GLIS_REQUIRE(le == cudaSuccess, GLIS_E_CUDA, "glis_conv_forward_bf16(pixel-major): launch failed: %s", cudaGetErrorString(le));

@@ -324,13 +324,7 @@ static int wg_plan(const glis_geom_t* g, int passes, TcWgradParams& P, int& n_at
   // Split K so that the CTAs fill whole waves of the machine (one CTA per SM: the stages take most of
   // the shared memory): cost = waves x (K tiles per CTA + the fixed prologue / reduction epilogue,
   // worth about EPI tiles); fewer splits also mean fewer reductions into G.
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = plan_sms();
   int epi = 10;
   {
     const char* e = getenv("GLIS_WG_EPI");

@@ -94,6 +94,7 @@ SIGNATURES = {
     "glis_unfold4x4s2_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "glis_fold4x4s2": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "glis_wn_pack_matrix_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "glis_peer_allreduce": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, _i, _i64, _i64, _vp, _i, _vp],
 }
 
 _lib = None
@@ -119,6 +120,8 @@ def load():
     lib.glis_version.argtypes = []
     lib.glis_set_pdl.restype = C.c_int
     lib.glis_set_pdl.argtypes = [C.c_int]
+    lib.glis_set_reserved_sms.restype = C.c_int
+    lib.glis_set_reserved_sms.argtypes = [C.c_int]
     _lib = lib
     return lib
 

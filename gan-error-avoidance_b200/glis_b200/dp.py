@@ -114,6 +114,46 @@ def split_rows(rows, row_elems, chunk_elems, max_parts=8):
     return out
 
 
+class _PeerExchange(object):
+    """State of the peer-memory all-reduce (``glis_peer_allreduce``): a symmetric flag array, this rank's epoch
+    counters, and per adopted flat buffer the ranks' base pointers.  PyTorch's symmetric memory does the allocation
+    and the handle exchange; the kernel is ours."""
+
+    BLOCKS = 64
+
+    def __init__(self, world, group):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self.world, self.group = world, group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.flags = symm_mem.empty(128 * 8, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        handle = symm_mem.rendezvous(self.flags, self.group)
+        self.flag_ptrs = (C.c_void_p * world)(*[int(p) for p in handle.buffer_ptrs])
+        self.epochs = torch.zeros(128, dtype=torch.int32, device=dev)
+        self._keep = [handle]
+        self._L, self._C = L, C
+        torch.cuda.synchronize()
+        dist.barrier(self.group)          # nobody signals a flag array that its owner has not zeroed yet
+
+    def adopt(self, flat):
+        handle = flat.to_symmetric(self.group)
+        self._keep.append(handle)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        return (self._C.c_void_p * self.world)(*[int(p) for p in handle.buffer_ptrs])
+
+    def all_reduce(self, bufs, off, n):
+        """Sum floats [off, off + n) of the adopted buffer across ranks, on the current stream."""
+        L, C = self._L, self._C
+        work = n // (4 * self.world)                      # float4 per rank
+        blocks = max(1, min(self.BLOCKS, (work + 2047) // 2048))
+        L.call("glis_peer_allreduce", bufs, self.flag_ptrs, self.rank, self.world, int(off), int(n),
+               C.c_void_p(self.epochs.data_ptr()), blocks, L.stream())
+
+
 class OverlappedGradSync(object):
     """Bucketed gradient all-reduce launched from a side stream WHILE backward is still running.
 
@@ -134,7 +174,7 @@ class OverlappedGradSync(object):
     def __init__(self, world, bucket_mb=None, group=None, split_mb=None):
         self.world, self.group = world, group
         if bucket_mb is None:
-            bucket_mb = float(os.environ.get("GLIS_DP_BUCKET_MB", "2"))
+            bucket_mb = float(os.environ.get("GLIS_DP_BUCKET_MB", "16"))
         if split_mb is None:
             # 0 = off (default).  Measured on 8 B200 at config 2 (tools/dp_bench.sh): cutting the 13 MB gradient of
             # G's initial linear into 4-6 chunks is SLOWER (2.19 vs 2.12 ms): its kernel takes ~10 us, the exchange
@@ -146,8 +186,20 @@ class OverlappedGradSync(object):
         self.side = torch.cuda.Stream() if torch.cuda.is_available() else None
         self.sets = {}
         self.bytes_reduced = 0
+        # The exchange itself: our own all-reduce over NVLink peer memory (csrc/peer_allreduce.cu) when the gradient
+        # buffers can live in symmetric memory (2, 4 or 8 ranks on one node; GLIS_DP_PEER=0: ncclAllReduce).
+        self.peer = None
+        if (world in (2, 4, 8) and torch.cuda.is_available() and os.environ.get("GLIS_DP_PEER", "1") != "0"
+                and dist.is_initialized() and dist.get_backend(group) == "nccl"):
+            try:
+                self.peer = _PeerExchange(world, group)
+            except Exception as e:       # noqa: BLE001 — no symmetric memory on this system: NCCL carries the exchange
+                import warnings
+                warnings.warn("glis_b200.dp: peer-memory gradient exchange unavailable (%s); using ncclAllReduce" % e)
+                self.peer = None
 
     def register(self, tag, flat):
+        peer_bufs = self.peer.adopt(flat) if self.peer is not None else None
         # units: whole parameters, or the row chunks of a large linear weight
         units, unit_of = [], []          # (start, length); per parameter: its unit indices, in part order
         for idx, (p, off) in enumerate(zip(flat.params, flat.offsets)):
@@ -180,7 +232,7 @@ class OverlappedGradSync(object):
                 owner[u] = b
         st = {"flat": flat, "buckets": buckets, "owner": owner, "unit_of": unit_of,
               "need": [len(m) for _, _, m in plan], "left": [0] * len(buckets), "sent": [False] * len(buckets),
-              "armed": False, "seen": set()}
+              "armed": False, "seen": set(), "peer_bufs": peer_bufs}
         self.sets[tag] = st
         for idx, p in enumerate(flat.params):
             hook = self._make_hook(st, idx)
@@ -222,7 +274,10 @@ class OverlappedGradSync(object):
                 ev.record(other)
                 self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
-            dist.all_reduce(st["flat"].g[off:off + n], op=dist.ReduceOp.SUM, group=self.group)
+            if st["peer_bufs"] is not None:
+                self.peer.all_reduce(st["peer_bufs"], off, n)
+            else:
+                dist.all_reduce(st["flat"].g[off:off + n], op=dist.ReduceOp.SUM, group=self.group)
         st["sent"][b] = True
         self.bytes_reduced += 4 * n
 

@@ -20,7 +20,7 @@ from . import ops
 class FlatParams(object):
     """Re-homes a module's parameters (and their ``.grad``) into contiguous flat buffers."""
 
-    ALIGN = 4  # floats (16 bytes)
+    ALIGN = 32  # floats (128 bytes): 16-byte kernels, and any run of whole parameters splits into 8 ranks x float4
 
     def __init__(self, module):
         self.params = [p for p in module.parameters()]
@@ -47,6 +47,24 @@ class FlatParams(object):
             p.grad = self.g[o:o + n].view(p.shape)
             p._glis_direct_grad = True                      # kernels may add into .grad in place
             p._glis_scratch = self.scratch[o:o + n].view(p.shape) if p.dim() >= 2 else None
+
+    def to_symmetric(self, group):
+        """Re-home the gradient buffer (+ scratch) in symmetric memory — every rank's copy mapped into every rank's
+        address space — so that the gradient exchange can run over NVLink peer loads / stores
+        (``glis_peer_allreduce``).  Collective: every rank of ``group`` calls it, in the same order.  Returns the
+        symmetric-memory handle (``buffer_ptrs``: the ranks' copies)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        new = symm_mem.empty(2 * self.numel, dtype=torch.float32, device=self.p.device)
+        new.copy_(self.gs)
+        handle = symm_mem.rendezvous(new, group)
+        self.gs = new
+        self.g, self.scratch = new[:self.numel], new[self.numel:]
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            p.grad = self.g[o:o + n].view(p.shape)
+            p._glis_direct_grad = True
+            p._glis_scratch = self.scratch[o:o + n].view(p.shape) if p.dim() >= 2 else None
+        return handle
 
     def _scratch_clean(self):
         for p in self.params:

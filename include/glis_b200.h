@@ -91,6 +91,22 @@ int glis_version(void);
  * (PyTorch launches every kernel fully serialised).  Returns the previous setting. */
 int glis_set_pdl(int on);
 
+/* Sum all-reduce of the slice [offset, offset + count) (floats) of a flat buffer that exists once per rank, over
+ * NVLink peer memory: bufs[r] / flags[r] = rank r's buffer / flag array (>= 128 * world int32, zero-initialised) mapped
+ * into THIS process (symmetric memory), epochs = this rank's own 128 int32 counters (zero-initialised).  One kernel
+ * per rank: barrier, each rank sums its 1/world of the slice from all copies in rank order and stores the result into
+ * every copy, barrier (csrc/peer_allreduce.cu).  Every rank must enqueue the same calls in the same order.  offset %
+ * 4 == 0, count % (4 * world) == 0, world in {2, 4, 8}.  Replaces the ncclAllReduce of the gradient exchange
+ * (no reference counterpart: the reference is single-GPU). */
+int glis_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, int64_t offset, int64_t count,
+                        void* epochs, int blocks, void* stream);
+
+/* SMs the launch planners of the persistent tcgen05 kernels leave FREE (process-wide; env GLIS_RESERVE_SMS, default 0):
+ * under data parallelism the communication library's kernels need SMs of their own while 148 one-CTA-per-SM compute
+ * CTAs are resident.  Only the plans change (tile shapes, K splits, grid sizes), never the results.  No reference
+ * counterpart.  Returns the previous setting. */
+int glis_set_reserved_sms(int n);
+
 /* ---- weight normalisation ------------------------------------------------------
  * Replaces `_WeightNormalizedConvNd.weight_norm` (common/modules/WeightNormalizedConv.py:29-38)
  * and `WeightNormalizedLinear.weight_norm` (WeightNormalizedLinear.py:30-31), plus the

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(lib, name), "missing export %s" % name
-    assert declared == set(_lib.SIGNATURES) | {"glis_last_error", "glis_version", "glis_set_pdl"}
+    assert declared == set(_lib.SIGNATURES) | {"glis_last_error", "glis_version", "glis_set_pdl", "glis_set_reserved_sms"}
     assert _lib.load().glis_version() >= 100
 
 
