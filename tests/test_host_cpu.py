@@ -219,3 +219,83 @@ def test_tc_conv_plan_invariants():
                                 (L.TCONV, 64, 20, 128, 64), (L.CONV, 32, 80, 64, 128), (L.TCONV, 32, 40, 128, 64)):
         check(rel, 4, 2, 1, n, h, h, ci, co, True)
         check(rel, 4, 2, 1, n, h, h, ci, co, False)
+
+
+def test_pair_plan_invariants(monkeypatch):
+    """The cta_group::2 planner (host code, no GPU): off unless GLIS_TC_PAIR=1; when it takes a launch the pair's tile
+    splits into two TMA-expressible halves (rows or images), each padded to 8 B rows, UMMA N = 2 x that <= 256, the
+    accumulators fit TMEM twice and at least two stages fit shared memory."""
+    import ctypes as C
+    from glis_b200 import _lib as L, ops
+    lib = L.load()
+    cdiv = lambda a, b: -(-a // b)
+    spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
+    cases = [(L.CONV, 128, 20, 128, 256), (L.CONV, 128, 10, 256, 512), (L.CONV, 64, 10, 256, 512), (L.TCONV, 64, 5, 512, 256),
+             (L.CONV, 7, 10, 64, 256), (L.CONV, 3, 20, 128, 512)]
+    out = (C.c_int * 16)()
+    g0 = spec.geom(L.CONV, 128, 20, 20, 128, 10, 10, 256)
+    monkeypatch.delenv("GLIS_TC_PAIR", raising=False)
+    assert lib.glis_conv_tc_pair_plan(C.byref(g0), 0, out) == -2          # opt-in
+    monkeypatch.setenv("GLIS_TC_PAIR", "1")
+    for rel, n, h, ci, co in cases:
+        for plain in (0, 1):
+            if rel == L.CONV:
+                g = spec.geom(L.CONV, n, h, h, ci, h // 2, h // 2, co)
+                hq, wq, nphase = h // 2, h // 2, 1
+            else:
+                g = spec.geom(L.TCONV, n, h, h, ci, 2 * h, 2 * h, co)
+                hq, wq, nphase = h, h, 4
+            assert lib.glis_conv_tc_pair_plan(C.byref(g), plain, out) == 0, lib.glis_last_error()
+            tw, th, tn, hh, hn, n_half, n_mma, tmem, kblocks, ksplit, stages, tiles_h, tiles_x, pairs, total, groups = list(out)
+            assert tw == wq and ((hn == tn == 1 and 2 * hh == th) or (hh == th == hq and 2 * hn == tn))
+            assert n_half == tw * hh * hn and n_mma % 16 == 0 and n_half <= n_mma // 2 < n_half + 8 and n_mma <= 256
+            assert tmem in (64, 128, 256, 512) and tmem >= 2 * n_mma
+            assert kblocks == ci // 64 and 1 <= ksplit <= min(32, kblocks) and (plain or ksplit == 1)
+            assert 2 <= stages <= 4 and stages * (2 * 128 * 128 + n_mma * 128) <= 219 * 1024
+            assert pairs == co // 256 and tiles_h == cdiv(hq, th) and tiles_x == tiles_h * cdiv(n, tn)
+            assert total == tiles_x * pairs * nphase and groups == total * ksplit
+    # not for < 256 output channels, nor where the halo kernel runs (maps >= 16 wide)
+    assert lib.glis_conv_tc_pair_plan(C.byref(spec.geom(L.CONV, 64, 20, 20, 128, 10, 10, 128)), 0, out) == -2
+    assert lib.glis_conv_tc_pair_plan(C.byref(spec.geom(L.CONV, 64, 80, 80, 64, 40, 40, 256)), 0, out) == -2
+
+
+def test_process_wide_switches_and_reserved_sms():
+    """glis_set_pdl / glis_set_reserved_sms return the previous setting; reserving SMs changes launch plans only."""
+    import ctypes as C
+    from glis_b200 import _lib as L, ops
+    lib = L.load()
+    prev = lib.glis_set_pdl(2)
+    assert lib.glis_set_pdl(1) == 2 and lib.glis_set_pdl(7) == 1 and lib.glis_set_pdl(prev) == 2
+    spec = ops.ContractionSpec(False, (4, 4), (2, 2), (1, 1), (1, 1))
+    g = spec.geom(L.TCONV, 64, 5, 5, 512, 10, 10, 256)            # a split-K data gradient: the split follows the SM count
+    out = (C.c_int * 15)()
+    r0 = lib.glis_set_reserved_sms(0)
+    try:
+        assert lib.glis_conv_tc_plan(C.byref(g), 1, out) == 0
+        full = list(out)
+        assert lib.glis_set_reserved_sms(100) == 0
+        assert lib.glis_conv_tc_plan(C.byref(g), 1, out) == 0
+        small = list(out)
+        assert small[13] <= full[13] and small[:3] != full[:3] or small[6] <= full[6]     # fewer work items / a smaller split
+        assert lib.glis_set_reserved_sms(-5) == 100 and lib.glis_set_reserved_sms(0) == 0
+    finally:
+        lib.glis_set_reserved_sms(r0)
+
+
+def test_peer_allreduce_argument_checks():
+    """glis_peer_allreduce validates before it launches (no GPU needed): rank / world, slice alignment, block count."""
+    import ctypes as C
+    from glis_b200 import _lib as L
+    lib = L.load()
+    two = (C.c_void_p * 2)(C.c_void_p(4096), C.c_void_p(8192))
+    e = C.c_void_p(4096)
+    call = lambda *a: lib.glis_peer_allreduce(*a)
+    assert call(None, two, 0, 2, 0, 64, e, 8, None) == -1
+    assert call(two, two, 2, 2, 0, 64, e, 8, None) == -1 and b"rank" in lib.glis_last_error()
+    assert call(two, two, 0, 9, 0, 72, e, 8, None) == -1
+    assert call(two, two, 0, 2, 2, 64, e, 8, None) == -1 and b"multiple of 4" in lib.glis_last_error()
+    assert call(two, two, 0, 2, 0, 60, e, 8, None) == -1
+    assert call(two, two, 0, 2, 0, 64, e, 0, None) == -1 and call(two, two, 0, 2, 0, 64, e, 1000, None) == -1
+    assert call(two, two, 0, 2, 0, 0, e, 8, None) == 0              # an empty slice is a no-op
+    three = (C.c_void_p * 3)(C.c_void_p(4096), C.c_void_p(8192), C.c_void_p(12288))
+    assert call(three, three, 0, 3, 0, 96, e, 8, None) == -2        # 2, 4 or 8 ranks
