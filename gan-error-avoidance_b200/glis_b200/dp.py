@@ -199,7 +199,13 @@ class OverlappedGradSync(object):
                 self.peer = None
 
     def register(self, tag, flat):
-        peer_bufs = self.peer.adopt(flat) if self.peer is not None else None
+        peer_bufs = None
+        if self.peer is not None:
+            try:
+                peer_bufs = self.peer.adopt(flat)
+            except Exception as e:       # noqa: BLE001 — this buffer stays where it is: ncclAllReduce carries its exchange
+                import warnings
+                warnings.warn("glis_b200.dp: %s gradients not in symmetric memory (%s); using ncclAllReduce" % (tag, e))
         # units: whole parameters, or the row chunks of a large linear weight
         units, unit_of = [], []          # (start, length); per parameter: its unit indices, in part order
         for idx, (p, off) in enumerate(zip(flat.params, flat.offsets)):
