@@ -157,6 +157,9 @@ class _PeerExchange(object):
 class OverlappedGradSync(object):
     """Bucketed gradient all-reduce launched from a side stream WHILE backward is still running.
 
+    The all-reduce of a bucket is ``glis_peer_allreduce`` — our own kernel over NVLink peer memory, the gradient
+    buffers living in symmetric memory (``_PeerExchange``) — on 2, 4 or 8 ranks of one node, ``ncclAllReduce`` otherwise.
+
     One instance serves several flat buffers (``register(tag, flat)``).  Every parameter gets a
     post-accumulate-grad hook; when the last parameter of a bucket has its gradient, the main
     stream records an event, the side stream waits for it and issues that bucket's all-reduce, so

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Time glis_wn_prepare_bf16_perm (norm + bf16 hi/lo packs) per layer of config 2: tiled vs element-wise kernel
-(GLIS_PACK_TILED=0), checking both packs against torch."""
+"""Time glis_wn_prepare_bf16_perm (norm + bf16 hi/lo packs) per layer of config 2: wide-store kernel vs the element-wise
+one (GLIS_PACK_WIDE=0), checking both packs against torch."""
 import os
 import sys
 
