@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -45,6 +49,17 @@ int split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n
 using namespace glis;
 
 extern "C" const char* glis_last_error(void) { return g_err; }
+
+cudaError_t glis::ensure_max_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == kernel && d.second >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.emplace_back(kernel, bytes);
+  return e;
+}
 
 static int g_reserved_sms = -1;   // -1: not decided yet (GLIS_RESERVE_SMS, default 0)
 int glis::plan_sms() {

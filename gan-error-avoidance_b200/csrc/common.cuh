@@ -81,6 +81,10 @@ int validate_geom(const glis_geom_t* g, const char* who);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and process, under a mutex (entry points are
+// re-entrant: two host threads may make a kernel's first launch at the same time).  Returns a cudaError_t.
+cudaError_t ensure_max_dynamic_smem(const void* kernel, int bytes);
+
 // SMs the launch planners of the persistent kernels fill: the device's count minus a reserve (GLIS_RESERVE_SMS /
 // glis_set_reserved_sms: left free for a communication library's kernels under data parallelism).
 int plan_sms();

@@ -211,12 +211,10 @@ static int lis_launch(const LisParams& P, bool backward, cudaStream_t st) {
   cfg.gridDim = dim3(P.code / LIS_COLS, (P.B + LIS_ROWS - 1) / LIS_ROWS, 1);
   cfg.blockDim = dim3(LIS_NT);
   const size_t smem = sizeof(float) * (LIS_ROWS * (LIS_MAX_CODE + 4) + 2 * LIS_MAX_CODE * LIS_COLS + 3 * LIS_ROWS * LIS_COLS);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(lis_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(lis_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e1 = ensure_max_dynamic_smem(reinterpret_cast<const void*>(lis_chain_kernel<true>), (int)smem);
+    cudaError_t e2 = ensure_max_dynamic_smem(reinterpret_cast<const void*>(lis_chain_kernel<false>), (int)smem);
     GLIS_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, GLIS_E_CUDA, "glis_lis: cudaFuncSetAttribute failed");
-    attr_set = true;
   }
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

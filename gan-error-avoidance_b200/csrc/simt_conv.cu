@@ -628,11 +628,7 @@ int simt_conv_forward(const glis_geom_t* g, const float* in, const float* wpack,
     const size_t wsmem = (size_t)g->KH * g->KW * g->Ci * sizeof(float4);
     if (g->Co <= 4 && g->Ci % 32 == 0 && pixels >= 4096 && wsmem <= 96 * 1024 &&
         (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(small_cout_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_set = true;
-      }
+      (void)ensure_max_dynamic_smem(reinterpret_cast<const void*>(small_cout_fwd), 96 * 1024);
       int64_t want = (pixels + SC_NT / 8 - 1) / (SC_NT / 8);
       const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
       if (g->relation == GLIS_TCONV && g->KH == 4 && g->KW == 4 && g->stride_h == 2 && g->stride_w == 2 &&

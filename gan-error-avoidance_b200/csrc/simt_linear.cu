@@ -603,12 +603,9 @@ int linear_wgrad_project(const float* dy, const float* x, const float* w, const 
 #define LP_LAUNCH(PER) do { if (rows == 1) LP_LAUNCH2(PER, 1); else if (rows == 2) LP_LAUNCH2(PER, 2); else LP_LAUNCH2(PER, 4); } while (0)
 #define LP_LAUNCH2(PER, ROWS)                                                                                       \
   do {                                                                                                              \
-    static bool attr_set = false;                                                                                   \
-    if (!attr_set) {                                                                                                \
-      cudaError_t e = cudaFuncSetAttribute(linear_wgrad_project_kernel<PER, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           200 * 1024);                                                             \
+    {                                                                                                               \
+      cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(linear_wgrad_project_kernel<PER, ROWS>), 200 * 1024); \
       GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(linear_wgrad_project): %s", cudaGetErrorString(e)); \
-      attr_set = true;                                                                                              \
     }                                                                                                               \
     GLIS_LAUNCH((linear_wgrad_project_kernel<PER, ROWS>), dim3(blocks), dim3(LP_NT), smem, (cudaStream_t)(st), dy, x, w, scale, norm, dw, dscale, M, Ca, Cb, perm_c, \
                                                                   perm_p, accumulate, rows_per_block, row_begin,   \

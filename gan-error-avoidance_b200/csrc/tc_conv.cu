@@ -663,11 +663,9 @@ int tc_conv_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_
 
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*column offsets*/;
   GLIS_REQUIRE(P.tmem_cols <= 512, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: accumulators exceed TMEM");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_conv_kernel), 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS);

@@ -698,13 +698,10 @@ int tc_conv_halo_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const 
 
   const size_t smem = (size_t)T2_NX * 2 * P.x_rows * 2 * P.bk + (size_t)P.nw * 2 * P.a_rows * 2 * P.bk + 1024 + 256 + 1024 + T2_TAIL;
   GLIS_REQUIRE(P.tmem_cols <= 512 && smem <= 227 * 1024, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: halo tile does not fit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_conv_halo_kernel<64>), 227 * 1024);
+    if (e == cudaSuccess) e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_conv_halo_kernel<32>), 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_halo_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int num_sms = t2_num_sms();
   const int grid = P.n_groups < num_sms ? P.n_groups : num_sms;

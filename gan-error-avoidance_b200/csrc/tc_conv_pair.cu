@@ -524,11 +524,9 @@ int tc_conv_pair_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const 
   const size_t stage_bytes = 2 * 128 * 128 + 2 * (size_t)P.n_half_pad * 128;
   const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*alignment*/ + 256 /*barriers*/ + 2048 /*column tables*/;
   GLIS_REQUIRE(P.tmem_cols <= 512 && smem <= 227 * 1024, GLIS_E_UNSUPPORTED, "glis_conv_forward_bf16: pair tile does not fit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_conv_pair_kernel), 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_conv_pair_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS);

@@ -318,11 +318,9 @@ int tc_pm_forward(const glis_geom_t* g, const __nv_bfloat16* x_hi, const __nv_bf
     if (rc) return rc;
   }
   const size_t smem = fixed + (size_t)stages * stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_pm_kernel), 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_pm_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int num_sms = plan_sms();
   const int grid = P.tiles < num_sms ? P.tiles : num_sms;

@@ -411,11 +411,9 @@ int tc_wgrad(const glis_geom_t* g, const __nv_bfloat16* s_hi, const __nv_bfloat1
     if (rc) return rc;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(tc_wgrad_kernel), 227 * 1024);
     GLIS_REQUIRE(e == cudaSuccess, GLIS_E_CUDA, "cudaFuncSetAttribute(tc_wgrad_kernel): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid(splits, n_atiles * P.n_btiles, T / P.tpc);
   cudaError_t le = launch_pdl(tc_wgrad_kernel, grid, dim3(WG_THREADS), smem, st, ms_hi, ms_lo, mb_hi, mb_lo, P);
