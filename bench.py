@@ -270,7 +270,8 @@ def probe_dominant_kernel(dev):
         traffic, traffic_src = tj.get("tc_conv_kernel_d1_2B_dram_bytes"), tj.get("captured_at")
     return {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "traffic": traffic,
             "traffic_source": traffic_src,
-            "kernel": "tc_conv_kernel  D level-1 conv 64->128, 40x40->20x20, 128 images (M=51200 N=128 K=1024)",
+            "kernel": "tc_conv_halo_kernel<64> (csrc/tc_conv2.cu)  D level-1 conv 64->128, 40x40->20x20, 128 images "
+                      "(M=51200 N=128 K=1024)",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flop / 1e9,
             "mma_passes": passes, "mma_pipe_tflops": passes * flop / (ms * 1e-3) / 1e12,
             "note": "bf16x3 issues 3 MMAs per algorithmic product (fp32-faithful split); "
